@@ -1,0 +1,280 @@
+/*
+ * nbm_b200.h — C ABI of the B200-native neural-bootstrapping (NBM) training step for the
+ * interfacial Poisson problem (drop-in for the hot path behind JAX-DIPS
+ * `trainer.setup -> init_fn -> solve_fn`, jax_dips/solvers/poisson/trainer.py:980-1137).
+ *
+ * The reference has NO native interface for this path: the seam is the pure function
+ * `Trainer.loss(params, points, dx, dy, dz)` differentiated by `jax.value_and_grad`
+ * (trainer.py:786, 826, 893).  These entry points are what an XLA-FFI / ctypes binding of that
+ * seam binds to.  Conventions:
+ *
+ *   - extern "C", plain pointers and sizes only.  Every pointer is a DEVICE pointer unless its
+ *     name ends in `_host`.  The caller owns every buffer; the library allocates nothing that
+ *     outlives a call except the per-device `__constant__` copy of the network parameters.
+ *   - every call only enqueues work on `stream` (no host synchronisation), so a sequence of
+ *     calls is CUDA-graph capturable.  Exception: functions documented as "synchronous".
+ *   - return value: 0 = ok, otherwise an nbm_status; nbm_last_error() gives a message
+ *     (thread-local).
+ *   - all arithmetic is fp32 (the reference runs with jax_enable_x64 = False).
+ *   - grids are z-fastest: index = (i*Ny + j)*Nz + k   (jax_dips/domain/mesh.py:121-153).
+ *
+ * "Lattice": a tensor-product set of sites given by three 1-D coordinate arrays.  The training
+ * grid, its +-d shifted copies (stencil sites) and the rank-local node lattice with halo are all
+ * lattices.  "Site": a position at which u^-/u^+ are needed (discretization.py:426).  "Crossed":
+ * the cell of size d centred on the site has corner level-set values of mixed sign
+ * (geometric_integrations_per_point.py:203-263).
+ */
+#ifndef NBM_B200_H
+#define NBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* nbm_stream_t; /* cudaStream_t */
+
+enum nbm_status {
+    NBM_OK = 0,
+    NBM_ERR_BAD_ARG = 1,      /* null pointer / non-positive size / inconsistent dims */
+    NBM_ERR_UNSUPPORTED = 2,  /* network shape or option outside the kernel contract */
+    NBM_ERR_CUDA = 3,         /* a CUDA runtime call failed; see nbm_last_error() */
+    NBM_ERR_WORKSPACE = 4     /* workspace too small */
+};
+
+const char* nbm_last_error(void);
+int nbm_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Level-set grid (a14).  Replaces interpolate.add_ghost_layer_3d (domain/interpolate.py:762-816)
+ * + multilinear_interpolation (:906-1021) / nonoscillatory_quadratic_interpolation_per_point
+ * (:388-569) + level_set.perturb_level_set_fn (geometry/level_set.py:34-48).
+ * ---------------------------------------------------------------------------------------- */
+enum nbm_interp { NBM_INTERP_TRILINEAR = 0, NBM_INTERP_QUADRATIC = 1 };
+
+typedef struct {
+    const float* phi_g;      /* ghosted level set, (nx+2)*(ny+2)*(nz+2), z fastest */
+    const float* xg;         /* ghosted node coordinates, nx+2 */
+    const float* yg;         /* ny+2 */
+    const float* zg;         /* nz+2 */
+    int gx, gy, gz;          /* ghosted dims = n+2 */
+    int interp;              /* nbm_interp */
+    float perturb_eps;       /* 1e-10 when the level set is wrapped in perturb_level_set_fn, else 0 */
+} nbm_lvl_t;
+
+/* phi (nx,ny,nz) -> phi_g (nx+2,ny+2,nz+2) and x -> xg etc. (linear extrapolation, x then y then z). */
+int nbm_ghost_layer_f32(const float* phi, const float* x, const float* y, const float* z,
+                        int nx, int ny, int nz,
+                        float* phi_g, float* xg, float* yg, float* zg, nbm_stream_t stream);
+
+/* phi at arbitrary points; pts is (n,3) row-major.  out[n]. */
+int nbm_phi_interp_f32(const nbm_lvl_t* lvl, const float* pts, int64_t n, float* out, nbm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Lattices and site classification (a12: is_point_cell_crossed_by_interface,
+ * geometry/geometric_integrations_per_point.py:203-263)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* xs;   /* nx site coordinates */
+    const float* ys;
+    const float* zs;
+    int nx, ny, nz;
+    /* only sites with index inside [lo, hi) per axis are classified; others get flag = 2 */
+    int lo[3], hi[3];
+    /* the lattice is replicated n_shift times (1..7), copy k displaced by shift[k] (fp32 add, as the
+     * reference forms stencil points `point[0] - dx`, discretization.py:348-353).  Site id of
+     * (copy k, node e) = k*nx*ny*nz + e. */
+    int n_shift;
+    float shift[7][3];
+} nbm_lattice_t;
+
+/* flag[e] in {-1, 0 (crossed), +1, 2 (not a site)};  side[e]: bit0 = phi>=0 (MLP.py:98 head
+ * select), bit1 = phi>0 (discretization.py:484 branch select).  side is written for EVERY node. */
+int nbm_classify_f32(const nbm_lvl_t* lvl, const nbm_lattice_t* lat, float dx, float dy, float dz,
+                     int8_t* flag, uint8_t* side, nbm_stream_t stream);
+
+/* Stream compaction of crossed sites (flag == 0): idx_out[0..*count_dev) = ascending site ids,
+ * cidx[site] = position in the list or -1.  idx_out must hold `capacity` entries; count_dev is a
+ * device int64.  Workspace: call with workspace == NULL to get *ws_bytes. */
+int nbm_compact_crossed(const int8_t* flag, int64_t n, int64_t* idx_out, int64_t capacity,
+                        int32_t* cidx, int64_t* count_dev,
+                        void* workspace, size_t* ws_bytes, nbm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1: cut-cell geometry of crossed cells (a10-a13: compute_cell_faces_areas_values :464-1009,
+ * integrate_over_interface_at_point :383-421, get_vertices_of_cell_intersection_with_interface
+ * :201-367, vol_fn/area_fn :370-380)
+ * ---------------------------------------------------------------------------------------- */
+/* For each crossed site c (lattice `lat`, site index idx[c]):
+ *   frac[c*14 + 0..11] = area^- , area^+ for faces (x-,x+,y-,y+,z-,z+) interleaved (m,p)
+ *   frac[c*14 + 12,13] = V^-, V^+
+ *   tri[c*90 + t*9 + v*3 + a] = Gamma triangle t (<=10), vertex v, axis a (unused slots zero)
+ *   tri_area[c*10 + t]
+ */
+int nbm_cutcell_f32(const nbm_lvl_t* lvl, const nbm_lattice_t* lat, float dx, float dy, float dz,
+                    const int64_t* idx, int64_t n_crossed,
+                    float* frac, float* tri, float* tri_area, nbm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2a: regression extrapolation geometry at crossed sites (a9: get_regression_coeffs_at_point,
+ * discretization.py:238-296; normal_point_fn :199-218)
+ *   pos[c*3..]   site position s
+ *   proj[c*3..]  projected point s - phi(s) n          (discretization.py:467)
+ *   delta[c]     phi(s)
+ *   Cm[c*27+q], Cp[c*27+q] = n . D^-/+ column q  (pinv(X^T W X)(W X)^T, jnp.linalg.pinv cutoff)
+ *   cube_side[c] bit q = phi(s + X_q) >= 0
+ * ---------------------------------------------------------------------------------------- */
+int nbm_regression_f32(const nbm_lvl_t* lvl, const nbm_lattice_t* lat, float dx, float dy, float dz,
+                       const int64_t* idx, int64_t n_crossed,
+                       float* pos, float* proj, float* delta, float* Cm, float* Cp,
+                       uint32_t* cube_side, nbm_stream_t stream);
+
+/* K2b: jump-condition weights at crossed sites (a8, discretization.py:464-513).  The value on the
+ * far side of the interface is  E = sum_q B[c*28+q] * u(s + X_q) + B[c*28+27]  (B[13] includes
+ * the centre term).  mu_*_s sampled at s, alpha/beta/mu_*_proj sampled at proj. */
+int nbm_site_weights_f32(int64_t n_crossed, const float* delta, const float* Cm, const float* Cp,
+                         const float* mu_m_s, const float* mu_p_s,
+                         const float* alpha_proj, const float* beta_proj,
+                         const float* mu_m_proj, const float* mu_p_proj,
+                         float* B, nbm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2c: row assembly (a7: compute_Ax_and_b_preconditioned_fn, discretization.py:299-423)
+ * ---------------------------------------------------------------------------------------- */
+enum nbm_nonlinear { NBM_NL_NONE = 0, NBM_NL_SINH = 1 /* N(u) = coef * sinh(u) */ };
+
+typedef struct {
+    /* points: lattice 0; n_points = nx*ny*nz of `pts` */
+    nbm_lattice_t pts;
+    float dx, dy, dz;
+    float bounds[6];                 /* xmin,xmax,ymin,ymax,zmin,zmax of the LVL grid (discretization.py:60-65) */
+    /* site access.  shared = 1: sites are nodes of one lattice `site_dims` and slot k of point
+     * (i,j,k) is node (i+pt_off[0]+e_k ...);  shared = 0: 7 lattices of the points' dims, site id
+     * = k*n_points + p. */
+    int shared;
+    int site_dims[3];
+    int pt_off[3];
+    const int8_t* flag;              /* per site */
+    const uint8_t* side;             /* per site */
+    const int32_t* cidx;             /* per site: crossed index or -1 */
+    const float* frac;               /* per crossed site (only lattice-0 / node entries are read) */
+    const float* beta_gamma;         /* per crossed site: integral_Gamma beta  (host: sum_t area_t*mean beta) */
+    /* coefficient samples, per point */
+    const float* mu_m_faces;         /* [6][n_points]  (x-,x+,y-,y+,z-,z+) at face centres */
+    const float* mu_p_faces;
+    const float* k_m; const float* k_p; const float* f_m; const float* f_p; const float* g_dir;
+    /* outputs */
+    float* w;                        /* [7][n_out]: weight on u(site k) after division by diag */
+    float* rhs;                      /* [n_out] */
+    float* nl;                       /* [2][n_out] V^-/diag, V^+/diag (may be NULL when nonlinear = none) */
+    int32_t* irr;                    /* [n_out] index into the irregular list or -1 */
+    int64_t n_out; int64_t out_stride[3]; int64_t out_off; /* output index = out_off + i*s0 + j*s1 + k*s2 */
+    /* irregular rows (a point with >=1 crossed stencil site) */
+    int64_t irr_capacity;
+    int64_t* irr_count;              /* device counter (zeroed by the caller) */
+    int64_t* irr_point;              /* [cap] output index of the point */
+    float* irr_wE;                   /* [cap][7] weight on E(site k) */
+    int32_t* irr_c;                  /* [cap][7] crossed index of site k or -1 */
+    uint8_t* irr_nl;                 /* [cap] 0: none, 1: N^-(E(centre)), 2: N^+(E(centre)) enters the row */
+    float* irr_nlw;                  /* [cap] its weight V/diag */
+} nbm_assemble_t;
+
+int nbm_assemble_f32(const nbm_assemble_t* a, nbm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3/K4: the training step (a6, a15, a16, a17)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int layers_p, hidden_p, layers_m, hidden_m;  /* model_dict["mlp"], tanh */
+} nbm_net_t;
+
+int nbm_net_num_params(const nbm_net_t* net);
+
+/* copy the flat parameter vector (device) into the per-device __constant__ bank */
+int nbm_upload_params(const nbm_net_t* net, const float* params, nbm_stream_t stream);
+
+typedef struct {
+    nbm_net_t net;
+    int nonlinear_m, nonlinear_p;    /* nbm_nonlinear */
+    float nl_coef_m, nl_coef_p;
+    /* node lattice with halo */
+    const float* xe; const float* ye; const float* ze;
+    int ex, ey, ez;
+    const uint8_t* side;             /* [ex*ey*ez] */
+    /* row tables in lattice layout (zero rows where no training point) */
+    const float* w;                  /* [7][ne] */
+    const float* rhs;                /* [ne] */
+    const float* nl;                 /* [2][ne] or NULL */
+    /* crossed sites */
+    int64_t n_crossed; const int64_t* c_node; const float* B;  /* [nc][28] */
+    /* irregular rows */
+    int64_t n_irr; const int64_t* irr_point; const float* irr_wE; const int32_t* irr_c; const uint8_t* irr_nl; const float* irr_nlw;
+    float inv_n_points;              /* 1 / (number of points the mean runs over) */
+    /* work buffers */
+    float* U; float* R; float* G;    /* [ne] each */
+    float* E; float* gE;             /* [nc] each */
+    float* partials;                 /* [n_partial_rows][P+1] */
+    int n_partial_rows;              /* >= nbm_step_partial_rows() */
+    float* loss_grad;                /* [P+1]: grad[0..P), loss at [P] */
+} nbm_shared_step_t;
+
+int nbm_step_partial_rows(void);
+
+/* loss and d loss/d params for the rows of the plan, network parameters taken from the
+ * __constant__ bank (call nbm_upload_params first).  Native-spacing "shared evaluation" path:
+ * the network is evaluated once per lattice node. */
+int nbm_loss_grad_shared_f32(const nbm_shared_step_t* s, nbm_stream_t stream);
+
+typedef struct {
+    nbm_net_t net;
+    int nonlinear_m, nonlinear_p;
+    float nl_coef_m, nl_coef_p;
+    const float* xs; const float* ys; const float* zs;   /* training-grid coordinates */
+    int nx, ny, nz;
+    int64_t p0, p1;                  /* the batch: flattened point range [p0, p1) */
+    float dx, dy, dz;                /* cell size of this level */
+    const uint8_t* side;             /* [7][n_points] */
+    const float* w;                  /* [7][n_points] */
+    const float* rhs;                /* [n_points] */
+    const float* nl;                 /* [2][n_points] or NULL */
+    const int32_t* irr;              /* [n_points] */
+    int64_t n_crossed; const int64_t* c_site; const float* c_pos; const uint32_t* c_cube_side; const float* B;
+    int64_t n_irr; const float* irr_wE; const int32_t* irr_c; const uint8_t* irr_nl; const float* irr_nlw;
+    float inv_n_points;
+    float* E; float* gE;
+    float* partials; int n_partial_rows;
+    float* loss_grad;
+} nbm_points_step_t;
+
+/* General path (any cell size, any contiguous batch): 7 network evaluations per point, fused
+ * forward + backward, no neighbour sharing. */
+int nbm_loss_grad_points_f32(const nbm_points_step_t* s, nbm_stream_t stream);
+
+/* optax chain of solvers/optimizers.py:33-54 on device: clip_by_global_norm(max_norm) ->
+ * scale_by_adam(b1,b2,eps) -> scale_by_schedule(lr*decay^(count/transition)) -> scale(-1) ->
+ * apply_updates.  state = [m(P), v(P)], count = device int32 step counter.  grad_scale multiplies
+ * the gradient first (1 normally).  loss_hist may be NULL, else loss_hist[count] = loss. */
+typedef struct {
+    int n_params;
+    float lr, decay_rate, transition_steps, max_norm, b1, b2, eps;
+    int optimizer;                   /* 0 = "custom" chain, 1 = plain adam (no clip, constant lr) */
+} nbm_optimizer_t;
+
+int nbm_apply_update_f32(const nbm_optimizer_t* opt, const float* loss_grad, float* params,
+                         float* state, int32_t* count, float* loss_hist, nbm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5: post-training evaluation (trainer.py:960-977): u, grad u (analytic Jacobian of the
+ * selected head), d u / d n with the central-difference normal (discretization.py:199-218).
+ * pts (n,3); outputs u[n], grad_u[n*3], grad_n[n]  (grad_u / grad_n may be NULL)
+ * ---------------------------------------------------------------------------------------- */
+int nbm_evaluate_f32(const nbm_net_t* net, const nbm_lvl_t* lvl, const float* pts, int64_t n,
+                     float dx, float dy, float dz, float* u, float* grad_u, float* grad_n,
+                     nbm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBM_B200_H */

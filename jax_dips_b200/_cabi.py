@@ -1,0 +1,147 @@
+"""ctypes binding of `libnbm_b200.so` (the C ABI declared in include/nbm_b200.h).
+
+This is the only way the Python host reaches the CUDA kernels.  There is no CPU fallback: if the
+library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnbm_b200.so")
+
+c_f = C.c_float
+c_fp = C.c_void_p  # all device pointers travel as void*
+
+
+class NbmError(RuntimeError):
+    pass
+
+
+class Lvl(C.Structure):
+    _fields_ = [("phi_g", c_fp), ("xg", c_fp), ("yg", c_fp), ("zg", c_fp),
+                ("gx", C.c_int), ("gy", C.c_int), ("gz", C.c_int),
+                ("interp", C.c_int), ("perturb_eps", c_f)]
+
+
+class Lattice(C.Structure):
+    _fields_ = [("xs", c_fp), ("ys", c_fp), ("zs", c_fp),
+                ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
+                ("lo", C.c_int * 3), ("hi", C.c_int * 3),
+                ("n_shift", C.c_int), ("shift", (c_f * 3) * 7)]
+
+
+class Assemble(C.Structure):
+    _fields_ = [("pts", Lattice),
+                ("dx", c_f), ("dy", c_f), ("dz", c_f),
+                ("bounds", c_f * 6),
+                ("shared", C.c_int), ("site_dims", C.c_int * 3), ("pt_off", C.c_int * 3),
+                ("flag", c_fp), ("side", c_fp), ("cidx", c_fp), ("frac", c_fp), ("beta_gamma", c_fp),
+                ("mu_m_faces", c_fp), ("mu_p_faces", c_fp),
+                ("k_m", c_fp), ("k_p", c_fp), ("f_m", c_fp), ("f_p", c_fp), ("g_dir", c_fp),
+                ("w", c_fp), ("rhs", c_fp), ("nl", c_fp), ("irr", c_fp),
+                ("n_out", C.c_int64), ("out_stride", C.c_int64 * 3), ("out_off", C.c_int64),
+                ("irr_capacity", C.c_int64), ("irr_count", c_fp), ("irr_point", c_fp),
+                ("irr_wE", c_fp), ("irr_c", c_fp), ("irr_nl", c_fp), ("irr_nlw", c_fp)]
+
+
+class Net(C.Structure):
+    _fields_ = [("layers_p", C.c_int), ("hidden_p", C.c_int), ("layers_m", C.c_int), ("hidden_m", C.c_int)]
+
+
+class SharedStep(C.Structure):
+    _fields_ = [("net", Net),
+                ("nonlinear_m", C.c_int), ("nonlinear_p", C.c_int), ("nl_coef_m", c_f), ("nl_coef_p", c_f),
+                ("xe", c_fp), ("ye", c_fp), ("ze", c_fp),
+                ("ex", C.c_int), ("ey", C.c_int), ("ez", C.c_int),
+                ("side", c_fp), ("w", c_fp), ("rhs", c_fp), ("nl", c_fp),
+                ("n_crossed", C.c_int64), ("c_node", c_fp), ("B", c_fp),
+                ("n_irr", C.c_int64), ("irr_point", c_fp), ("irr_wE", c_fp), ("irr_c", c_fp),
+                ("irr_nl", c_fp), ("irr_nlw", c_fp),
+                ("inv_n_points", c_f),
+                ("U", c_fp), ("R", c_fp), ("G", c_fp), ("E", c_fp), ("gE", c_fp),
+                ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp)]
+
+
+class PointsStep(C.Structure):
+    _fields_ = [("net", Net),
+                ("nonlinear_m", C.c_int), ("nonlinear_p", C.c_int), ("nl_coef_m", c_f), ("nl_coef_p", c_f),
+                ("xs", c_fp), ("ys", c_fp), ("zs", c_fp),
+                ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
+                ("p0", C.c_int64), ("p1", C.c_int64),
+                ("dx", c_f), ("dy", c_f), ("dz", c_f),
+                ("side", c_fp), ("w", c_fp), ("rhs", c_fp), ("nl", c_fp), ("irr", c_fp),
+                ("n_crossed", C.c_int64), ("c_site", c_fp), ("c_pos", c_fp), ("c_cube_side", c_fp), ("B", c_fp),
+                ("n_irr", C.c_int64), ("irr_wE", c_fp), ("irr_c", c_fp), ("irr_nl", c_fp), ("irr_nlw", c_fp),
+                ("inv_n_points", c_f),
+                ("E", c_fp), ("gE", c_fp),
+                ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp)]
+
+
+class Optimizer(C.Structure):
+    _fields_ = [("n_params", C.c_int),
+                ("lr", c_f), ("decay_rate", c_f), ("transition_steps", c_f), ("max_norm", c_f),
+                ("b1", c_f), ("b2", c_f), ("eps", c_f), ("optimizer", C.c_int)]
+
+
+# every symbol include/nbm_b200.h declares: name -> (restype, argtypes)
+_P = C.POINTER
+SYMBOLS = {
+    "nbm_last_error": (C.c_char_p, []),
+    "nbm_version": (C.c_int, []),
+    "nbm_ghost_layer_f32": (C.c_int, [c_fp] * 4 + [C.c_int] * 3 + [c_fp] * 4 + [c_fp]),
+    "nbm_phi_interp_f32": (C.c_int, [_P(Lvl), c_fp, C.c_int64, c_fp, c_fp]),
+    "nbm_classify_f32": (C.c_int, [_P(Lvl), _P(Lattice), c_f, c_f, c_f, c_fp, c_fp, c_fp]),
+    "nbm_compact_crossed": (C.c_int, [c_fp, C.c_int64, c_fp, C.c_int64, c_fp, c_fp, c_fp, _P(C.c_size_t), c_fp]),
+    "nbm_cutcell_f32": (C.c_int, [_P(Lvl), _P(Lattice), c_f, c_f, c_f, c_fp, C.c_int64, c_fp, c_fp, c_fp, c_fp]),
+    "nbm_regression_f32": (C.c_int, [_P(Lvl), _P(Lattice), c_f, c_f, c_f, c_fp, C.c_int64] + [c_fp] * 6 + [c_fp]),
+    "nbm_site_weights_f32": (C.c_int, [C.c_int64] + [c_fp] * 10 + [c_fp]),
+    "nbm_assemble_f32": (C.c_int, [_P(Assemble), c_fp]),
+    "nbm_net_num_params": (C.c_int, [_P(Net)]),
+    "nbm_upload_params": (C.c_int, [_P(Net), c_fp, c_fp]),
+    "nbm_step_partial_rows": (C.c_int, []),
+    "nbm_loss_grad_shared_f32": (C.c_int, [_P(SharedStep), c_fp]),
+    "nbm_loss_grad_points_f32": (C.c_int, [_P(PointsStep), c_fp]),
+    "nbm_apply_update_f32": (C.c_int, [_P(Optimizer), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "nbm_evaluate_f32": (C.c_int, [_P(Net), _P(Lvl), c_fp, C.c_int64, c_f, c_f, c_f, c_fp, c_fp, c_fp, c_fp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the library (once).  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NbmError(
+                f"{LIB_PATH} is missing: build it with `python -m jax_dips_b200.build` "
+                "(the NBM path has no CPU / eager fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the export is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().nbm_last_error().decode("utf-8", "replace")
+        raise NbmError(f"{what or 'nbm call'} failed (status {rc}): {msg}")
+
+
+def ptr(t) -> int:
+    """device pointer of a tensor (None -> NULL)"""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "C ABI needs contiguous buffers"
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,616 @@
+// Per-optimizer-step kernels (K3/K4) and the evaluation kernel (K5).
+//
+// Shared-evaluation path (cell size == grid spacing): the network is evaluated ONCE per node of
+// the rank-local lattice (fwd_nodes), crossed nodes get their far-side value from the 27-point
+// regression table (extrap), every row is a 7-point stencil on U (+ irregular corrections),
+// the adjoint stencil gathers d loss/d U per node, and one fused forward-recompute + backward
+// kernel turns it into per-CTA partial sums of d loss/d theta held in registers.
+//
+// The network parameters live in __constant__ memory so that every FFMA takes its weight as a
+// constant-bank operand (no load, no register).
+#include "nbm_common.cuh"
+
+namespace nbm {
+
+#define NBM_MAXP 1024
+__constant__ float c_P[NBM_MAXP];
+
+constexpr int kThreads = 256;
+
+// tanh(x) = 1 - 2/(exp(2x)+1): 2 MUFU (ex2, rcp) + 3 FP32 ops, abs error ~1.5e-7 (tanh.approx's
+// 2^-11 is not enough for the 1e-5 residual tolerance).  Saturates correctly at +-inf.
+__device__ __forceinline__ float tanh_nbm(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+
+// hk.Linear stack (MLP.py:111-116, 128-139): y = x W + b, W (in,out) row-major, tanh on hidden layers.
+// Flat layout per head: W1(3xH) b1(H) [W(HxH) b(H)]*(L-1) Wout(H) bout(1).
+template <int L, int H>
+struct Mlp {
+    static constexpr int NP = 3 * H + H + (L - 1) * (H * H + H) + H + 1;
+
+    template <int OFF>
+    __device__ __forceinline__ static float forward(float x, float y, float z, float (&a)[L][H]) {
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            float s = c_P[OFF + 3 * H + j];
+            s = fmaf(x, c_P[OFF + j], s);
+            s = fmaf(y, c_P[OFF + H + j], s);
+            s = fmaf(z, c_P[OFF + 2 * H + j], s);
+            a[0][j] = tanh_nbm(s);
+        }
+#pragma unroll
+        for (int l = 1; l < L; ++l) {
+            const int o = OFF + 4 * H + (l - 1) * (H * H + H);
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                float s = c_P[o + H * H + j];
+#pragma unroll
+                for (int i = 0; i < H; ++i) s = fmaf(a[l - 1][i], c_P[o + i * H + j], s);
+                a[l][j] = tanh_nbm(s);
+            }
+        }
+        const int o = OFF + 4 * H + (L - 1) * (H * H + H);
+        float out = c_P[o + H];
+#pragma unroll
+        for (int i = 0; i < H; ++i) out = fmaf(a[L - 1][i], c_P[o + i], out);
+        return out;
+    }
+
+    // acc[OFF..OFF+NP) += g * d u / d theta
+    template <int OFF, int NTOT>
+    __device__ __forceinline__ static void backward(float x, float y, float z, const float (&a)[L][H], float g,
+                                                    float (&acc)[NTOT]) {
+        const int oo = OFF + 4 * H + (L - 1) * (H * H + H);
+        float d[H];
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            acc[oo + i] = fmaf(a[L - 1][i], g, acc[oo + i]);
+            d[i] = c_P[oo + i] * g * fmaf(-a[L - 1][i], a[L - 1][i], 1.0f);
+        }
+        acc[oo + H] += g;
+#pragma unroll
+        for (int l = L - 1; l >= 1; --l) {
+            const int o = OFF + 4 * H + (l - 1) * (H * H + H);
+            float dn[H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) dn[i] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < H; ++j) acc[o + H * H + j] += d[j];
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    acc[o + i * H + j] = fmaf(a[l - 1][i], d[j], acc[o + i * H + j]);
+                    dn[i] = fmaf(c_P[o + i * H + j], d[j], dn[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < H; ++i) d[i] = dn[i] * fmaf(-a[l - 1][i], a[l - 1][i], 1.0f);
+        }
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            acc[OFF + 3 * H + j] += d[j];
+            acc[OFF + j] = fmaf(x, d[j], acc[OFF + j]);
+            acc[OFF + H + j] = fmaf(y, d[j], acc[OFF + H + j]);
+            acc[OFF + 2 * H + j] = fmaf(z, d[j], acc[OFF + 2 * H + j]);
+        }
+    }
+
+    // gradient of the head w.r.t. the position (K5: jax.grad of solution_at_point_fn, trainer.py:953-957)
+    template <int OFF>
+    __device__ __forceinline__ static void input_grad(const float (&a)[L][H], float (&gx)[3]) {
+        const int oo = OFF + 4 * H + (L - 1) * (H * H + H);
+        float d[H];
+#pragma unroll
+        for (int i = 0; i < H; ++i) d[i] = c_P[oo + i] * fmaf(-a[L - 1][i], a[L - 1][i], 1.0f);
+#pragma unroll
+        for (int l = L - 1; l >= 1; --l) {
+            const int o = OFF + 4 * H + (l - 1) * (H * H + H);
+            float dn[H];
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                dn[i] = 0.0f;
+#pragma unroll
+                for (int j = 0; j < H; ++j) dn[i] = fmaf(c_P[o + i * H + j], d[j], dn[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < H; ++i) d[i] = dn[i] * fmaf(-a[l - 1][i], a[l - 1][i], 1.0f);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < H; ++j) s = fmaf(c_P[OFF + c * H + j], d[j], s);
+            gx[c] = s;
+        }
+    }
+};
+
+template <int LP, int HP, int LM, int HM>
+struct Net {
+    using P = Mlp<LP, HP>;
+    using M = Mlp<LM, HM>;
+    static constexpr int NP = P::NP + M::NP;
+
+    // DoubleMLP.__call__ (MLP.py:98): phi >= 0 ? mlp_p : mlp_m
+    __device__ __forceinline__ static float eval(bool plus, float x, float y, float z) {
+        if (plus) {
+            float a[LP][HP];
+            return P::template forward<0>(x, y, z, a);
+        } else {
+            float a[LM][HM];
+            return M::template forward<P::NP>(x, y, z, a);
+        }
+    }
+    __device__ __forceinline__ static void grad(bool plus, float x, float y, float z, float g, float (&acc)[NP]) {
+        if (plus) {
+            float a[LP][HP];
+            P::template forward<0>(x, y, z, a);
+            P::template backward<0, NP>(x, y, z, a, g, acc);
+        } else {
+            float a[LM][HM];
+            M::template forward<P::NP>(x, y, z, a);
+            M::template backward<P::NP, NP>(x, y, z, a, g, acc);
+        }
+    }
+};
+
+// nonlinear operator N(u) and N'(u) (discretization.py:369; examples/biomolecules/coefficients.py:126-131)
+__device__ __forceinline__ float nl_apply(int kind, float coef, float u) {
+    return kind == NBM_NL_SINH ? coef * sinhf(u) : 0.0f;
+}
+__device__ __forceinline__ float nl_deriv(int kind, float coef, float u) {
+    return kind == NBM_NL_SINH ? coef * coshf(u) : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// task decomposition shared by fwd_nodes and node_grad: the (y,z) plane is cut into strips of
+// kThreads consecutive cells (z fastest -> coalesced), x into chunks; a CTA walks tasks with a
+// grid stride, a thread keeps its (y,z) and marches along x.
+// ---------------------------------------------------------------------------------------------
+struct Tasks {
+    int plane, mblocks, xchunk, nxch, total;
+};
+__host__ __device__ inline Tasks make_tasks(int ex, int ey, int ez, int xchunk) {
+    Tasks t;
+    t.plane = ey * ez;
+    t.mblocks = (t.plane + kThreads - 1) / kThreads;
+    t.xchunk = xchunk;
+    t.nxch = (ex + xchunk - 1) / xchunk;
+    t.total = t.mblocks * t.nxch;
+    return t;
+}
+
+// A: U[e] = u(node e)   (evaluate_solution_fn, trainer.py:836-844)
+template <class NET>
+__global__ void __launch_bounds__(kThreads) fwd_nodes_kernel(nbm_shared_step_t s, Tasks T) {
+    for (int task = blockIdx.x; task < T.total; task += gridDim.x) {
+        int mb = task % T.mblocks, xc = task / T.mblocks;
+        int m = mb * kThreads + threadIdx.x;
+        if (m >= T.plane) continue;
+        int iy = m / s.ez, iz = m - iy * s.ez;
+        float y = __ldg(s.ye + iy), z = __ldg(s.ze + iz);
+        int x0 = xc * T.xchunk, x1 = min(s.ex, x0 + T.xchunk);
+        for (int ix = x0; ix < x1; ++ix) {
+            size_t e = (size_t)ix * T.plane + m;
+            float x = __ldg(s.xe + ix);
+            bool plus = (__ldg(s.side + e) & 1) != 0;
+            s.U[e] = NET::eval(plus, x, y, z);
+        }
+    }
+}
+
+// A2: E[c] = sum_q B[c][q] U[node_c + off_q] + B[c][27]   (discretization.py:464-513); clears gE
+__global__ void extrap_kernel(nbm_shared_step_t s) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= s.n_crossed) return;
+    int64_t e = s.c_node[c];
+    const float* B = s.B + c * 28;
+    int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
+    float acc = B[27];
+#pragma unroll
+    for (int q = 0; q < 27; ++q) {
+        int a = q % 3 - 1, b = (q / 3) % 3 - 1, cc = q / 9 - 1;
+        acc = fmaf(B[q], s.U[e + a * sx + b * sy + cc], acc);
+    }
+    s.E[c] = acc;
+    s.gE[c] = 0.0f;
+}
+
+// B: residual rows, 7-point stencil on U (discretization.py:366-379 after division by diag)
+__global__ void __launch_bounds__(kThreads) residual_kernel(nbm_shared_step_t s) {
+    int iz = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    int iy = blockIdx.y + 1;
+    int ix = blockIdx.z + 1;
+    if (iz >= s.ez - 1) return;
+    int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
+    int64_t ne = sx * s.ex;
+    int64_t e = ix * sx + iy * sy + iz;
+    float u0 = s.U[e];
+    float r = s.w[e] * u0;
+    r = fmaf(s.w[1 * ne + e], s.U[e - sx], r);
+    r = fmaf(s.w[2 * ne + e], s.U[e + sx], r);
+    r = fmaf(s.w[3 * ne + e], s.U[e - sy], r);
+    r = fmaf(s.w[4 * ne + e], s.U[e + sy], r);
+    r = fmaf(s.w[5 * ne + e], s.U[e - 1], r);
+    r = fmaf(s.w[6 * ne + e], s.U[e + 1], r);
+    if (s.nl) {
+        r = fmaf(s.nl[e], nl_apply(s.nonlinear_m, s.nl_coef_m, u0), r);
+        r = fmaf(s.nl[ne + e], nl_apply(s.nonlinear_p, s.nl_coef_p, u0), r);
+    }
+    s.R[e] = r - s.rhs[e];
+}
+
+// B2: irregular rows: add the far-side (E) terms
+__global__ void irregular_fwd_kernel(nbm_shared_step_t s) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= s.n_irr) return;
+    float r = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        int32_t c = s.irr_c[q * 7 + k];
+        if (c >= 0) r = fmaf(s.irr_wE[q * 7 + k], s.E[c], r);
+    }
+    uint8_t nlr = s.irr_nl[q];
+    if (nlr) {
+        float Ec = s.E[s.irr_c[q * 7]];
+        r = fmaf(s.irr_nlw[q],
+                 nlr == 1 ? nl_apply(s.nonlinear_m, s.nl_coef_m, Ec) : nl_apply(s.nonlinear_p, s.nl_coef_p, Ec), r);
+    }
+    s.R[s.irr_point[q]] += r;
+}
+
+// C1: G[x] = sum_k w_k[x - off_k] R[x - off_k]  (adjoint of the 7-point rows)
+__global__ void __launch_bounds__(kThreads) adjoint_kernel(nbm_shared_step_t s) {
+    int iz = blockIdx.x * blockDim.x + threadIdx.x;
+    int iy = blockIdx.y;
+    int ix = blockIdx.z;
+    if (iz >= s.ez) return;
+    int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
+    int64_t ne = sx * s.ex;
+    int64_t e = ix * sx + iy * sy + iz;
+    float r0 = s.R[e];
+    float g = s.w[e] * r0;
+    // the point p = x + e_a has x as its "minus a" site (slot 1,3,5); p = x - e_a has x as slot 2,4,6
+    if (ix + 1 < s.ex) g = fmaf(s.w[1 * ne + e + sx], s.R[e + sx], g);
+    if (ix > 0) g = fmaf(s.w[2 * ne + e - sx], s.R[e - sx], g);
+    if (iy + 1 < s.ey) g = fmaf(s.w[3 * ne + e + sy], s.R[e + sy], g);
+    if (iy > 0) g = fmaf(s.w[4 * ne + e - sy], s.R[e - sy], g);
+    if (iz + 1 < s.ez) g = fmaf(s.w[5 * ne + e + 1], s.R[e + 1], g);
+    if (iz > 0) g = fmaf(s.w[6 * ne + e - 1], s.R[e - 1], g);
+    if (s.nl) {
+        float u0 = s.U[e];
+        g = fmaf(s.nl[e] * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0) +
+                     s.nl[ne + e] * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0), r0, g);
+    }
+    s.G[e] = g;
+}
+
+// C0: adjoint of the irregular rows: gE[c] += wE * R[p]
+__global__ void irregular_bwd_kernel(nbm_shared_step_t s) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= s.n_irr) return;
+    float r = s.R[s.irr_point[q]];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        int32_t c = s.irr_c[q * 7 + k];
+        if (c >= 0) atomicAdd(s.gE + c, s.irr_wE[q * 7 + k] * r);
+    }
+    uint8_t nlr = s.irr_nl[q];
+    if (nlr) {
+        int32_t c0 = s.irr_c[q * 7];
+        float Ec = s.E[c0];
+        float d = nlr == 1 ? nl_deriv(s.nonlinear_m, s.nl_coef_m, Ec) : nl_deriv(s.nonlinear_p, s.nl_coef_p, Ec);
+        atomicAdd(s.gE + c0, s.irr_nlw[q] * d * r);
+    }
+}
+
+// C0b: adjoint of the extrapolation: G[node_c + off_q] += B[c][q] gE[c]
+__global__ void extrap_bwd_kernel(nbm_shared_step_t s) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t c = t / 27;
+    int q = (int)(t - c * 27);
+    if (c >= s.n_crossed) return;
+    float g = s.gE[c];
+    if (g == 0.0f) return;
+    int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
+    int a = q % 3 - 1, b = (q / 3) % 3 - 1, cc = q / 9 - 1;
+    atomicAdd(s.G + s.c_node[c] + a * sx + b * sy + cc, s.B[c * 28 + q] * g);
+}
+
+// block-level reduction of per-thread accumulators into partials[blockIdx.x][0..NP] (loss last)
+template <int NP>
+__device__ __forceinline__ void block_reduce_store(float (&acc)[NP], float loss, float* __restrict__ partials) {
+    __shared__ float sm[kThreads / 32][NP + 1];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[warp][i] = v;
+    }
+    {
+        float v = loss;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[warp][NP] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NP + 1; i += kThreads) {
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) v += sm[w][i];
+        partials[(size_t)blockIdx.x * (NP + 1) + i] = v;
+    }
+}
+
+// C2: d loss/d theta = sum_nodes (G/n) d u(node)/d theta, loss = sum_rows 0.5 R^2 / n
+// (value_and_grad(self.loss), trainer.py:786; mean of optax.l2_loss, :899-901)
+template <class NET>
+__global__ void __launch_bounds__(kThreads, 1) node_grad_kernel(nbm_shared_step_t s, Tasks T) {
+    float acc[NET::NP];
+#pragma unroll
+    for (int i = 0; i < NET::NP; ++i) acc[i] = 0.0f;
+    float loss = 0.0f;
+    for (int task = blockIdx.x; task < T.total; task += gridDim.x) {
+        int mb = task % T.mblocks, xc = task / T.mblocks;
+        int m = mb * kThreads + threadIdx.x;
+        if (m >= T.plane) continue;
+        int iy = m / s.ez, iz = m - iy * s.ez;
+        float y = __ldg(s.ye + iy), z = __ldg(s.ze + iz);
+        int x0 = xc * T.xchunk, x1 = min(s.ex, x0 + T.xchunk);
+        for (int ix = x0; ix < x1; ++ix) {
+            size_t e = (size_t)ix * T.plane + m;
+            float g = s.G[e] * s.inv_n_points;
+            float r = s.R[e];
+            loss = fmaf(0.5f * r, r, loss);
+            if (g != 0.0f) {
+                float x = __ldg(s.xe + ix);
+                bool plus = (__ldg(s.side + e) & 1) != 0;
+                NET::grad(plus, x, y, z, g, acc);
+            }
+        }
+    }
+    loss *= s.inv_n_points;
+    block_reduce_store<NET::NP>(acc, loss, s.partials);
+}
+
+// K4a: deterministic sum of the per-CTA partial rows
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int rows, int np1, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np1) return;
+    float v = 0.0f;
+    for (int r = 0; r < rows; ++r) v += partials[(size_t)r * np1 + i];
+    out[i] = v;
+}
+
+// K4b: optax chain (solvers/optimizers.py:33-54, optax 0.1.5 semantics), one CTA
+__global__ void apply_update_kernel(nbm_optimizer_t o, const float* __restrict__ loss_grad, float* __restrict__ params,
+                                    float* __restrict__ state, int32_t* __restrict__ count,
+                                    float* __restrict__ loss_hist) {
+    __shared__ float red[32];
+    __shared__ float s_scale;
+    int P = o.n_params;
+    float ss = 0.0f;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) ss = fmaf(loss_grad[i], loss_grad[i], ss);
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        float gn = sqrtf(t);
+        // clip_by_global_norm: g if norm < max_norm else g / norm * max_norm
+        s_scale = (o.optimizer == 0 && !(gn < o.max_norm)) ? (o.max_norm / gn) : 1.0f;
+    }
+    __syncthreads();
+    int t_prev = *count;
+    float t = (float)(t_prev + 1);
+    float bc1 = 1.0f - powf(o.b1, t), bc2 = 1.0f - powf(o.b2, t);
+    float step = o.optimizer == 0 ? o.lr * powf(o.decay_rate, (float)t_prev / o.transition_steps) : o.lr;
+    float* m = state;
+    float* v = state + P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        float g = loss_grad[i] * s_scale;
+        float mi = (1.0f - o.b1) * g + o.b1 * m[i];
+        float vi = (1.0f - o.b2) * (g * g) + o.b2 * v[i];
+        m[i] = mi;
+        v[i] = vi;
+        float upd = (mi / bc1) / (sqrtf(vi / bc2) + o.eps);
+        params[i] += -1.0f * (step * upd);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (loss_hist) loss_hist[t_prev] = loss_grad[P];
+        *count = t_prev + 1;
+    }
+}
+
+// K5: evaluation (trainer.py:960-977)
+template <class NET, int LP, int HP, int LM, int HM>
+__global__ void evaluate_kernel(nbm_lvl_t L, const float* __restrict__ pts, int64_t n, float dx, float dy, float dz,
+                                float* __restrict__ u, float* __restrict__ grad_u, float* __restrict__ grad_n) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float x = pts[3 * e], y = pts[3 * e + 1], z = pts[3 * e + 2];
+    float ph = phi_at(L, x, y, z);
+    float gx[3], val;
+    if (ph >= 0.0f) {
+        float a[LP][HP];
+        val = Mlp<LP, HP>::template forward<0>(x, y, z, a);
+        Mlp<LP, HP>::template input_grad<0>(a, gx);
+    } else {
+        float a[LM][HM];
+        val = Mlp<LM, HM>::template forward<Mlp<LP, HP>::NP>(x, y, z, a);
+        Mlp<LM, HM>::template input_grad<Mlp<LP, HP>::NP>(a, gx);
+    }
+    u[e] = val;
+    if (grad_u) { grad_u[3 * e] = gx[0]; grad_u[3 * e + 1] = gx[1]; grad_u[3 * e + 2] = gx[2]; }
+    if (grad_n) {
+        float px = (phi_at(L, x + dx, y, z) - phi_at(L, x - dx, y, z)) / (2.0f * dx);
+        float py = (phi_at(L, x, y + dy, z) - phi_at(L, x, y - dy, z)) / (2.0f * dy);
+        float pz = (phi_at(L, x, y, z + dz) - phi_at(L, x, y, z - dz)) / (2.0f * dz);
+        float nrm = sqrtf(px * px + py * py + pz * pz);
+        grad_n[e] = (px / nrm) * gx[0] + (py / nrm) * gx[1] + (pz / nrm) * gx[2];
+    }
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+constexpr int kPartialRows = 148 * 2;  // upper bound on the node_grad grid
+
+template <class NET>
+static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
+    const int sms = sm_count();
+    Tasks T = make_tasks(s.ex, s.ey, s.ez, 16);
+    // A
+    int gridA = min(T.total, sms * 4);
+    fwd_nodes_kernel<NET><<<gridA, kThreads, 0, st>>>(s, T);
+    // A2
+    if (s.n_crossed > 0) extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
+    // B
+    {
+        dim3 g((s.ez - 2 + kThreads - 1) / kThreads, s.ey - 2, s.ex - 2);
+        residual_kernel<<<g, kThreads, 0, st>>>(s);
+    }
+    if (s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
+    // C1
+    {
+        dim3 g((s.ez + kThreads - 1) / kThreads, s.ey, s.ex);
+        adjoint_kernel<<<g, kThreads, 0, st>>>(s);
+    }
+    if (s.n_irr > 0) irregular_bwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
+    if (s.n_crossed > 0) extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, st>>>(s);
+    // C2
+    int gridC = min(T.total, min(kPartialRows, sms));
+    if (gridC > s.n_partial_rows) gridC = s.n_partial_rows;
+    node_grad_kernel<NET><<<gridC, kThreads, 0, st>>>(s, T);
+    reduce_partials_kernel<<<(NET::NP + 1 + 127) / 128, 128, 0, st>>>(s.partials, gridC, NET::NP + 1, s.loss_grad);
+    return cuda_check(cudaGetLastError(), "shared step launch");
+}
+
+#define NBM_NET_DISPATCH(net, FN, ...)                                                                       \
+    do {                                                                                                     \
+        const nbm_net_t& _n = (net);                                                                         \
+        if (_n.layers_p == 2 && _n.hidden_p == 10 && _n.layers_m == 1 && _n.hidden_m == 1)                   \
+            return FN<Net<2, 10, 1, 1>>(__VA_ARGS__);                                                        \
+        if (_n.layers_p == 2 && _n.hidden_p == 10 && _n.layers_m == 1 && _n.hidden_m == 3)                   \
+            return FN<Net<2, 10, 1, 3>>(__VA_ARGS__);                                                        \
+        if (_n.layers_p == 1 && _n.hidden_p == 10 && _n.layers_m == 1 && _n.hidden_m == 1)                   \
+            return FN<Net<1, 10, 1, 1>>(__VA_ARGS__);                                                        \
+        if (_n.layers_p == 3 && _n.hidden_p == 10 && _n.layers_m == 1 && _n.hidden_m == 1)                   \
+            return FN<Net<3, 10, 1, 1>>(__VA_ARGS__);                                                        \
+        set_error("network shape p(%d x %d) m(%d x %d) is outside the compiled kernel set", _n.layers_p,     \
+                  _n.hidden_p, _n.layers_m, _n.hidden_m);                                                    \
+        return NBM_ERR_UNSUPPORTED;                                                                          \
+    } while (0)
+
+static int dispatch_shared(const nbm_shared_step_t& s, cudaStream_t st) { NBM_NET_DISPATCH(s.net, launch_shared, s, st); }
+
+template <int LP, int HP, int LM, int HM>
+static int launch_eval_impl(const nbm_lvl_t& L, const float* pts, int64_t n, float dx, float dy, float dz, float* u,
+                            float* grad_u, float* grad_n, cudaStream_t st) {
+    evaluate_kernel<Net<LP, HP, LM, HM>, LP, HP, LM, HM>
+        <<<(unsigned)((n + 127) / 128), 128, 0, st>>>(L, pts, n, dx, dy, dz, u, grad_u, grad_n);
+    return cuda_check(cudaGetLastError(), "evaluate launch");
+}
+
+static int net_num_params(const nbm_net_t& n) {
+    auto cnt = [](int L, int H) { return 3 * H + H + (L - 1) * (H * H + H) + H + 1; };
+    return cnt(n.layers_p, n.hidden_p) + cnt(n.layers_m, n.hidden_m);
+}
+
+}  // namespace nbm
+
+using namespace nbm;
+
+extern "C" {
+
+int nbm_net_num_params(const nbm_net_t* net) {
+    if (!net || net->layers_p < 1 || net->layers_m < 1 || net->hidden_p < 1 || net->hidden_m < 1) return -1;
+    return net_num_params(*net);
+}
+
+int nbm_upload_params(const nbm_net_t* net, const float* params, nbm_stream_t stream) {
+    NBM_REQUIRE(net && params, "null pointer");
+    int P = nbm_net_num_params(net);
+    if (P <= 0 || P > NBM_MAXP) {
+        set_error("parameter count %d outside (0, %d]", P, NBM_MAXP);
+        return NBM_ERR_UNSUPPORTED;
+    }
+    return cuda_check(
+        cudaMemcpyToSymbolAsync(c_P, params, sizeof(float) * P, 0, cudaMemcpyDeviceToDevice, as_stream(stream)),
+        "upload params");
+}
+
+int nbm_step_partial_rows(void) { return kPartialRows; }
+
+int nbm_loss_grad_shared_f32(const nbm_shared_step_t* s, nbm_stream_t stream) {
+    NBM_REQUIRE(s, "null plan");
+    NBM_REQUIRE(s->xe && s->ye && s->ze && s->side && s->w && s->rhs, "null tables");
+    NBM_REQUIRE(s->ex >= 3 && s->ey >= 3 && s->ez >= 3, "lattice too small");
+    NBM_REQUIRE(s->U && s->R && s->G && s->partials && s->loss_grad, "null work buffers");
+    NBM_REQUIRE(s->n_partial_rows >= 1, "n_partial_rows must be >= 1");
+    NBM_REQUIRE(s->n_crossed == 0 || (s->c_node && s->B && s->E && s->gE), "null crossed-site tables");
+    NBM_REQUIRE(s->n_irr == 0 || (s->irr_point && s->irr_wE && s->irr_c && s->irr_nl && s->irr_nlw),
+                "null irregular-row tables");
+    NBM_REQUIRE((s->nonlinear_m == NBM_NL_NONE && s->nonlinear_p == NBM_NL_NONE) || s->nl,
+                "nonlinear operator needs the nl table");
+    return dispatch_shared(*s, as_stream(stream));
+}
+
+int nbm_loss_grad_points_f32(const nbm_points_step_t* s, nbm_stream_t stream) {
+    (void)s; (void)stream;
+    set_error("general per-point path not built yet");
+    return NBM_ERR_UNSUPPORTED;
+}
+
+int nbm_apply_update_f32(const nbm_optimizer_t* opt, const float* loss_grad, float* params, float* state,
+                         int32_t* count, float* loss_hist, nbm_stream_t stream) {
+    NBM_REQUIRE(opt && loss_grad && params && state && count, "null pointer");
+    NBM_REQUIRE(opt->n_params > 0 && opt->n_params <= NBM_MAXP, "bad parameter count");
+    if (opt->optimizer != 0 && opt->optimizer != 1) {
+        set_error("unknown optimizer id %d", opt->optimizer);
+        return NBM_ERR_UNSUPPORTED;
+    }
+    apply_update_kernel<<<1, 256, 0, as_stream(stream)>>>(*opt, loss_grad, params, state, count, loss_hist);
+    NBM_LAUNCH_CHECK("apply_update");
+    return NBM_OK;
+}
+
+int nbm_evaluate_f32(const nbm_net_t* net, const nbm_lvl_t* lvl, const float* pts, int64_t n, float dx, float dy,
+                     float dz, float* u, float* grad_u, float* grad_n, nbm_stream_t stream) {
+    NBM_REQUIRE(net && lvl && lvl->phi_g && lvl->xg && lvl->yg && lvl->zg, "null pointer");
+    NBM_REQUIRE(n >= 0, "negative n");
+    if (n == 0) return NBM_OK;
+    NBM_REQUIRE(pts && u, "null pointer");
+    cudaStream_t st = as_stream(stream);
+    const nbm_net_t& q = *net;
+    if (q.layers_p == 2 && q.hidden_p == 10 && q.layers_m == 1 && q.hidden_m == 1)
+        return launch_eval_impl<2, 10, 1, 1>(*lvl, pts, n, dx, dy, dz, u, grad_u, grad_n, st);
+    if (q.layers_p == 2 && q.hidden_p == 10 && q.layers_m == 1 && q.hidden_m == 3)
+        return launch_eval_impl<2, 10, 1, 3>(*lvl, pts, n, dx, dy, dz, u, grad_u, grad_n, st);
+    if (q.layers_p == 1 && q.hidden_p == 10 && q.layers_m == 1 && q.hidden_m == 1)
+        return launch_eval_impl<1, 10, 1, 1>(*lvl, pts, n, dx, dy, dz, u, grad_u, grad_n, st);
+    if (q.layers_p == 3 && q.hidden_p == 10 && q.layers_m == 1 && q.hidden_m == 1)
+        return launch_eval_impl<3, 10, 1, 1>(*lvl, pts, n, dx, dy, dz, u, grad_u, grad_n, st);
+    set_error("network shape p(%d x %d) m(%d x %d) is outside the compiled kernel set", q.layers_p, q.hidden_p,
+              q.layers_m, q.hidden_m);
+    return NBM_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,379 @@
+"""Per-level, parameter-free set-up of the NBM step (host orchestration of K1/K2 over the C ABI).
+
+Everything the reference recomputes for every point at every optimizer step although it does not
+depend on the network parameters (crossing flags, cut-cell fractions, regression weights, face
+coefficients; discretization.py:337-408) is computed here ONCE per (grid, cell size) and stored in
+HBM as the row tables the step kernels stream.
+
+User coefficient callables cannot run inside a CUDA kernel: the kernels emit the positions they
+need (face centres, Gamma-triangle vertices, projected points), the host evaluates the batched
+callables there with torch on the device, and K2 consumes the sample arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional, Sequence
+
+import torch
+
+from . import _cabi as cabi
+
+NL_NONE, NL_SINH = 0, 1
+INTERP = {"trilinear": 0, "quadratic": 1}
+
+
+class Nonlinear:
+    """N(u) = coef*sinh(u) (examples/biomolecules/coefficients.py:126-131) or nothing.  The
+    reference takes an arbitrary callable (discretization.py:369); a CUDA kernel cannot, so the
+    operator is named.  `Nonlinear.sinh(c)` objects are also callable so that the same object can be
+    handed to code that wants the reference's callable form."""
+
+    def __init__(self, kind: int = NL_NONE, coef: float = 0.0):
+        self.kind, self.coef = kind, float(coef)
+
+    @staticmethod
+    def sinh(coef: float) -> "Nonlinear":
+        return Nonlinear(NL_SINH, coef)
+
+    def __call__(self, u):
+        if self.kind == NL_NONE:
+            return 0.0 * u
+        return self.coef * torch.sinh(u)
+
+    @staticmethod
+    def coerce(op) -> "Nonlinear":
+        if op is None:
+            return Nonlinear()
+        if isinstance(op, Nonlinear):
+            return op
+        # a plain callable: accept it only if it is identically zero (the reference default,
+        # trainer.py:1007-1017); anything else is outside the kernel contract.
+        probe = torch.linspace(-1.0, 1.0, 5)
+        val = op(probe)
+        val = val if isinstance(val, torch.Tensor) else torch.as_tensor(val, dtype=torch.float32)
+        if bool((val == 0).all()):
+            return Nonlinear()
+        raise NotImplementedError(
+            "nonlinear_op must be None, identically zero, or jax_dips_b200.Nonlinear.sinh(coef): "
+            "arbitrary callables cannot be evaluated inside the CUDA step kernels")
+
+
+class NetShape:
+    """model_dict["mlp"] (trainer.py:116-123): tanh heads u^+ (p) and u^- (m)."""
+
+    def __init__(self, layers_p=2, hidden_p=10, layers_m=1, hidden_m=1):
+        self.layers_p, self.hidden_p, self.layers_m, self.hidden_m = layers_p, hidden_p, layers_m, hidden_m
+
+    @staticmethod
+    def from_model_dict(model_dict: dict) -> "NetShape":
+        mt = model_dict.get("model_type", "mlp")
+        if mt != "mlp":
+            raise NotImplementedError(f"model_type {mt!r}: only the compact tanh 'mlp' surrogate is on this path")
+        m = model_dict["mlp"]
+        for k in ("activation_m", "activation_p"):
+            if m.get(k, "jnp.tanh") not in ("jnp.tanh", "nn.tanh", "tanh"):
+                raise NotImplementedError(f"{k}={m[k]!r}: the kernels implement tanh")
+        return NetShape(m["hidden_layers_p"], m["hidden_dim_p"], m["hidden_layers_m"], m["hidden_dim_m"])
+
+    def struct(self) -> cabi.Net:
+        return cabi.Net(self.layers_p, self.hidden_p, self.layers_m, self.hidden_m)
+
+    @staticmethod
+    def _count(L, H):
+        return 3 * H + H + (L - 1) * (H * H + H) + H + 1
+
+    @property
+    def n_p(self): return self._count(self.layers_p, self.hidden_p)
+    @property
+    def n_m(self): return self._count(self.layers_m, self.hidden_m)
+    @property
+    def n_params(self): return self.n_p + self.n_m
+
+
+class LevelSet:
+    """phi on `lvl_gstate` + the reference's interpolant, evaluated inside the kernels
+    (interpolate.py:906-1021 trilinear, :388-569 non-oscillatory quadratic; level_set.py:34-48)."""
+
+    def __init__(self, lvl_gstate, phi_values: torch.Tensor, interp: str = "trilinear",
+                 perturb_eps: float = 1e-10, device=None):
+        if interp not in INTERP:
+            raise ValueError(f"unknown level-set interpolant {interp!r}")
+        self.device = torch.device(device if device is not None else "cuda")
+        nx, ny, nz = lvl_gstate.shape()
+        phi = phi_values.to(self.device, torch.float32).contiguous().reshape(-1)
+        if phi.numel() != nx * ny * nz:
+            raise ValueError("phi_values does not match lvl_gstate")
+        x, y, z = (a.to(self.device) for a in (lvl_gstate.x, lvl_gstate.y, lvl_gstate.z))
+        self.phi_g = torch.empty((nx + 2) * (ny + 2) * (nz + 2), dtype=torch.float32, device=self.device)
+        self.xg = torch.empty(nx + 2, dtype=torch.float32, device=self.device)
+        self.yg = torch.empty(ny + 2, dtype=torch.float32, device=self.device)
+        self.zg = torch.empty(nz + 2, dtype=torch.float32, device=self.device)
+        L = cabi.lib()
+        with torch.cuda.device(self.device):
+            cabi.check(L.nbm_ghost_layer_f32(cabi.ptr(phi), cabi.ptr(x), cabi.ptr(y), cabi.ptr(z), nx, ny, nz,
+                                             cabi.ptr(self.phi_g), cabi.ptr(self.xg), cabi.ptr(self.yg),
+                                             cabi.ptr(self.zg), cabi.stream_ptr()), "nbm_ghost_layer_f32")
+        self.struct = cabi.Lvl(cabi.ptr(self.phi_g), cabi.ptr(self.xg), cabi.ptr(self.yg), cabi.ptr(self.zg),
+                               nx + 2, ny + 2, nz + 2, INTERP[interp], float(perturb_eps))
+        self.bounds = [float(v) for v in (lvl_gstate.xmin(), lvl_gstate.xmax(), lvl_gstate.ymin(),
+                                          lvl_gstate.ymax(), lvl_gstate.zmin(), lvl_gstate.zmax())]
+
+    def __call__(self, pts: torch.Tensor) -> torch.Tensor:
+        """phi at (n,3) points, on the device, through the CUDA interpolation kernel."""
+        pts = pts.to(self.device, torch.float32).contiguous()
+        out = torch.empty(pts.shape[0], dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            cabi.check(cabi.lib().nbm_phi_interp_f32(C.byref(self.struct), cabi.ptr(pts), pts.shape[0],
+                                                     cabi.ptr(out), cabi.stream_ptr()), "nbm_phi_interp_f32")
+        return out
+
+
+def _lattice(xs, ys, zs, lo=None, hi=None, shifts=None) -> cabi.Lattice:
+    lat = cabi.Lattice()
+    lat.xs, lat.ys, lat.zs = cabi.ptr(xs), cabi.ptr(ys), cabi.ptr(zs)
+    lat.nx, lat.ny, lat.nz = xs.numel(), ys.numel(), zs.numel()
+    lo = lo or (0, 0, 0)
+    hi = hi or (lat.nx, lat.ny, lat.nz)
+    for a in range(3):
+        lat.lo[a], lat.hi[a] = int(lo[a]), int(hi[a])
+    shifts = shifts or [(0.0, 0.0, 0.0)]
+    lat.n_shift = len(shifts)
+    for k, sh in enumerate(shifts):
+        for a in range(3):
+            lat.shift[k][a] = float(sh[a])
+    return lat
+
+
+def _sample(fn: Callable, pts: torch.Tensor) -> torch.Tensor:
+    out = fn(pts)
+    if not isinstance(out, torch.Tensor):
+        out = torch.as_tensor(out, dtype=torch.float32, device=pts.device)
+    out = out.to(device=pts.device, dtype=torch.float32)
+    if out.numel() == 1 and pts.shape[0] != 1:
+        out = out.reshape(1).expand(pts.shape[0])
+    return out.reshape(pts.shape[0]).contiguous()
+
+
+class CrossedSites:
+    """Crossed sites of a lattice: compaction, K1 cut-cell, K2a regression, K2b jump weights."""
+
+    def __init__(self, lvl: LevelSet, lat: cabi.Lattice, n_sites: int, d, fns, dev):
+        L = cabi.lib()
+        st = cabi.stream_ptr()
+        dx, dy, dz = d
+        self.flag = torch.empty(n_sites, dtype=torch.int8, device=dev)
+        self.side = torch.empty(n_sites, dtype=torch.uint8, device=dev)
+        cabi.check(L.nbm_classify_f32(C.byref(lvl.struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.flag),
+                                      cabi.ptr(self.side), st), "nbm_classify_f32")
+        # compaction
+        idx = torch.empty(n_sites, dtype=torch.int64, device=dev)
+        self.cidx = torch.empty(n_sites, dtype=torch.int32, device=dev)
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        ws = C.c_size_t(0)
+        cabi.check(L.nbm_compact_crossed(cabi.ptr(self.flag), n_sites, cabi.ptr(idx), n_sites, cabi.ptr(self.cidx),
+                                         cabi.ptr(count), None, C.byref(ws), st), "nbm_compact_crossed(size)")
+        work = torch.empty(max(int(ws.value), 1), dtype=torch.uint8, device=dev)
+        cabi.check(L.nbm_compact_crossed(cabi.ptr(self.flag), n_sites, cabi.ptr(idx), n_sites, cabi.ptr(self.cidx),
+                                         cabi.ptr(count), cabi.ptr(work), C.byref(ws), st), "nbm_compact_crossed")
+        nc = int(count.item())
+        self.n = nc
+        self.idx = idx[:nc].clone()
+        del idx, work
+        n1 = max(nc, 1)
+        self.frac = torch.zeros(n1 * 14, dtype=torch.float32, device=dev)
+        self.tri = torch.zeros(n1 * 90, dtype=torch.float32, device=dev)
+        self.tri_area = torch.zeros(n1 * 10, dtype=torch.float32, device=dev)
+        self.pos = torch.zeros(n1 * 3, dtype=torch.float32, device=dev)
+        self.proj = torch.zeros(n1 * 3, dtype=torch.float32, device=dev)
+        self.delta = torch.zeros(n1, dtype=torch.float32, device=dev)
+        self.Cm = torch.zeros(n1 * 27, dtype=torch.float32, device=dev)
+        self.Cp = torch.zeros(n1 * 27, dtype=torch.float32, device=dev)
+        self.cube_side = torch.zeros(n1, dtype=torch.int32, device=dev)
+        self.B = torch.zeros(n1 * 28, dtype=torch.float32, device=dev)
+        self.beta_gamma = torch.zeros(n1, dtype=torch.float32, device=dev)
+        if nc == 0:
+            return
+        cabi.check(L.nbm_cutcell_f32(C.byref(lvl.struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.idx), nc,
+                                     cabi.ptr(self.frac), cabi.ptr(self.tri), cabi.ptr(self.tri_area), st),
+                   "nbm_cutcell_f32")
+        cabi.check(L.nbm_regression_f32(C.byref(lvl.struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.idx), nc,
+                                        cabi.ptr(self.pos), cabi.ptr(self.proj), cabi.ptr(self.delta),
+                                        cabi.ptr(self.Cm), cabi.ptr(self.Cp), cabi.ptr(self.cube_side), st),
+                   "nbm_regression_f32")
+        # ---- host samples the user callables at the positions the kernels emitted
+        pos, proj = self.pos.view(nc, 3), self.proj.view(nc, 3)
+        mu_m_s, mu_p_s = _sample(fns.mu_m_fn, pos), _sample(fns.mu_p_fn, pos)
+        alpha_p, beta_p = _sample(fns.alpha_fn, proj), _sample(fns.beta_fn, proj)
+        mu_m_p, mu_p_p = _sample(fns.mu_m_fn, proj), _sample(fns.mu_p_fn, proj)
+        cabi.check(L.nbm_site_weights_f32(nc, cabi.ptr(self.delta), cabi.ptr(self.Cm), cabi.ptr(self.Cp),
+                                          cabi.ptr(mu_m_s), cabi.ptr(mu_p_s), cabi.ptr(alpha_p), cabi.ptr(beta_p),
+                                          cabi.ptr(mu_m_p), cabi.ptr(mu_p_p), cabi.ptr(self.B), st),
+                   "nbm_site_weights_f32")
+        # integral over Gamma of beta (geometric_integrations_per_point.py:385-412): sum_t area_t * mean_v beta
+        area = self.tri_area.view(nc, 10)
+        beta_v = _sample(fns.beta_fn, self.tri.view(nc * 30, 3)).view(nc, 10, 3).mean(dim=2)
+        beta_v = torch.where(area > 0, beta_v, torch.zeros_like(beta_v))  # padded slots carry no area
+        self.beta_gamma = (area * beta_v).sum(dim=1).contiguous()
+        torch.cuda.current_stream().synchronize()  # sample tensors die here
+
+
+class SharedPlan:
+    """Shared-evaluation plan for the x-planes [xa, xb) of the training grid at the native cell size
+    (d == grid spacing): one lattice = slab + 2 halo planes in x, 1 halo layer in y and z."""
+
+    HX, HY, HZ = 2, 1, 1
+
+    def __init__(self, lvl: LevelSet, tr_gstate, xa: int, xb: int, fns, net: NetShape,
+                 nonlinear_m: Nonlinear, nonlinear_p: Nonlinear, n_mean: Optional[int] = None, device=None):
+        dev = torch.device(device if device is not None else lvl.device)
+        self.device, self.net, self.lvl = dev, net, lvl
+        L = cabi.lib()
+        with torch.cuda.device(dev):
+            st = cabi.stream_ptr()
+            Nx, Ny, Nz = tr_gstate.shape()
+            assert 0 <= xa < xb <= Nx
+            xs, ys, zs = (a.to(dev) for a in (tr_gstate.x, tr_gstate.y, tr_gstate.z))
+            dx, dy, dz = float(tr_gstate.dx), float(tr_gstate.dy), float(tr_gstate.dz)
+            self.d = (dx, dy, dz)
+            nxl = xb - xa
+            self.n_points = nxl * Ny * Nz
+
+            def extend(a, lo, hi, h, step):
+                # coordinates of global indices [lo-h, hi+h): grid values inside, a[0]-k*step / a[-1]+k*step outside
+                n = a.numel()
+                gi = torch.arange(lo - h, hi + h, device=dev)
+                inside = a[gi.clamp(0, n - 1)]
+                st32 = torch.tensor(step, dtype=torch.float32, device=dev)
+                below = a[0] - (-gi).clamp(min=0).to(torch.float32) * st32
+                above = a[n - 1] + (gi - (n - 1)).clamp(min=0).to(torch.float32) * st32
+                return torch.where(gi < 0, below, torch.where(gi > n - 1, above, inside)).contiguous()
+
+            self.xe = extend(xs, xa, xb, self.HX, dx)
+            self.ye = extend(ys, 0, Ny, self.HY, dy)
+            self.ze = extend(zs, 0, Nz, self.HZ, dz)
+            ex, ey, ez = self.xe.numel(), self.ye.numel(), self.ze.numel()
+            self.dims = (ex, ey, ez)
+            ne = ex * ey * ez
+            self.ne = ne
+            # sites: real grid nodes within one plane of the slab
+            gx_lo, gx_hi = max(xa - 1, 0), min(xb + 1, Nx)
+            lo = (gx_lo - (xa - self.HX), self.HY, self.HZ)
+            hi = (gx_hi - (xa - self.HX), self.HY + Ny, self.HZ + Nz)
+            lat = _lattice(self.xe, self.ye, self.ze, lo, hi)
+            self.sites = CrossedSites(lvl, lat, ne, self.d, fns, dev)
+            cs = self.sites
+
+            # ---- per-point coefficient samples (face centres :533-548, node values :355-356, :403-411)
+            pxs = xs[xa:xb].contiguous()
+            X, Y, Z = torch.meshgrid(pxs, ys, zs, indexing="ij")
+            R = torch.stack((X.reshape(-1), Y.reshape(-1), Z.reshape(-1)), dim=1)
+            del X, Y, Z
+            np_ = self.n_points
+            mu_m_faces = torch.empty(6 * np_, dtype=torch.float32, device=dev)
+            mu_p_faces = torch.empty(6 * np_, dtype=torch.float32, device=dev)
+            half = [(-dx, 0, 0), (dx, 0, 0), (0, -dy, 0), (0, dy, 0), (0, 0, -dz), (0, 0, dz)]
+            for f, off in enumerate(half):
+                o = torch.tensor(off, dtype=torch.float32, device=dev) * 0.5
+                Rf = R + o
+                mu_m_faces[f * np_:(f + 1) * np_] = _sample(fns.mu_m_fn, Rf)
+                mu_p_faces[f * np_:(f + 1) * np_] = _sample(fns.mu_p_fn, Rf)
+                del Rf
+            k_m, k_p = _sample(fns.k_m_fn, R), _sample(fns.k_p_fn, R)
+            f_m, f_p = _sample(fns.f_m_fn, R), _sample(fns.f_p_fn, R)
+            g_dir = _sample(fns.dir_bc_fn, R)
+            del R
+
+            # ---- K2c row assembly into lattice layout
+            use_nl = (nonlinear_m.kind != NL_NONE) or (nonlinear_p.kind != NL_NONE)
+            self.w = torch.zeros(7 * ne, dtype=torch.float32, device=dev)
+            self.rhs = torch.zeros(ne, dtype=torch.float32, device=dev)
+            self.nl = torch.zeros(2 * ne, dtype=torch.float32, device=dev) if use_nl else None
+            irr = torch.full((ne,), -1, dtype=torch.int32, device=dev)
+            cap = min(np_, 7 * cs.n) + 1
+            irr_count = torch.zeros(1, dtype=torch.int64, device=dev)
+            irr_point = torch.zeros(cap, dtype=torch.int64, device=dev)
+            irr_wE = torch.zeros(cap * 7, dtype=torch.float32, device=dev)
+            irr_c = torch.full((cap * 7,), -1, dtype=torch.int32, device=dev)
+            irr_nl = torch.zeros(cap, dtype=torch.uint8, device=dev)
+            irr_nlw = torch.zeros(cap, dtype=torch.float32, device=dev)
+            a = cabi.Assemble()
+            a.pts = _lattice(pxs, ys, zs)
+            a.dx, a.dy, a.dz = dx, dy, dz
+            for i, b in enumerate(lvl.bounds):
+                a.bounds[i] = b
+            a.shared = 1
+            a.site_dims[0], a.site_dims[1], a.site_dims[2] = ex, ey, ez
+            a.pt_off[0], a.pt_off[1], a.pt_off[2] = self.HX, self.HY, self.HZ
+            a.flag, a.side, a.cidx = cabi.ptr(cs.flag), cabi.ptr(cs.side), cabi.ptr(cs.cidx)
+            a.frac, a.beta_gamma = cabi.ptr(cs.frac), cabi.ptr(cs.beta_gamma)
+            a.mu_m_faces, a.mu_p_faces = cabi.ptr(mu_m_faces), cabi.ptr(mu_p_faces)
+            a.k_m, a.k_p, a.f_m, a.f_p, a.g_dir = (cabi.ptr(t) for t in (k_m, k_p, f_m, f_p, g_dir))
+            a.w, a.rhs, a.nl, a.irr = cabi.ptr(self.w), cabi.ptr(self.rhs), cabi.ptr(self.nl), cabi.ptr(irr)
+            a.n_out = ne
+            a.out_stride[0], a.out_stride[1], a.out_stride[2] = ey * ez, ez, 1
+            a.out_off = (self.HX * ey + self.HY) * ez + self.HZ
+            a.irr_capacity = cap
+            a.irr_count, a.irr_point = cabi.ptr(irr_count), cabi.ptr(irr_point)
+            a.irr_wE, a.irr_c, a.irr_nl, a.irr_nlw = (cabi.ptr(t) for t in (irr_wE, irr_c, irr_nl, irr_nlw))
+            cabi.check(L.nbm_assemble_f32(C.byref(a), st), "nbm_assemble_f32")
+            n_irr = int(irr_count.item())
+            if n_irr > cap:
+                raise cabi.NbmError(f"irregular-row capacity exceeded ({n_irr} > {cap})")
+            self.n_irr = n_irr
+            self.irr_point = irr_point[:max(n_irr, 1)].clone()
+            self.irr_wE = irr_wE[:max(n_irr, 1) * 7].clone()
+            self.irr_c = irr_c[:max(n_irr, 1) * 7].clone()
+            self.irr_nl = irr_nl[:max(n_irr, 1)].clone()
+            self.irr_nlw = irr_nlw[:max(n_irr, 1)].clone()
+            self.irr = irr
+            del mu_m_faces, mu_p_faces, k_m, k_p, f_m, f_p, g_dir
+
+            # ---- work buffers + the step descriptor
+            P = net.n_params
+            self.U = torch.zeros(ne, dtype=torch.float32, device=dev)
+            self.R = torch.zeros(ne, dtype=torch.float32, device=dev)  # halo rows stay 0 for ever
+            self.G = torch.zeros(ne, dtype=torch.float32, device=dev)
+            self.E = torch.zeros(max(cs.n, 1), dtype=torch.float32, device=dev)
+            self.gE = torch.zeros(max(cs.n, 1), dtype=torch.float32, device=dev)
+            rows = L.nbm_step_partial_rows()
+            self.partials = torch.zeros(rows * (P + 1), dtype=torch.float32, device=dev)
+            self.loss_grad = torch.zeros(P + 1, dtype=torch.float32, device=dev)
+            s = cabi.SharedStep()
+            s.net = net.struct()
+            s.nonlinear_m, s.nonlinear_p = nonlinear_m.kind, nonlinear_p.kind
+            s.nl_coef_m, s.nl_coef_p = nonlinear_m.coef, nonlinear_p.coef
+            s.xe, s.ye, s.ze = cabi.ptr(self.xe), cabi.ptr(self.ye), cabi.ptr(self.ze)
+            s.ex, s.ey, s.ez = ex, ey, ez
+            s.side, s.w, s.rhs, s.nl = cabi.ptr(cs.side), cabi.ptr(self.w), cabi.ptr(self.rhs), cabi.ptr(self.nl)
+            s.n_crossed, s.c_node, s.B = cs.n, cabi.ptr(cs.idx), cabi.ptr(cs.B)
+            s.n_irr = n_irr
+            s.irr_point, s.irr_wE, s.irr_c = cabi.ptr(self.irr_point), cabi.ptr(self.irr_wE), cabi.ptr(self.irr_c)
+            s.irr_nl, s.irr_nlw = cabi.ptr(self.irr_nl), cabi.ptr(self.irr_nlw)
+            s.inv_n_points = 1.0 / float(n_mean if n_mean is not None else self.n_points)
+            s.U, s.R, s.G, s.E, s.gE = (cabi.ptr(t) for t in (self.U, self.R, self.G, self.E, self.gE))
+            s.partials, s.n_partial_rows, s.loss_grad = cabi.ptr(self.partials), rows, cabi.ptr(self.loss_grad)
+            self.step = s
+            self.xa, self.xb = xa, xb
+            # the regression/cut-cell scratch is not needed by the step
+            for name in ("tri", "tri_area", "pos", "proj", "Cm", "Cp"):
+                pass  # kept: tests read them back; they are O(crossed sites)
+
+    def loss_grad_launch(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Enqueue loss and d loss/d params for this plan's rows (parameters must have been uploaded
+        with `upload_params`).  Returns the device buffer [grad(P), loss]."""
+        if out is not None:
+            self.step.loss_grad = cabi.ptr(out)
+        cabi.check(cabi.lib().nbm_loss_grad_shared_f32(C.byref(self.step), cabi.stream_ptr()),
+                   "nbm_loss_grad_shared_f32")
+        return out if out is not None else self.loss_grad
+
+    # ---- read-backs for tests -----------------------------------------------------------------
+    def point_view(self, t: torch.Tensor) -> torch.Tensor:
+        """lattice-layout array -> (n_points,) in the reference's point order"""
+        ex, ey, ez = self.dims
+        return t.view(ex, ey, ez)[self.HX:ex - self.HX, self.HY:ey - self.HY, self.HZ:ez - self.HZ].reshape(-1)
+
+
+def upload_params(net: NetShape, params: torch.Tensor) -> None:
+    s = net.struct()
+    cabi.check(cabi.lib().nbm_upload_params(C.byref(s), cabi.ptr(params), cabi.stream_ptr()), "nbm_upload_params")

@@ -1,0 +1,125 @@
+"""GPU parity of the shared-evaluation path (cell size == grid spacing) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): cut-cell fractions and residual rows 1e-5, loss and
+gradients 1e-4.  "Relative" is normwise: max|a-b| / max|b| over the array (rows of one problem share
+one scale: the Dirichlet rows are O(1)); per-element relative error is meaningless where the
+finite-volume row cancels to ~h^2.  The oracle runs in float64 (the exact-arithmetic value of the
+reference's algorithm) on float32 level-set samples, so that every sign decision is identical.
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+import util
+from jax_dips_b200 import _cabi as cabi
+from jax_dips_b200 import numpy as jnp
+from jax_dips_b200 import plan as nplan
+from jax_dips_b200 import problems
+from jax_dips_b200.simulation_states import PoissonSimStateFn
+from oracle import nbm_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_FRAC, TOL_ROW, TOL_LOSS = 1e-5, 1e-5, 1e-4
+
+
+def fns_of(problem):
+    v = jnp.vmap
+    return PoissonSimStateFn(v(problem.initial_value_fn), v(problem.dirichlet_bc_fn), v(problem.phi_fn),
+                             v(problem.mu_m_fn), v(problem.mu_p_fn), v(problem.k_m_fn), v(problem.k_p_fn),
+                             v(problem.f_m_fn), v(problem.f_p_fn), v(problem.alpha_fn), v(problem.beta_fn),
+                             problem.nonlinear_op_m, problem.nonlinear_op_p)
+
+
+def build(problem, n_train, n_lvl, interp="trilinear", net=None, xa=0, xb=None):
+    tr, lv, phi_grid, oprob = util.make_case(problem, n_train, n_lvl, interp, torch.float64, net=net)
+    lvl = nplan.LevelSet(lv, phi_grid, interp=interp, perturb_eps=1e-10, device=DEV)
+    shape = nplan.NetShape(oprob.shape.Lp, oprob.shape.Hp, oprob.shape.Lm, oprob.shape.Hm)
+    pl = nplan.SharedPlan(lvl, tr, xa, xb if xb is not None else tr.shape()[0], fns_of(problem), shape,
+                          nplan.Nonlinear.coerce(problem.nonlinear_op_m),
+                          nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=DEV)
+    return tr, lv, lvl, oprob, pl, shape
+
+
+@pytest.mark.parametrize("interp", ["trilinear", "quadratic"])
+def test_phi_interp_matches_oracle(interp):
+    P = problems.sphere()
+    tr, lv, phi_grid, oprob = util.make_case(P, 8, 20, interp, torch.float32, perturb_eps=0.0)
+    lvl = nplan.LevelSet(lv, phi_grid, interp=interp, perturb_eps=0.0, device=DEV)
+    g = torch.Generator().manual_seed(1)
+    pts = (torch.rand(20000, 3, generator=g) * 2.6 - 1.3).float()   # includes points outside the box
+    got = lvl(pts.to(DEV)).cpu()
+    want = oprob.phi_fn(pts)
+    assert torch.equal(got, want) or util.rel_inf(got, want) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["sphere", "star"])
+def test_classification_and_cut_cells(name):
+    P = problems.PROBLEMS[name]()
+    tr, lv, lvl, oprob, pl, _ = build(P, 16, 32)
+    dt = torch.float64
+    d = [tr.dx.to(dt), tr.dy.to(dt), tr.dz.to(dt)]
+    R = tr.R.to(dt)
+    flag_o = O.is_cell_crossed(R, *d, oprob.phi_fn)
+    flag_k = pl.point_view(pl.sites.flag).cpu().to(dt)
+    assert torch.equal(flag_k, flag_o), f"{(flag_k != flag_o).sum()} crossing flags differ"
+    # fractions of crossed cells against the exact-arithmetic oracle (mu = 1 -> columns 14.. are areas)
+    one = lambda X: torch.ones(X.shape[0], dtype=dt)
+    crossed = (flag_o == 0).nonzero().reshape(-1)
+    assert crossed.numel() > 50
+    co = O.cell_faces_areas_values(R[crossed], *d, oprob.phi_fn, one, one)
+    cidx = pl.point_view(pl.sites.cidx).cpu()[crossed].long()
+    frac = pl.sites.frac.view(-1, 14).cpu().to(dt)[cidx]
+    vol = float(d[0] * d[1] * d[2])
+    area = float(d[1] * d[2])
+    err_v = (frac[:, 12:14] - co[:, 12:14]).abs().max() / vol
+    err_a = (frac[:, 0:12] - co[:, 14:26]).abs().max() / area
+    assert err_v < TOL_FRAC and err_a < TOL_FRAC, (float(err_v), float(err_a))
+    # Gamma integral of beta
+    bg = pl.sites.beta_gamma.cpu().to(dt)[cidx]
+    bo = O.integrate_over_interface(R[crossed], *d, oprob.phi_fn, oprob.beta_fn)
+    assert util.rel_inf(bg, bo) < TOL_FRAC
+
+
+@pytest.mark.parametrize("name,n,nl", [("sphere", 16, 32), ("star", 16, 32), ("no_jump", 12, 16), ("sphere", 24, 24)])
+def test_rows_loss_and_gradient(name, n, nl):
+    P = problems.PROBLEMS[name]()
+    tr, lv, lvl, oprob, pl, shape = build(P, n, nl)
+    dt = torch.float64
+    params = O.init_params(oprob.shape, seed=7, dtype=dt)
+    d = [tr.dx.to(dt), tr.dy.to(dt), tr.dz.to(dt)]
+    lhs_o, rhs_o = O.compute_Ax_and_b(params, tr.R.to(dt), *d, oprob)
+    loss_o, grad_o = O.loss_and_grad(params, tr.R.to(dt), *d, oprob)
+    p_dev = params.float().to(DEV)
+    with torch.cuda.device(DEV):
+        nplan.upload_params(shape, p_dev)
+        lg = pl.loss_grad_launch()
+        torch.cuda.synchronize()
+    rhs_k = pl.point_view(pl.rhs).cpu()
+    lhs_k = pl.point_view(pl.R).cpu() + rhs_k
+    e_rhs, e_lhs = util.rel_inf(rhs_k, rhs_o), util.rel_inf(lhs_k, lhs_o)
+    assert e_rhs < TOL_ROW and e_lhs < TOL_ROW, (e_lhs, e_rhs)
+    loss_k, grad_k = float(lg[-1]), lg[:-1].cpu()
+    assert abs(loss_k - float(loss_o)) / float(loss_o) < TOL_LOSS, (loss_k, float(loss_o))
+    assert util.rel_inf(grad_k, grad_o) < TOL_LOSS, util.rel_inf(grad_k, grad_o)
+    # per-coordinate check on the large entries too
+    big = grad_o.abs() > 1e-2 * grad_o.abs().max()
+    assert ((grad_k.double()[big] - grad_o[big]).abs() / grad_o[big].abs()).max() < 10 * TOL_LOSS
+
+
+def test_slab_plans_sum_to_the_whole_grid():
+    """x-slabs (the multi-GPU partition, data_management.py:121-130) : sum of per-slab
+    n_slab*mean-gradients equals the whole-grid n*mean-gradient."""
+    P = problems.sphere()
+    tr, lv, lvl, oprob, whole, shape = build(P, 16, 32)
+    params = O.init_params(oprob.shape, seed=3).to(DEV)
+    with torch.cuda.device(DEV):
+        nplan.upload_params(shape, params)
+        ref = whole.loss_grad_launch().clone()
+        acc = torch.zeros_like(ref)
+        for (a, b) in ((0, 4), (4, 8), (8, 16)):
+            tr2, lv2, lvl2, _, pl, _ = build(P, 16, 32, xa=a, xb=b)
+            acc += pl.loss_grad_launch() * (pl.n_points / whole.n_points)
+        torch.cuda.synchronize()
+    assert util.rel_inf(acc, ref) < 1e-5
