@@ -575,7 +575,11 @@ __global__ void assemble_kernel(nbm_assemble_t a) {
         }
     }
     for (int s = 0; s < 7; ++s) a.w[s * a.n_out + out] = wU[s];
-    a.rhs[out] = ok ? rhs * inv : 0.0f;
+    // nan_to_num(rhs/diag) (:419): NaN -> 0, +-inf -> +-FLT_MAX
+    float rn = ok ? rhs * inv : 0.0f;
+    if (isnan(rn)) rn = 0.0f;
+    else if (isinf(rn)) rn = rn > 0.0f ? 3.4028234664e38f : -3.4028234664e38f;
+    a.rhs[out] = rn;
     if (a.nl) { a.nl[out] = nl0; a.nl[a.n_out + out] = nl1; }
     int32_t slot = -1;
     if (irregular && ok) {

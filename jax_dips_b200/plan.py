@@ -211,8 +211,11 @@ class CrossedSites:
                    "nbm_site_weights_f32")
         # integral over Gamma of beta (geometric_integrations_per_point.py:385-412): sum_t area_t * mean_v beta
         area = self.tri_area.view(nc, 10)
+        # Unused triangle slots are all-zero vertices with zero area: like the reference (:397-410) the
+        # callable IS evaluated at the origin and multiplied by 0, so a beta that is singular at the
+        # origin turns the integral into NaN, which nan_to_num(rhs/diag) (discretization.py:419) then
+        # maps to 0.  Kept bit-for-bit: results must match the reference on the same inputs.
         beta_v = _sample(fns.beta_fn, self.tri.view(nc * 30, 3)).view(nc, 10, 3).mean(dim=2)
-        beta_v = torch.where(area > 0, beta_v, torch.zeros_like(beta_v))  # padded slots carry no area
         self.beta_gamma = (area * beta_v).sum(dim=1).contiguous()
         torch.cuda.current_stream().synchronize()  # sample tensors die here
 

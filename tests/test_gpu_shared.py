@@ -79,7 +79,19 @@ def test_classification_and_cut_cells(name):
     # Gamma integral of beta
     bg = pl.sites.beta_gamma.cpu().to(dt)[cidx]
     bo = O.integrate_over_interface(R[crossed], *d, oprob.phi_fn, oprob.beta_fn)
-    assert util.rel_inf(bg, bo) < TOL_FRAC
+    # (sphere: beta is NaN at the origin, where the reference evaluates it for the unused triangle
+    # slots -> the whole integral is NaN there, on both sides)
+    assert torch.equal(torch.isnan(bg), torch.isnan(bo))
+    fin = ~torch.isnan(bo)
+    if fin.any():
+        assert util.rel_inf(bg[fin], bo[fin]) < TOL_FRAC
+    # and with a beta that is regular at the origin the integral itself is checked
+    tri = pl.sites.tri.view(-1, 10, 3, 3)[cidx.to(pl.sites.tri.device)]
+    area = pl.sites.tri_area.view(-1, 10)[cidx.to(pl.sites.tri.device)]
+    smooth = lambda X: torch.cos(X[:, 0]) * torch.exp(X[:, 1]) + X[:, 2]
+    got = (area.double().cpu() * smooth(tri.reshape(-1, 3).double().cpu()).view(-1, 10, 3).mean(-1)).sum(-1)
+    want = O.integrate_over_interface(R[crossed], *d, oprob.phi_fn, smooth)
+    assert util.rel_inf(got, want) < TOL_FRAC
 
 
 @pytest.mark.parametrize("name,n,nl", [("sphere", 16, 32), ("star", 16, 32), ("no_jump", 12, 16), ("sphere", 24, 24)])
