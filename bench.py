@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the NBM training step (one optimizer step = residual + d loss/d params at every
+training point + gradient all-reduce + optax chain) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU restatement of the reference, on the host cores
+
+Prints ONE JSON line (rank 0).  metric = point-evaluations per second (BASELINE.json).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "point_evals_per_sec"
+UNIT = "points/s"
+
+# Algorithmic work per point-evaluation (DESIGN.md "Roofline"):
+# default net p(3-10-10-1) | m(3-1-1), shared evaluation at native spacing
+F_STEP = 1.0e3        # FLOP per point for the whole step (fwd 0.38k + bwd 0.55k + stencil 0.06k)
+F_GRAD = 0.93e3       # FLOP per lattice node for the dominant kernel (forward recompute 0.38k + backward 0.55k)
+B_STEP = 64.0         # bytes per point streamed by the step (row table 7 w + rhs = 32 B read twice)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sphere", choices=["sphere", "star", "stars", "dragon_like", "poisson_boltzmann"])
+    ap.add_argument("--grid", type=int, default=256, help="training points per axis per GPU-slab (x grows with N: weak scaling)")
+    ap.add_argument("--lvl", type=int, default=128)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=12288)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def make_problem(name):
+    from jax_dips_b200 import problems
+    return problems.PROBLEMS[name]()
+
+
+def grids(problem, args, world):
+    from jax_dips_b200 import mesh
+    lo, hi = problem.box
+    nx = args.grid * world if args.scaling == "weak" else args.grid
+    tr = mesh.linspace_grid(lo, hi, [nx, args.grid, args.grid])
+    lv = mesh.linspace_grid(lo, hi, [args.lvl] * 3)
+    return tr, lv
+
+
+def sim_fns(problem):
+    from jax_dips_b200 import numpy as jnp
+    from jax_dips_b200.simulation_states import PoissonSimStateFn
+    v = jnp.vmap
+    return PoissonSimStateFn(v(problem.initial_value_fn), v(problem.dirichlet_bc_fn), v(problem.phi_fn),
+                             v(problem.mu_m_fn), v(problem.mu_p_fn), v(problem.k_m_fn), v(problem.k_p_fn),
+                             v(problem.f_m_fn), v(problem.f_p_fn), v(problem.alpha_fn), v(problem.beta_fn),
+                             problem.nonlinear_op_m, problem.nonlinear_op_p)
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed region (NVML, 10 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=1.0)
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_baseline(problem, args, n_sample, steps=1, warmup=0):
+    """The oracle (CPU restatement of the reference: 197 network evaluations per point, JAX unavailable)
+    on the host cores, on a bounded sample of the SAME workload: every (N/n_sample)-th training point."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    from oracle import nbm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    tr, lv, phi_grid, oprob = util.make_case(problem, [args.grid] * 3, args.lvl, "trilinear", torch.float32)
+    n = tr.num_points()
+    stride = max(1, n // n_sample)
+    # build the sample without materialising the whole (n,3) point list
+    idx = torch.arange(0, n, stride)[:n_sample]
+    ny, nz = tr.shape()[1], tr.shape()[2]
+    pts = torch.stack((tr.x[idx // (ny * nz)], tr.y[(idx // nz) % ny], tr.z[idx % nz]), dim=1)
+    params = O.init_params(oprob.shape, seed=42)
+    d = [tr.dx, tr.dy, tr.dz]
+    for _ in range(warmup):
+        O.loss_and_grad(params, pts[:256], *d, oprob)
+    t0 = time.time()
+    for _ in range(steps):
+        O.loss_and_grad(params, pts, *d, oprob, chunk=4096)
+    dt = (time.time() - t0) / steps
+    return {"value": pts.shape[0] / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{pts.shape[0]} of the {n} training points (every {stride}-th), one loss+grad pass each; "
+                      "torch-CPU restatement of the reference's literal formulation (JAX is not installed)",
+            "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    problem = make_problem(args.workload)
+    n_step = 2048
+    res = cpu_baseline(problem, args, n_step, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds"] * 1e3,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload} {args.grid}^3 train / {args.lvl}^3 lvl (bounded sample)",
+                       "sample_points_per_step": n_step},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from jax_dips_b200 import _cabi as cabi
+    from jax_dips_b200 import plan as nplan
+    from jax_dips_b200.optimizers import get_optimizer
+    from jax_dips_b200.trainer import haiku_init
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = cabi.lib()
+
+    problem = make_problem(args.workload)
+    tr, lv = grids(problem, args, world)
+    fns = sim_fns(problem)
+    Nx, Ny, Nz = tr.shape()
+    per = Nx // world
+    xa, xb = rank * per, (rank + 1) * per
+    net = nplan.NetShape()
+    P = net.n_params
+    phi_lvl = fns.phi_fn(lv.R.to(dev))
+    lvl = nplan.LevelSet(lv, phi_lvl, interp="trilinear", perturb_eps=1e-10, device=dev)
+    t_setup = time.time()
+    pl = nplan.SharedPlan(lvl, tr, xa, xb, fns, net, nplan.Nonlinear.coerce(problem.nonlinear_op_m),
+                          nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=dev)
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+
+    params = haiku_init(net, 42).to(dev)
+    opt_state = torch.zeros(2 * P, device=dev)
+    opt_count = torch.zeros(1, dtype=torch.int32, device=dev)
+    spec = get_optimizer("custom", "exponential", 1e-3, 0.975)
+    ostruct = cabi.Optimizer(P, 1e-3, 0.975, 1000.0, 1.0, 0.9, 0.999, 1e-8, 0, 0)
+    lg = pl.loss_grad
+
+    def step():
+        nplan.upload_params(net, params)
+        pl.loss_grad_launch()
+        if world > 1:
+            dist.all_reduce(lg, op=dist.ReduceOp.SUM)
+        cabi.check(L.nbm_apply_update_f32(C.byref(ostruct), cabi.ptr(lg), cabi.ptr(params), cabi.ptr(opt_state),
+                                          cabi.ptr(opt_count), None, cabi.stream_ptr()))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches_per_step = 5 + (1 if pl.sites.n > 0 else 0) * 2 + (1 if pl.n_irr > 0 else 0) * 2 + 1  # + update kernel
+
+    # ---------------- value: device-resident inputs -------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    n_points_total = Nx * Ny * Nz
+    value = n_points_total * args.steps / (ms * 1e-3)
+    loss_now = float(lg[-1].item())
+
+    # ---------------- e2e: the operator seam with HOST buffers --------------------------------
+    # per step: params + grid coordinate arrays from pinned host memory -> device, the step, then
+    # [grad, loss] back to pinned host memory and a stream synchronize (what a host framework sees).
+    h_params = params.detach().cpu().pin_memory()
+    h_coords = torch.cat((pl.xe.cpu(), pl.ye.cpu(), pl.ze.cpu())).pin_memory()
+    d_coords = torch.empty_like(h_coords, device=dev)
+    h_out = torch.empty(P + 1).pin_memory()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        params.copy_(h_params, non_blocking=True)
+        d_coords.copy_(h_coords, non_blocking=True)
+        step()
+        h_out.copy_(lg, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h_params.copy_(params)  # the host keeps the parameters: next step's input
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    e2e = {"value": n_points_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": int(h_params.numel() * 4 + h_coords.numel() * 4),
+           "d2h_bytes_per_step": int((P + 1) * 4 + P * 4),
+           "what": "params + lattice coordinate arrays H2D from pinned memory, step through the C ABI, "
+                   "[grad, loss] and updated params D2H, stream sync, every step"}
+
+    # ---------------- roofline of the dominant kernel (node_grad) -----------------------------
+    roof = None
+    cpu = None
+    if rank == 0:
+        # measured FP32 FMA peak (MEASURED_PEAKS.json holds no FP32 figure)
+        scratch = torch.zeros(4, device=dev)
+        flops = C.c_double(0.0)
+        L.nbm_ffma_probe_f32(64, cabi.ptr(scratch), C.byref(flops), cabi.stream_ptr())
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(3):
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            L.nbm_ffma_probe_f32(4096, cabi.ptr(scratch), C.byref(flops), cabi.stream_ptr())
+            g1.record()
+            torch.cuda.synchronize()
+            best = max(best, flops.value / (g0.elapsed_time(g1) * 1e-3) / 1e12)
+        ffma_peak = best
+        # per-stage device time, live, on the launching stream
+        stage_ms = {}
+        names = {1: "fwd_nodes", 4: "residual", 8: "adjoint", 16: "node_grad"}
+        nplan.upload_params(net, params)
+        pl.step.stages = 0
+        pl.loss_grad_launch()
+        for bit, nm in names.items():
+            pl.step.stages = bit
+            tot = 0.0
+            for _ in range(min(args.steps, 20)):
+                h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                h0.record()
+                pl.loss_grad_launch()
+                h1.record()
+                torch.cuda.synchronize()
+                tot += h0.elapsed_time(h1)
+            stage_ms[nm] = tot / min(args.steps, 20)
+        pl.step.stages = 0
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        ne = pl.ne
+        ach = F_GRAD * ne / (stage_ms["node_grad"] * 1e-3) / 1e12
+        step_ach = F_STEP * (pl.n_points) / ((ms / args.steps) * 1e-3) / 1e12
+        roof = {"bound": "fp32", "kernel": "node_grad_kernel", "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s",
+                "frac": ach / ffma_peak if ffma_peak else None, "traffic": None,
+                "peak_source": "FFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP32 figure; "
+                               "nominal 148 SM x 128 x 2 x 1.965 GHz = 74.5)",
+                "algorithmic_flop_per_node": F_GRAD, "nodes_per_launch": ne,
+                "stage_ms": stage_ms,
+                "step": {"achieved": step_ach, "frac": step_ach / ffma_peak if ffma_peak else None,
+                         "algorithmic_flop_per_point": F_STEP},
+                "hbm": {"achieved": B_STEP * pl.n_points / ((stage_ms["residual"] + stage_ms["adjoint"]) * 1e-3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s", "kernels": "residual + adjoint",
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"}}
+        roof["hbm"]["frac"] = roof["hbm"]["achieved"] / hbm_peak
+        if not args.no_cpu_baseline and world == 1:
+            r = cpu_baseline(problem, args, args.cpu_sample, steps=1, warmup=1)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: train grid {Nx}x{Ny}x{Nz} ({n_points_total} points, "
+                                       f"x-slabs of {per} planes per GPU), level set on {args.lvl}^3 lvl grid "
+                                       "(trilinear), MLP p 3-10-10-1 | m 3-1-1 tanh, optimizer custom(adam), "
+                                       "one batch per GPU",
+                           "l2": "row tables (553 MB at 256^3) exceed the 126 MB L2; no flush needed",
+                           "crossed_sites": int(pl.sites.n), "irregular_rows": int(pl.n_irr),
+                           "setup_seconds": t_setup, "loss": loss_now},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

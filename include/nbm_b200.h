@@ -218,9 +218,25 @@ typedef struct {
     float* partials;                 /* [n_partial_rows][P+1] */
     int n_partial_rows;              /* >= nbm_step_partial_rows() */
     float* loss_grad;                /* [P+1]: grad[0..P), loss at [P] */
+    int stages;                      /* 0 = the whole step; else a bit mask of nbm_stage (profiling / timing) */
 } nbm_shared_step_t;
 
+/* stages of the shared-evaluation step, in launch order */
+enum nbm_stage {
+    NBM_STAGE_FWD = 1,        /* U = u(node) for every lattice node */
+    NBM_STAGE_EXTRAP = 2,     /* far-side values E at crossed nodes */
+    NBM_STAGE_RESIDUAL = 4,   /* rows: 7-point stencil on U (+ irregular rows) */
+    NBM_STAGE_ADJOINT = 8,    /* G = d loss / d U (adjoint stencil + adjoint of irregular rows / extrapolation) */
+    NBM_STAGE_GRAD = 16,      /* forward recompute + backward per node, per-CTA partial sums */
+    NBM_STAGE_REDUCE = 32     /* partial rows -> [grad, loss] */
+};
+
 int nbm_step_partial_rows(void);
+
+/* FP32 FMA-pipe micro-benchmark (the roofline denominator MEASURED_PEAKS.json lacks): every thread
+ * runs `iters` x 16 independent FFMAs; returns the number of FLOPs issued through *flops_host (host
+ * pointer); the caller times it with events on `stream`.  out[1] receives a checksum. */
+int nbm_ffma_probe_f32(int iters, float* out, double* flops_host, nbm_stream_t stream);
 
 /* loss and d loss/d params for the rows of the plan, network parameters taken from the
  * __constant__ bank (call nbm_upload_params first).  Native-spacing "shared evaluation" path:
@@ -259,7 +275,9 @@ int nbm_loss_grad_points_f32(const nbm_points_step_t* s, nbm_stream_t stream);
 typedef struct {
     int n_params;
     float lr, decay_rate, transition_steps, max_norm, b1, b2, eps;
-    int optimizer;                   /* 0 = "custom" chain, 1 = plain adam (no clip, constant lr) */
+    int optimizer;                   /* 0 = "custom" chain, 1 = optax.adam (no clip, constant lr),
+                                        2 = optax.rmsprop (scale_by_rms(0.9, eps) -> -lr; b2 is the decay) */
+    int scheduler;                   /* "custom" only: 0 = exponential_decay, 1 = polynomial(power 1, end 0) */
 } nbm_optimizer_t;
 
 int nbm_apply_update_f32(const nbm_optimizer_t* opt, const float* loss_grad, float* params,

@@ -63,7 +63,7 @@ class SharedStep(C.Structure):
                 ("irr_nl", c_fp), ("irr_nlw", c_fp),
                 ("inv_n_points", c_f),
                 ("U", c_fp), ("R", c_fp), ("G", c_fp), ("E", c_fp), ("gE", c_fp),
-                ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp)]
+                ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp), ("stages", C.c_int)]
 
 
 class PointsStep(C.Structure):
@@ -84,7 +84,7 @@ class PointsStep(C.Structure):
 class Optimizer(C.Structure):
     _fields_ = [("n_params", C.c_int),
                 ("lr", c_f), ("decay_rate", c_f), ("transition_steps", c_f), ("max_norm", c_f),
-                ("b1", c_f), ("b2", c_f), ("eps", c_f), ("optimizer", C.c_int)]
+                ("b1", c_f), ("b2", c_f), ("eps", c_f), ("optimizer", C.c_int), ("scheduler", C.c_int)]
 
 
 # every symbol include/nbm_b200.h declares: name -> (restype, argtypes)
@@ -103,6 +103,7 @@ SYMBOLS = {
     "nbm_net_num_params": (C.c_int, [_P(Net)]),
     "nbm_upload_params": (C.c_int, [_P(Net), c_fp, c_fp]),
     "nbm_step_partial_rows": (C.c_int, []),
+    "nbm_ffma_probe_f32": (C.c_int, [C.c_int, c_fp, _P(C.c_double), c_fp]),
     "nbm_loss_grad_shared_f32": (C.c_int, [_P(SharedStep), c_fp]),
     "nbm_loss_grad_points_f32": (C.c_int, [_P(PointsStep), c_fp]),
     "nbm_apply_update_f32": (C.c_int, [_P(Optimizer), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),

@@ -412,16 +412,27 @@ __global__ void apply_update_kernel(nbm_optimizer_t o, const float* __restrict__
     int t_prev = *count;
     float t = (float)(t_prev + 1);
     float bc1 = 1.0f - powf(o.b1, t), bc2 = 1.0f - powf(o.b2, t);
-    float step = o.optimizer == 0 ? o.lr * powf(o.decay_rate, (float)t_prev / o.transition_steps) : o.lr;
+    float step = o.lr;
+    if (o.optimizer == 0) {
+        if (o.scheduler == 0) step = o.lr * powf(o.decay_rate, (float)t_prev / o.transition_steps);
+        else step = o.lr * (1.0f - fminf((float)t_prev, o.transition_steps) / o.transition_steps);
+    }
     float* m = state;
     float* v = state + P;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
         float g = loss_grad[i] * s_scale;
-        float mi = (1.0f - o.b1) * g + o.b1 * m[i];
-        float vi = (1.0f - o.b2) * (g * g) + o.b2 * v[i];
-        m[i] = mi;
-        v[i] = vi;
-        float upd = (mi / bc1) / (sqrtf(vi / bc2) + o.eps);
+        float upd;
+        if (o.optimizer == 2) {  // optax.scale_by_rms: nu = d nu + (1-d) g^2 ; g * rsqrt(nu + eps)
+            float vi = o.b2 * v[i] + (1.0f - o.b2) * (g * g);
+            v[i] = vi;
+            upd = g * rsqrtf(vi + o.eps);
+        } else {
+            float mi = (1.0f - o.b1) * g + o.b1 * m[i];
+            float vi = (1.0f - o.b2) * (g * g) + o.b2 * v[i];
+            m[i] = mi;
+            v[i] = vi;
+            upd = (mi / bc1) / (sqrtf(vi / bc2) + o.eps);
+        }
         params[i] += -1.0f * (step * upd);
     }
     __syncthreads();
@@ -476,31 +487,50 @@ constexpr int kPartialRows = 148 * 2;  // upper bound on the node_grad grid
 template <class NET>
 static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     const int sms = sm_count();
+    const int stages = s.stages == 0 ? 0x3f : s.stages;
     Tasks T = make_tasks(s.ex, s.ey, s.ez, 16);
-    // A
-    int gridA = min(T.total, sms * 4);
-    fwd_nodes_kernel<NET><<<gridA, kThreads, 0, st>>>(s, T);
-    // A2
-    if (s.n_crossed > 0) extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
-    // B
-    {
+    if (stages & NBM_STAGE_FWD) {
+        int gridA = min(T.total, sms * 4);
+        fwd_nodes_kernel<NET><<<gridA, kThreads, 0, st>>>(s, T);
+    }
+    if ((stages & NBM_STAGE_EXTRAP) && s.n_crossed > 0)
+        extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
+    if (stages & NBM_STAGE_RESIDUAL) {
         dim3 g((s.ez - 2 + kThreads - 1) / kThreads, s.ey - 2, s.ex - 2);
         residual_kernel<<<g, kThreads, 0, st>>>(s);
+        if (s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
     }
-    if (s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
-    // C1
-    {
+    if (stages & NBM_STAGE_ADJOINT) {
         dim3 g((s.ez + kThreads - 1) / kThreads, s.ey, s.ex);
         adjoint_kernel<<<g, kThreads, 0, st>>>(s);
+        if (s.n_irr > 0) irregular_bwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
+        if (s.n_crossed > 0) extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, st>>>(s);
     }
-    if (s.n_irr > 0) irregular_bwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
-    if (s.n_crossed > 0) extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, st>>>(s);
-    // C2
     int gridC = min(T.total, min(kPartialRows, sms));
     if (gridC > s.n_partial_rows) gridC = s.n_partial_rows;
-    node_grad_kernel<NET><<<gridC, kThreads, 0, st>>>(s, T);
-    reduce_partials_kernel<<<(NET::NP + 1 + 127) / 128, 128, 0, st>>>(s.partials, gridC, NET::NP + 1, s.loss_grad);
+    if (stages & NBM_STAGE_GRAD) node_grad_kernel<NET><<<gridC, kThreads, 0, st>>>(s, T);
+    if (stages & NBM_STAGE_REDUCE)
+        reduce_partials_kernel<<<(NET::NP + 1 + 127) / 128, 128, 0, st>>>(s.partials, gridC, NET::NP + 1, s.loss_grad);
     return cuda_check(cudaGetLastError(), "shared step launch");
+}
+
+// FP32 FMA-pipe probe: 16 independent accumulator chains per thread
+__global__ void __launch_bounds__(256) ffma_probe_kernel(int iters, float* out) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = 1.0f + 1e-3f * (float)(threadIdx.x + i);
+    float b = 1.0000001f, c = 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456f) out[1] = s;  // keeps the chains alive without memory traffic
 }
 
 #define NBM_NET_DISPATCH(net, FN, ...)                                                                       \
@@ -520,6 +550,186 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     } while (0)
 
 static int dispatch_shared(const nbm_shared_step_t& s, cudaStream_t st) { NBM_NET_DISPATCH(s.net, launch_shared, s, st); }
+
+
+// =============================================================================================
+// General path: any cell size (multi-resolution levels, data_management.py:320-326) and any
+// contiguous batch.  Stencil sites p +- d e_a are not grid nodes, nothing is shared between points:
+// 7 network evaluations per point (the reference does 197), fused forward + residual + backward.
+// =============================================================================================
+struct PointsArgs {
+    nbm_points_step_t s;
+    float shift[7][3];
+    int64_t n_points;  // nx*ny*nz
+};
+
+// Z0: E[c] for the crossed sites of the batch: one warp per site, lane q < 27 evaluates the cube
+// vertex s + X_q (get_Xijk, discretization.py:164-197: x fastest)
+template <class NET>
+__global__ void __launch_bounds__(kThreads) points_extrap_kernel(PointsArgs a) {
+    const nbm_points_step_t& s = a.s;
+    int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < s.n_crossed; c += nwarps) {
+        int64_t p = s.c_site[c] % a.n_points;
+        if (p < s.p0 || p >= s.p1) continue;
+        float v = 0.0f;
+        if (lane < 27) {
+            float X0 = (float)(lane % 3 - 1) * s.dx, X1 = (float)((lane / 3) % 3 - 1) * s.dy,
+                  X2 = (float)(lane / 9 - 1) * s.dz;
+            bool plus = (s.c_cube_side[c] >> lane) & 1u;
+            float u = NET::eval(plus, s.c_pos[3 * c] + X0, s.c_pos[3 * c + 1] + X1, s.c_pos[3 * c + 2] + X2);
+            v = s.B[c * 28 + lane] * u;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+            s.E[c] = v + s.B[c * 28 + 27];
+            s.gE[c] = 0.0f;
+        }
+    }
+}
+
+// Z1: rows of the batch
+template <class NET>
+__global__ void __launch_bounds__(kThreads, 1) points_rows_kernel(PointsArgs a) {
+    const nbm_points_step_t& s = a.s;
+    float acc[NET::NP];
+#pragma unroll
+    for (int i = 0; i < NET::NP; ++i) acc[i] = 0.0f;
+    float loss = 0.0f;
+    const int64_t N = a.n_points;
+    for (int64_t p = s.p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < s.p1;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        int k = (int)(p % s.nz);
+        int64_t t = p / s.nz;
+        int j = (int)(t % s.ny), i = (int)(t / s.ny);
+        float x = __ldg(s.xs + i), y = __ldg(s.ys + j), z = __ldg(s.zs + k);
+        float u[7], w[7];
+        float r = -s.rhs[p];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            w[q] = s.w[q * N + p];
+            bool plus = (s.side[q * N + p] & 1) != 0;
+            u[q] = (w[q] != 0.0f || q == 0) ? NET::eval(plus, x + a.shift[q][0], y + a.shift[q][1], z + a.shift[q][2])
+                                            : 0.0f;
+            r = fmaf(w[q], u[q], r);
+        }
+        float nlw0 = 0.0f, nlw1 = 0.0f;
+        if (s.nl) {
+            nlw0 = s.nl[p];
+            nlw1 = s.nl[N + p];
+            r = fmaf(nlw0, nl_apply(s.nonlinear_m, s.nl_coef_m, u[0]), r);
+            r = fmaf(nlw1, nl_apply(s.nonlinear_p, s.nl_coef_p, u[0]), r);
+        }
+        int32_t q_irr = s.irr[p];
+        if (q_irr >= 0) {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                int32_t c = s.irr_c[(int64_t)q_irr * 7 + q];
+                if (c >= 0) r = fmaf(s.irr_wE[(int64_t)q_irr * 7 + q], s.E[c], r);
+            }
+            uint8_t nlr = s.irr_nl[q_irr];
+            if (nlr) {
+                float Ec = s.E[s.irr_c[(int64_t)q_irr * 7]];
+                r = fmaf(s.irr_nlw[q_irr], nlr == 1 ? nl_apply(s.nonlinear_m, s.nl_coef_m, Ec)
+                                                    : nl_apply(s.nonlinear_p, s.nl_coef_p, Ec), r);
+            }
+        }
+        loss = fmaf(0.5f * r, r, loss);
+        float g = r * s.inv_n_points;
+        if (q_irr >= 0) {
+            // each crossed site belongs to exactly one (point, slot): plain stores
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                int32_t c = s.irr_c[(int64_t)q_irr * 7 + q];
+                if (c >= 0) {
+                    float ge = s.irr_wE[(int64_t)q_irr * 7 + q] * g;
+                    if (q == 0) {
+                        uint8_t nlr = s.irr_nl[q_irr];
+                        if (nlr) {
+                            float Ec = s.E[c];
+                            ge = fmaf(s.irr_nlw[q_irr] * (nlr == 1 ? nl_deriv(s.nonlinear_m, s.nl_coef_m, Ec)
+                                                                   : nl_deriv(s.nonlinear_p, s.nl_coef_p, Ec)), g, ge);
+                        }
+                    }
+                    s.gE[c] = ge;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            float gq = w[q] * g;
+            if (q == 0 && s.nl)
+                gq = fmaf(nlw0 * nl_deriv(s.nonlinear_m, s.nl_coef_m, u[0]) +
+                              nlw1 * nl_deriv(s.nonlinear_p, s.nl_coef_p, u[0]), g, gq);
+            if (gq != 0.0f) {
+                bool plus = (s.side[q * N + p] & 1) != 0;
+                NET::grad(plus, x + a.shift[q][0], y + a.shift[q][1], z + a.shift[q][2], gq, acc);
+            }
+        }
+    }
+    loss *= s.inv_n_points;
+    block_reduce_store<NET::NP>(acc, loss, s.partials);
+}
+
+// Z2: backward through the extrapolation of the crossed sites of the batch
+template <class NET>
+__global__ void __launch_bounds__(kThreads, 1) points_extrap_bwd_kernel(PointsArgs a, int row0) {
+    const nbm_points_step_t& s = a.s;
+    float acc[NET::NP];
+#pragma unroll
+    for (int i = 0; i < NET::NP; ++i) acc[i] = 0.0f;
+    int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < s.n_crossed; c += nwarps) {
+        int64_t p = s.c_site[c] % a.n_points;
+        if (p < s.p0 || p >= s.p1) continue;
+        float ge = s.gE[c];
+        if (lane < 27 && ge != 0.0f) {
+            float X0 = (float)(lane % 3 - 1) * s.dx, X1 = (float)((lane / 3) % 3 - 1) * s.dy,
+                  X2 = (float)(lane / 9 - 1) * s.dz;
+            bool plus = (s.c_cube_side[c] >> lane) & 1u;
+            float gq = s.B[c * 28 + lane] * ge;
+            if (gq != 0.0f)
+                NET::grad(plus, s.c_pos[3 * c] + X0, s.c_pos[3 * c + 1] + X1, s.c_pos[3 * c + 2] + X2, gq, acc);
+        }
+    }
+    block_reduce_store<NET::NP>(acc, 0.0f, s.partials + (size_t)row0 * (NET::NP + 1));
+}
+
+template <class NET>
+static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
+    const int sms = sm_count();
+    PointsArgs a;
+    a.s = s;
+    const float sh[7][3] = {{0, 0, 0}, {-s.dx, 0, 0}, {s.dx, 0, 0}, {0, -s.dy, 0}, {0, s.dy, 0}, {0, 0, -s.dz}, {0, 0, s.dz}};
+    for (int q = 0; q < 7; ++q)
+        for (int c = 0; c < 3; ++c) a.shift[q][c] = sh[q][c];
+    a.n_points = (int64_t)s.nx * s.ny * s.nz;
+    int64_t nb = s.p1 - s.p0;
+    int rows_max = s.n_partial_rows;
+    int gridE = 0;
+    if (s.n_crossed > 0) {
+        gridE = (int)min((int64_t)sms, (s.n_crossed * 32 + kThreads - 1) / kThreads);
+        points_extrap_kernel<NET><<<(unsigned)min((int64_t)sms * 4, (s.n_crossed * 32 + kThreads - 1) / kThreads),
+                                    kThreads, 0, st>>>(a);
+    }
+    int gridR = (int)min((int64_t)sms, (nb + kThreads - 1) / kThreads);
+    if (gridR + gridE > rows_max) {
+        set_error("partials buffer has %d rows, %d needed", rows_max, gridR + gridE);
+        return NBM_ERR_WORKSPACE;
+    }
+    points_rows_kernel<NET><<<gridR, kThreads, 0, st>>>(a);
+    if (gridE > 0) points_extrap_bwd_kernel<NET><<<gridE, kThreads, 0, st>>>(a, gridR);
+    reduce_partials_kernel<<<(NET::NP + 1 + 127) / 128, 128, 0, st>>>(s.partials, gridR + gridE, NET::NP + 1,
+                                                                      s.loss_grad);
+    return cuda_check(cudaGetLastError(), "points step launch");
+}
+
+static int dispatch_points(const nbm_points_step_t& s, cudaStream_t st) { NBM_NET_DISPATCH(s.net, launch_points, s, st); }
 
 template <int LP, int HP, int LM, int HM>
 static int launch_eval_impl(const nbm_lvl_t& L, const float* pts, int64_t n, float dx, float dy, float dz, float* u,
@@ -559,6 +769,15 @@ int nbm_upload_params(const nbm_net_t* net, const float* params, nbm_stream_t st
 
 int nbm_step_partial_rows(void) { return kPartialRows; }
 
+int nbm_ffma_probe_f32(int iters, float* out, double* flops_host, nbm_stream_t stream) {
+    NBM_REQUIRE(out && iters > 0, "bad arguments");
+    int blocks = sm_count() * 8;
+    ffma_probe_kernel<<<blocks, 256, 0, as_stream(stream)>>>(iters, out);
+    if (flops_host) *flops_host = 2.0 * 16.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+    NBM_LAUNCH_CHECK("ffma probe");
+    return NBM_OK;
+}
+
 int nbm_loss_grad_shared_f32(const nbm_shared_step_t* s, nbm_stream_t stream) {
     NBM_REQUIRE(s, "null plan");
     NBM_REQUIRE(s->xe && s->ye && s->ze && s->side && s->w && s->rhs, "null tables");
@@ -574,16 +793,25 @@ int nbm_loss_grad_shared_f32(const nbm_shared_step_t* s, nbm_stream_t stream) {
 }
 
 int nbm_loss_grad_points_f32(const nbm_points_step_t* s, nbm_stream_t stream) {
-    (void)s; (void)stream;
-    set_error("general per-point path not built yet");
-    return NBM_ERR_UNSUPPORTED;
+    NBM_REQUIRE(s, "null plan");
+    NBM_REQUIRE(s->xs && s->ys && s->zs && s->side && s->w && s->rhs && s->irr, "null tables");
+    NBM_REQUIRE(s->nx > 0 && s->ny > 0 && s->nz > 0, "empty grid");
+    NBM_REQUIRE(s->p0 >= 0 && s->p1 > s->p0 && s->p1 <= (int64_t)s->nx * s->ny * s->nz, "bad batch range");
+    NBM_REQUIRE(s->dx > 0 && s->dy > 0 && s->dz > 0, "cell size must be positive");
+    NBM_REQUIRE(s->partials && s->loss_grad && s->n_partial_rows >= 2, "null work buffers");
+    NBM_REQUIRE(s->n_crossed == 0 || (s->c_site && s->c_pos && s->c_cube_side && s->B && s->E && s->gE),
+                "null crossed-site tables");
+    NBM_REQUIRE(s->n_irr == 0 || (s->irr_wE && s->irr_c && s->irr_nl && s->irr_nlw), "null irregular-row tables");
+    NBM_REQUIRE((s->nonlinear_m == NBM_NL_NONE && s->nonlinear_p == NBM_NL_NONE) || s->nl,
+                "nonlinear operator needs the nl table");
+    return dispatch_points(*s, as_stream(stream));
 }
 
 int nbm_apply_update_f32(const nbm_optimizer_t* opt, const float* loss_grad, float* params, float* state,
                          int32_t* count, float* loss_hist, nbm_stream_t stream) {
     NBM_REQUIRE(opt && loss_grad && params && state && count, "null pointer");
     NBM_REQUIRE(opt->n_params > 0 && opt->n_params <= NBM_MAXP, "bad parameter count");
-    if (opt->optimizer != 0 && opt->optimizer != 1) {
+    if (opt->optimizer < 0 || opt->optimizer > 2 || opt->scheduler < 0 || opt->scheduler > 1) {
         set_error("unknown optimizer id %d", opt->optimizer);
         return NBM_ERR_UNSUPPORTED;
     }

@@ -157,7 +157,9 @@ def _sample(fn: Callable, pts: torch.Tensor) -> torch.Tensor:
 class CrossedSites:
     """Crossed sites of a lattice: compaction, K1 cut-cell, K2a regression, K2b jump weights."""
 
-    def __init__(self, lvl: LevelSet, lat: cabi.Lattice, n_sites: int, d, fns, dev):
+    def __init__(self, lvl: LevelSet, lat: cabi.Lattice, n_sites: int, d, fns, dev, n_cut_sites: int = None):
+        """`n_cut_sites`: cut-cell geometry is only needed for crossed sites with id < n_cut_sites (the
+        training points themselves); default all."""
         L = cabi.lib()
         st = cabi.stream_ptr()
         dx, dy, dz = d
@@ -193,7 +195,9 @@ class CrossedSites:
         self.beta_gamma = torch.zeros(n1, dtype=torch.float32, device=dev)
         if nc == 0:
             return
-        cabi.check(L.nbm_cutcell_f32(C.byref(lvl.struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.idx), nc,
+        n_cut = nc if n_cut_sites is None else int((self.idx < n_cut_sites).sum().item())
+        self.n_cut = n_cut
+        cabi.check(L.nbm_cutcell_f32(C.byref(lvl.struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.idx), n_cut,
                                      cabi.ptr(self.frac), cabi.ptr(self.tri), cabi.ptr(self.tri_area), st),
                    "nbm_cutcell_f32")
         cabi.check(L.nbm_regression_f32(C.byref(lvl.struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.idx), nc,
@@ -266,25 +270,10 @@ class SharedPlan:
             self.sites = CrossedSites(lvl, lat, ne, self.d, fns, dev)
             cs = self.sites
 
-            # ---- per-point coefficient samples (face centres :533-548, node values :355-356, :403-411)
+            # ---- per-point coefficient samples
             pxs = xs[xa:xb].contiguous()
-            X, Y, Z = torch.meshgrid(pxs, ys, zs, indexing="ij")
-            R = torch.stack((X.reshape(-1), Y.reshape(-1), Z.reshape(-1)), dim=1)
-            del X, Y, Z
             np_ = self.n_points
-            mu_m_faces = torch.empty(6 * np_, dtype=torch.float32, device=dev)
-            mu_p_faces = torch.empty(6 * np_, dtype=torch.float32, device=dev)
-            half = [(-dx, 0, 0), (dx, 0, 0), (0, -dy, 0), (0, dy, 0), (0, 0, -dz), (0, 0, dz)]
-            for f, off in enumerate(half):
-                o = torch.tensor(off, dtype=torch.float32, device=dev) * 0.5
-                Rf = R + o
-                mu_m_faces[f * np_:(f + 1) * np_] = _sample(fns.mu_m_fn, Rf)
-                mu_p_faces[f * np_:(f + 1) * np_] = _sample(fns.mu_p_fn, Rf)
-                del Rf
-            k_m, k_p = _sample(fns.k_m_fn, R), _sample(fns.k_p_fn, R)
-            f_m, f_p = _sample(fns.f_m_fn, R), _sample(fns.f_p_fn, R)
-            g_dir = _sample(fns.dir_bc_fn, R)
-            del R
+            mu_m_faces, mu_p_faces, k_m, k_p, f_m, f_p, g_dir = _point_samples(fns, pxs, ys, zs, self.d, dev)
 
             # ---- K2c row assembly into lattice layout
             use_nl = (nonlinear_m.kind != NL_NONE) or (nonlinear_p.kind != NL_NONE)
@@ -380,3 +369,132 @@ class SharedPlan:
 def upload_params(net: NetShape, params: torch.Tensor) -> None:
     s = net.struct()
     cabi.check(cabi.lib().nbm_upload_params(C.byref(s), cabi.ptr(params), cabi.stream_ptr()), "nbm_upload_params")
+
+
+def _point_samples(fns, xs, ys, zs, d, dev):
+    """coefficient samples every row needs: mu^-/+ at the 6 face centres
+    (geometric_integrations_per_point.py:533-548), k, f, g_D at the point (discretization.py:355-356,
+    :403-411).  Returns ([6][n] mu_m, [6][n] mu_p, k_m, k_p, f_m, f_p, g_dir)."""
+    dx, dy, dz = d
+    X, Y, Z = torch.meshgrid(xs, ys, zs, indexing="ij")
+    R = torch.stack((X.reshape(-1), Y.reshape(-1), Z.reshape(-1)), dim=1)
+    del X, Y, Z
+    n = R.shape[0]
+    mu_m_faces = torch.empty(6 * n, dtype=torch.float32, device=dev)
+    mu_p_faces = torch.empty(6 * n, dtype=torch.float32, device=dev)
+    half = [(-dx, 0, 0), (dx, 0, 0), (0, -dy, 0), (0, dy, 0), (0, 0, -dz), (0, 0, dz)]
+    for f, off in enumerate(half):
+        o = torch.tensor(off, dtype=torch.float32, device=dev) * 0.5
+        Rf = R + o
+        mu_m_faces[f * n:(f + 1) * n] = _sample(fns.mu_m_fn, Rf)
+        mu_p_faces[f * n:(f + 1) * n] = _sample(fns.mu_p_fn, Rf)
+        del Rf
+    out = (mu_m_faces, mu_p_faces, _sample(fns.k_m_fn, R), _sample(fns.k_p_fn, R), _sample(fns.f_m_fn, R),
+           _sample(fns.f_p_fn, R), _sample(fns.dir_bc_fn, R))
+    return out
+
+
+class GeneralLevel:
+    """Row tables of the WHOLE training grid for one cell size d (any zoom level): 7 site lattices
+    (the grid displaced by 0, -+dx, -+dy, -+dz), nothing shared between points."""
+
+    def __init__(self, lvl: LevelSet, tr_gstate, d, fns, net: NetShape, nonlinear_m: Nonlinear,
+                 nonlinear_p: Nonlinear, device=None):
+        dev = torch.device(device if device is not None else lvl.device)
+        self.device, self.net, self.lvl, self.d = dev, net, lvl, tuple(float(v) for v in d)
+        self.nonlinear_m, self.nonlinear_p = nonlinear_m, nonlinear_p
+        L = cabi.lib()
+        with torch.cuda.device(dev):
+            st = cabi.stream_ptr()
+            Nx, Ny, Nz = tr_gstate.shape()
+            self.shape = (Nx, Ny, Nz)
+            N = Nx * Ny * Nz
+            self.n_points = N
+            self.xs, self.ys, self.zs = (a.to(dev).contiguous() for a in (tr_gstate.x, tr_gstate.y, tr_gstate.z))
+            dx, dy, dz = self.d
+            shifts = [(0, 0, 0), (-dx, 0, 0), (dx, 0, 0), (0, -dy, 0), (0, dy, 0), (0, 0, -dz), (0, 0, dz)]
+            lat = _lattice(self.xs, self.ys, self.zs, shifts=shifts)
+            self.sites = CrossedSites(lvl, lat, 7 * N, self.d, fns, dev, n_cut_sites=N)
+            cs = self.sites
+            mu_m_faces, mu_p_faces, k_m, k_p, f_m, f_p, g_dir = _point_samples(fns, self.xs, self.ys, self.zs,
+                                                                               self.d, dev)
+            use_nl = (nonlinear_m.kind != NL_NONE) or (nonlinear_p.kind != NL_NONE)
+            self.w = torch.zeros(7 * N, dtype=torch.float32, device=dev)
+            self.rhs = torch.zeros(N, dtype=torch.float32, device=dev)
+            self.nl = torch.zeros(2 * N, dtype=torch.float32, device=dev) if use_nl else None
+            self.irr = torch.full((N,), -1, dtype=torch.int32, device=dev)
+            cap = min(N, cs.n) + 1
+            irr_count = torch.zeros(1, dtype=torch.int64, device=dev)
+            irr_point = torch.zeros(cap, dtype=torch.int64, device=dev)
+            irr_wE = torch.zeros(cap * 7, dtype=torch.float32, device=dev)
+            irr_c = torch.full((cap * 7,), -1, dtype=torch.int32, device=dev)
+            irr_nl = torch.zeros(cap, dtype=torch.uint8, device=dev)
+            irr_nlw = torch.zeros(cap, dtype=torch.float32, device=dev)
+            a = cabi.Assemble()
+            a.pts = _lattice(self.xs, self.ys, self.zs)
+            a.dx, a.dy, a.dz = dx, dy, dz
+            for i, b in enumerate(lvl.bounds):
+                a.bounds[i] = b
+            a.shared = 0
+            a.site_dims[0], a.site_dims[1], a.site_dims[2] = Nx, Ny, Nz
+            a.flag, a.side, a.cidx = cabi.ptr(cs.flag), cabi.ptr(cs.side), cabi.ptr(cs.cidx)
+            a.frac, a.beta_gamma = cabi.ptr(cs.frac), cabi.ptr(cs.beta_gamma)
+            a.mu_m_faces, a.mu_p_faces = cabi.ptr(mu_m_faces), cabi.ptr(mu_p_faces)
+            a.k_m, a.k_p, a.f_m, a.f_p, a.g_dir = (cabi.ptr(t) for t in (k_m, k_p, f_m, f_p, g_dir))
+            a.w, a.rhs, a.nl, a.irr = cabi.ptr(self.w), cabi.ptr(self.rhs), cabi.ptr(self.nl), cabi.ptr(self.irr)
+            a.n_out = N
+            a.out_stride[0], a.out_stride[1], a.out_stride[2] = Ny * Nz, Nz, 1
+            a.out_off = 0
+            a.irr_capacity = cap
+            a.irr_count, a.irr_point = cabi.ptr(irr_count), cabi.ptr(irr_point)
+            a.irr_wE, a.irr_c, a.irr_nl, a.irr_nlw = (cabi.ptr(t) for t in (irr_wE, irr_c, irr_nl, irr_nlw))
+            cabi.check(L.nbm_assemble_f32(C.byref(a), st), "nbm_assemble_f32")
+            n_irr = int(irr_count.item())
+            if n_irr > cap:
+                raise cabi.NbmError(f"irregular-row capacity exceeded ({n_irr} > {cap})")
+            self.n_irr = n_irr
+            m = max(n_irr, 1)
+            self.irr_wE, self.irr_c = irr_wE[:m * 7].clone(), irr_c[:m * 7].clone()
+            self.irr_nl, self.irr_nlw = irr_nl[:m].clone(), irr_nlw[:m].clone()
+            self.E = torch.zeros(max(cs.n, 1), dtype=torch.float32, device=dev)
+            self.gE = torch.zeros(max(cs.n, 1), dtype=torch.float32, device=dev)
+            rows = L.nbm_step_partial_rows()
+            self.rows = rows
+            self.partials = torch.zeros(rows * (net.n_params + 1), dtype=torch.float32, device=dev)
+
+
+class PointsPlan:
+    """General path for the contiguous batch [p0, p1) of the flattened training points at the cell
+    size of `level`."""
+
+    def __init__(self, level: GeneralLevel, p0: int, p1: int, n_mean: Optional[int] = None):
+        self.level, self.p0, self.p1 = level, int(p0), int(p1)
+        self.device = level.device
+        self.n_points = self.p1 - self.p0
+        net, cs = level.net, level.sites
+        self.loss_grad = torch.zeros(net.n_params + 1, dtype=torch.float32, device=level.device)
+        s = cabi.PointsStep()
+        s.net = net.struct()
+        s.nonlinear_m, s.nonlinear_p = level.nonlinear_m.kind, level.nonlinear_p.kind
+        s.nl_coef_m, s.nl_coef_p = level.nonlinear_m.coef, level.nonlinear_p.coef
+        s.xs, s.ys, s.zs = cabi.ptr(level.xs), cabi.ptr(level.ys), cabi.ptr(level.zs)
+        s.nx, s.ny, s.nz = level.shape
+        s.p0, s.p1 = self.p0, self.p1
+        s.dx, s.dy, s.dz = level.d
+        s.side, s.w, s.rhs, s.nl, s.irr = (cabi.ptr(t) for t in (cs.side, level.w, level.rhs, level.nl, level.irr))
+        s.n_crossed, s.c_site, s.c_pos = cs.n, cabi.ptr(cs.idx), cabi.ptr(cs.pos)
+        s.c_cube_side, s.B = cabi.ptr(cs.cube_side), cabi.ptr(cs.B)
+        s.n_irr = level.n_irr
+        s.irr_wE, s.irr_c, s.irr_nl, s.irr_nlw = (cabi.ptr(t) for t in (level.irr_wE, level.irr_c, level.irr_nl,
+                                                                        level.irr_nlw))
+        s.inv_n_points = 1.0 / float(n_mean if n_mean is not None else self.n_points)
+        s.E, s.gE = cabi.ptr(level.E), cabi.ptr(level.gE)
+        s.partials, s.n_partial_rows, s.loss_grad = cabi.ptr(level.partials), level.rows, cabi.ptr(self.loss_grad)
+        self.step = s
+
+    def loss_grad_launch(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is not None:
+            self.step.loss_grad = cabi.ptr(out)
+        cabi.check(cabi.lib().nbm_loss_grad_points_f32(C.byref(self.step), cabi.stream_ptr()),
+                   "nbm_loss_grad_points_f32")
+        return out if out is not None else self.loss_grad

@@ -1,0 +1,477 @@
+"""Drop-in for `jax_dips.solvers.poisson.trainer`: `setup -> init_fn -> solve_fn` with the same
+names, keyword arguments, defaults, dict schemas and return shapes (trainer.py:980-1137), running
+the NBM step on hand-written sm_100a CUDA kernels through the C ABI in include/nbm_b200.h.
+
+Differences a user of the reference must know (all documented in DESIGN.md):
+
+* coefficient callables are the reference's per-point callables written against
+  `jax_dips_b200.numpy` (torch) instead of `jax.numpy`; they are batched by calling them once on
+  the (3, n) view of the point list (the role `vmap` plays at trainer.py:995-1005);
+* the level set is sampled once on `lvl_gstate` and read by the kernels through the reference's
+  own grid interpolant (`phi_interp="trilinear"`: interpolate.py:906, `"quadratic"`: :388) - the
+  configuration examples/dragon uses (solve_dragon.py:177);
+* `nonlinear_op_m/p` must be None / zero / `Nonlinear.sinh(coef)`;
+* the initial parameters follow haiku's initialisers (TruncatedNormal(0.1) hidden, 1/sqrt(fan_in)
+  output, zero bias; MLP.py:65,70) but are drawn from a torch generator seeded with 42, because
+  jax's PRNGKey(42) stream cannot be reproduced without jax; pass `init_params=` to pin them;
+* multi-GPU = one process per GPU (`torchrun`), gradient `psum` = NCCL all-reduce(SUM) of the
+  168-float [grad, loss] buffer (trainer.py:829-830);
+* only `algorithm=0`, `model_type="mlp"`, optimizers "custom" / "adam" / "rmsprop" exist on this
+  path; everything else raises the reference's exception types.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import math
+import os
+import pickle
+import signal
+import time
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi as cabi
+from . import data_management
+from . import numpy as jnp
+from .optimizers import OptimizerSpec, get_optimizer
+from .plan import GeneralLevel, LevelSet, NetShape, Nonlinear, PointsPlan, SharedPlan, upload_params
+from .simulation_states import PoissonSimState, PoissonSimStateFn, replace
+
+logger = logging.getLogger(__name__)
+
+stop_training = False
+
+
+def signalHandler(signal_num, frame):
+    """trainer.py:68-78: SIGINT asks the multi-GPU loop to stop after the current epoch."""
+    global stop_training
+    stop_training = True
+    logger.warning("Signal: %s. Training will stop after the completion of current epoch", signal_num)
+
+
+def install_sigint_handler():
+    signal.signal(signal.SIGINT, signalHandler)
+
+
+_DEFAULT_OPT = {"optimizer_name": "custom", "learning_rate": 1e-3,
+                "sched": {"scheduler_name": "exponential", "decay_rate": 0.9}}
+_DEFAULT_MODEL = {
+    "name": None, "model_type": "mlp",
+    "mlp": {"hidden_layers_m": 1, "hidden_dim_m": 1, "activation_m": "jnp.tanh",
+            "hidden_layers_p": 2, "hidden_dim_p": 10, "activation_p": "jnp.tanh"},
+    "resnet": {"res_blocks_m": 3, "res_dim_m": 40, "activation_m": "nn.tanh",
+               "res_blocks_p": 3, "res_dim_p": 80, "activation_p": "nn.tanh"},
+}
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+def default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise cabi.NbmError("no CUDA device: the NBM path runs only on the GPU (no CPU fallback)")
+    return torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count())
+
+
+def haiku_init(net: NetShape, seed: int = 42) -> torch.Tensor:
+    """Flat parameter vector, C-ABI order (p head then m head; W (in,out) row-major then b)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def trunc(n, std):
+        out = torch.empty(n, dtype=torch.float64)
+        torch.nn.init.trunc_normal_(out, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=g)
+        return out * std
+
+    parts = []
+    for (L, H) in ((net.layers_p, net.hidden_p), (net.layers_m, net.hidden_m)):
+        fan_in = 3
+        for _ in range(L):
+            parts += [trunc(fan_in * H, 0.1), torch.zeros(H, dtype=torch.float64)]
+            fan_in = H
+        parts += [trunc(fan_in, 1.0 / math.sqrt(fan_in)), torch.zeros(1, dtype=torch.float64)]
+    return torch.cat(parts).to(torch.float32)
+
+
+def params_to_tree(net: NetShape, flat: torch.Tensor) -> dict:
+    """haiku-style parameter tree (keys as the reference's checkpoints hold them, cf. trainer.py:323)."""
+    flat = flat.detach().cpu().numpy()
+    tree, off = {}, 0
+    for head, (L, H) in (("p", (net.layers_p, net.hidden_p)), ("m", (net.layers_m, net.hidden_m))):
+        fan_in = 3
+        for l in range(L + 1):
+            out = H if l < L else 1
+            name = f"double_mlp/~mlp_{head}_fn/linear" + ("" if l == 0 else f"_{l}")
+            w = flat[off: off + fan_in * out].reshape(fan_in, out).copy(); off += fan_in * out
+            b = flat[off: off + out].copy(); off += out
+            tree[name] = {"w": w, "b": b}
+            fan_in = out
+    tree["preconditioner"] = {}
+    return tree
+
+
+def tree_to_params(net: NetShape, tree: dict) -> torch.Tensor:
+    parts = []
+    for head, (L, H) in (("p", (net.layers_p, net.hidden_p)), ("m", (net.layers_m, net.hidden_m))):
+        for l in range(L + 1):
+            name = f"double_mlp/~mlp_{head}_fn/linear" + ("" if l == 0 else f"_{l}")
+            parts += [np.asarray(tree[name]["w"], dtype=np.float32).reshape(-1),
+                      np.asarray(tree[name]["b"], dtype=np.float32).reshape(-1)]
+    return torch.from_numpy(np.concatenate(parts))
+
+
+class Trainer:
+    """Trainer for the NBM Poisson solver (trainer.py:81-977): owns the level set, the per-level
+    plans (row tables in HBM), the parameters, the optimizer state and the training loops."""
+
+    def __init__(self, lvl_gstate, tr_gstate, eval_gstate, sim_state: PoissonSimState,
+                 sim_state_fn: PoissonSimStateFn, algorithm: int = 0, mgrad_over_pgrad_scalefactor: int = 1,
+                 lvl_set_fn: Callable = None, num_epochs: int = 1000, multi_gpu: bool = False,
+                 batch_size: int = 131072, checkpoint_dir: str = "./checkpoints", checkpoint_interval: int = 2,
+                 results_dir: str = "./", loss_plot_name: str = "solver_loss", optimizer_dict: dict = None,
+                 restart: bool = False, restart_checkpoint_dir: str = "./checkpoints", print_rate: int = 1,
+                 model_dict: dict = None, phi_interp: str = "trilinear", perturb_eps: float = 1e-10,
+                 device=None, init_params: Optional[torch.Tensor] = None, use_cuda_graph: bool = True):
+        global stop_training
+        if algorithm != 0:
+            # discretization.py:146-148 references undefined attributes for algorithm=1
+            raise NotImplementedError("only algorithm=0 (regression extrapolation) exists on this path")
+        optimizer_dict = optimizer_dict or _DEFAULT_OPT
+        model_dict = model_dict or _DEFAULT_MODEL
+        self.device = torch.device(device) if device is not None else default_device()
+        self.lvl_gstate, self.tr_gstate, self.eval_gstate = lvl_gstate, tr_gstate, eval_gstate
+        self.sim_state, self.sim_state_fn = sim_state, sim_state_fn
+        self.batch_size, self.num_epochs, self.multi_gpu = batch_size, num_epochs, multi_gpu
+        self.checkpoint_dir, self.checkpoint_interval = checkpoint_dir, checkpoint_interval
+        self.results_dir, self.loss_plot_name, self.print_rate = results_dir, loss_plot_name, print_rate
+        self.mgrad_over_pgrad_scalefactor = mgrad_over_pgrad_scalefactor
+        self.restart_checkpoint_dir = restart_checkpoint_dir
+        self.use_cuda_graph = use_cuda_graph
+        cabi.lib()  # fail here, loudly, if the CUDA library is not built
+
+        self.TD = data_management.TrainData(tr_gstate, lvl_set_fn, refine=False, refine_lod=False,
+                                            refine_normals=False, v_cycle_period=2, rest_at_level=100)
+        self.train_dx, self.train_dy, self.train_dz = (float(tr_gstate.dx), float(tr_gstate.dy), float(tr_gstate.dz))
+
+        self.net = NetShape.from_model_dict(model_dict)
+        if model_dict.get("preconditioner", {"enable": False}).get("enable", False):
+            raise NotImplementedError("the learned preconditioner (nn/preconditioner.py) is not on this path yet")
+        self.nonlinear_m = Nonlinear.coerce(sim_state_fn.nonlinear_op_m)
+        self.nonlinear_p = Nonlinear.coerce(sim_state_fn.nonlinear_op_p)
+
+        name = optimizer_dict["optimizer_name"]
+        if name == "lbfgs":
+            raise NotImplementedError("the jaxopt L-BFGS driver (trainer.py:354-427) is outside this path")
+        self.optimizer: OptimizerSpec = get_optimizer(
+            optimizer_name=name, scheduler_name=optimizer_dict["sched"]["scheduler_name"],
+            learning_rate=optimizer_dict["learning_rate"], decay_rate=optimizer_dict["sched"]["decay_rate"])
+
+        with torch.cuda.device(self.device):
+            # level set on the lvl grid, read by the kernels through the reference's interpolant
+            phi_lvl = sim_state_fn.phi_fn(lvl_gstate.R.to(self.device))
+            self.lvl = LevelSet(lvl_gstate, phi_lvl, interp=phi_interp, perturb_eps=perturb_eps, device=self.device)
+            P = self.net.n_params
+            self.opt_state = torch.zeros(2 * P, dtype=torch.float32, device=self.device)
+            self.opt_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+            if restart:
+                state = self.fetch_checkpoint(self.restart_checkpoint_dir)
+                if state is None:
+                    raise FileNotFoundError(f"no checkpoint under {self.restart_checkpoint_dir}")
+                self.params = tree_to_params(self.net, state["params"]).to(self.device)
+                self.opt_state.copy_(torch.as_tensor(state["opt_state"]["moments"]).to(self.device))
+                self.opt_count.fill_(int(state["opt_state"]["count"]))
+                self.batch_size = state["batch_size"]
+                logger.info(f"Resuming training from epoch {state['epoch']} with batch_size {self.batch_size}, "
+                            f"resolution {state['resolution']}.")
+            else:
+                p0 = init_params if init_params is not None else haiku_init(self.net, seed=42)
+                if p0.numel() != P:
+                    raise ValueError(f"init_params has {p0.numel()} entries, the network has {P}")
+                self.params = p0.detach().to(self.device, torch.float32).contiguous().clone()
+        self.epoch_start = 0  # trainer.py:261 (resume = warm start only)
+        self.loss_epochs = torch.zeros(self.num_epochs - self.epoch_start)
+        self.epoch_store = np.arange(self.epoch_start, self.num_epochs)
+        self._plans = {}
+        self._levels = {}
+        self._graphs = {}
+        self._opt_struct = None
+
+    # ------------------------------------------------------------------------------------------
+    # checkpoints (trainer.py:325-351): same dict keys
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def fetch_checkpoint(checkpoint_dir):
+        if checkpoint_dir is None or not os.path.exists(checkpoint_dir):
+            return None
+        checkpoints = [p for p in os.listdir(checkpoint_dir) if "checkpoint_" in p]
+        if not checkpoints:
+            return None
+        # the reference takes the lexicographic max (trainer.py:331-334); numeric max is what is meant
+        checkpoint = os.path.join(checkpoint_dir, max(checkpoints, key=lambda p: int(p.split("_")[-1])))
+        logger.info(f"Loading checkpoint {checkpoint}")
+        with open(checkpoint, "rb") as f:
+            return pickle.load(f)
+
+    @staticmethod
+    def save_checkpoint(checkpoint_dir, state):
+        if checkpoint_dir is None:
+            logger.info("No checkpoint dir. specified. Skipping checkpoint.")
+            return None
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        checkpoint = os.path.join(checkpoint_dir, "checkpoint_" + str(state["epoch"]))
+        logger.info(f"Saving checkpoint {checkpoint}")
+        with open(checkpoint, "wb") as f:
+            pickle.dump(state, f)
+        return checkpoint
+
+    def _checkpoint_state(self, epoch: int) -> dict:
+        return {"opt_state": {"moments": self.opt_state.cpu().numpy(), "count": int(self.opt_count.item())},
+                "params": params_to_tree(self.net, self.params), "epoch": epoch, "batch_size": self.batch_size,
+                "resolution": f"{self.train_dx}, {self.train_dy}, {self.train_dz}"}
+
+    # ------------------------------------------------------------------------------------------
+    # plans: one per (zoom level, batch range); built lazily, kept in HBM
+    # ------------------------------------------------------------------------------------------
+    def plan_for(self, zoom: int, p0: int, p1: int):
+        key = (zoom, p0, p1)
+        if key in self._plans:
+            return self._plans[key]
+        Nx, Ny, Nz = self.tr_gstate.shape()
+        plane = Ny * Nz
+        with torch.cuda.device(self.device):
+            if zoom == 0 and p0 % plane == 0 and p1 % plane == 0:
+                pl = SharedPlan(self.lvl, self.tr_gstate, p0 // plane, p1 // plane, self.sim_state_fn, self.net,
+                                self.nonlinear_m, self.nonlinear_p, device=self.device)
+            else:
+                pl = PointsPlan(self.general_level(zoom), p0, p1)
+        self._plans[key] = pl
+        return pl
+
+    def general_level(self, zoom: int) -> GeneralLevel:
+        if zoom not in self._levels:
+            with torch.cuda.device(self.device):
+                self._levels[zoom] = GeneralLevel(self.lvl, self.tr_gstate, self.TD.zoom_cell(zoom), self.sim_state_fn,
+                                                  self.net, self.nonlinear_m, self.nonlinear_p, device=self.device)
+        return self._levels[zoom]
+
+    def _optimizer_struct(self) -> cabi.Optimizer:
+        if self._opt_struct is None:
+            o, s = self.optimizer, self.optimizer.scheduler
+            self._opt_struct = cabi.Optimizer(self.net.n_params, float(o.learning_rate), float(s.decay_rate),
+                                              float(s.transition_steps), float(o.max_norm), o.b1,
+                                              0.9 if o.optimizer_name == "rmsprop" else o.b2, o.eps, o.kind,
+                                              0 if s.scheduler_name == "exponential" else 1)
+        return self._opt_struct
+
+    # ------------------------------------------------------------------------------------------
+    # the operator seam: loss and d loss/d params (Trainer.loss + value_and_grad, trainer.py:786, 893)
+    # ------------------------------------------------------------------------------------------
+    def loss_and_grad(self, params: torch.Tensor, plan) -> torch.Tensor:
+        """[grad(P), loss] on the device for the rows of `plan` (enqueued on the current stream)."""
+        upload_params(self.net, params)
+        return plan.loss_grad_launch()
+
+    def _step(self, plan, loss_hist: Optional[torch.Tensor], allreduce: bool):
+        """update (trainer.py:783-789) / update_multi_gpu (:824-834) on the current stream"""
+        lg = self.loss_and_grad(self.params, plan)
+        if allreduce:
+            d = _dist()
+            if d is not None and d.get_world_size() > 1:
+                d.all_reduce(lg, op=d.ReduceOp.SUM)      # psum of grads and loss (:829-830)
+        cabi.check(cabi.lib().nbm_apply_update_f32(C.byref(self._optimizer_struct()), cabi.ptr(lg),
+                                                   cabi.ptr(self.params), cabi.ptr(self.opt_state),
+                                                   cabi.ptr(self.opt_count), cabi.ptr(loss_hist),
+                                                   cabi.stream_ptr()), "nbm_apply_update_f32")
+
+    def _graph_step(self, plan, loss_hist, allreduce: bool):
+        """replay the step as a CUDA graph (launch-bound at small grids)"""
+        if not self.use_cuda_graph or allreduce:
+            return self._step(plan, loss_hist, allreduce)
+        key = (id(plan), loss_hist.data_ptr() if loss_hist is not None else 0)
+        g = self._graphs.get(key)
+        if g is None:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                # warm-up outside capture on scratch copies would change the state: capture directly
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    self._step(plan, loss_hist, False)
+            torch.cuda.current_stream().wait_stream(side)
+            self._graphs[key] = g
+            # the capture itself does not execute the step
+        g.replay()
+
+    # ------------------------------------------------------------------------------------------
+    # training loops
+    # ------------------------------------------------------------------------------------------
+    def solve_optax(self):
+        start_time = time.time()
+        if self.multi_gpu:
+            self.epoch_store, self.loss_epochs = self.multi_GPU_train()
+        else:
+            self.epoch_store, self.loss_epochs = self.single_GPU_train()
+        torch.cuda.synchronize(self.device)
+        logger.info(f"solve took {time.time() - start_time} (sec)")
+        d = _dist()
+        if d is None or d.get_rank() == 0:
+            self.save_checkpoint(self.checkpoint_dir, self._checkpoint_state(int(self.epoch_store[-1]) + 1))
+        final_solution, grad_u, grad_u_normal = self.evaluate_solution_and_gradients(self.params, self.eval_gstate)
+        return final_solution, grad_u, grad_u_normal, self.epoch_store, self.loss_epochs
+
+    solve = solve_optax
+
+    def single_GPU_train(self):
+        """trainer.py:501-591: epochs x batches, cell size halves every num_epochs//4 epochs
+        (data_management.py:320-326), loss_epochs[e] = mean over batches of the batch losses."""
+        DD = data_management.DatasetDict(num_points=self.tr_gstate.num_points(), batch_size=self.batch_size)
+        ranges = DD.ranges(0)
+        nb = len(ranges)
+        with torch.cuda.device(self.device):
+            loss_hist = torch.zeros(self.num_epochs * nb + 1, dtype=torch.float32, device=self.device)
+            base = int(self.opt_count.item())
+            hist = loss_hist if base == 0 else None
+            per_step = [] if hist is None else None
+            for epoch in range(self.num_epochs):
+                zoom = self.TD.zoom_level(self.num_epochs, epoch)
+                for (p0, p1) in ranges:
+                    plan = self.plan_for(zoom, p0, p1)
+                    self._graph_step(plan, hist, allreduce=False)
+                    if per_step is not None:
+                        per_step.append(plan.loss_grad[-1:].clone())
+                if self.print_rate and epoch % self.print_rate == 0 and logger.isEnabledFor(logging.INFO):
+                    logger.info(f"epoch # {epoch}")
+            torch.cuda.synchronize(self.device)
+            if hist is not None:
+                losses = hist[: self.num_epochs * nb].view(self.num_epochs, nb).mean(dim=1).cpu()
+            else:
+                losses = torch.cat(per_step).view(self.num_epochs, nb).mean(dim=1).cpu()
+        return np.arange(self.epoch_start, self.num_epochs), losses
+
+    def multi_GPU_train(self):
+        """trainer.py:715-779: one process per GPU; the points are split in contiguous blocks
+        (x-slabs, data_management.py:121-130), no multi-resolution schedule, grads and loss are
+        SUMMED over devices (:829-830) and every rank applies the identical update."""
+        global stop_training
+        d = _dist()
+        world = d.get_world_size() if d is not None else 1
+        rank = d.get_rank() if d is not None else 0
+        DD = data_management.DatasetDict(num_points=self.tr_gstate.num_points(), batch_size=world * self.batch_size,
+                                         num_gpus=world)
+        ranges = DD.ranges(rank)
+        nb = len(ranges)
+        loss_epochs, epoch_store = [], []
+        t0 = time.time()
+        with torch.cuda.device(self.device):
+            loss_hist = torch.zeros(self.num_epochs * nb + 1, dtype=torch.float32, device=self.device)
+            base = int(self.opt_count.item())
+            for epoch in range(self.epoch_start, self.num_epochs):
+                if stop_training:
+                    break
+                for (p0, p1) in ranges:
+                    plan = self.plan_for(0, p0, p1)
+                    self._step(plan, loss_hist if base == 0 else None, allreduce=True)
+                epoch_store.append(epoch)
+                if self.print_rate and epoch % self.print_rate == 0 and logger.isEnabledFor(logging.INFO):
+                    dt_avg = (time.time() - t0) / self.print_rate
+                    t0 = time.time()
+                    logger.info(f"Epoch # {epoch} \t avg epoch time is {dt_avg} (sec)")
+                if (epoch + 1) % self.checkpoint_interval == 0 and rank == 0:
+                    self.save_checkpoint(self.checkpoint_dir, self._checkpoint_state(epoch + 1))
+            torch.cuda.synchronize(self.device)
+            n_done = len(epoch_store)
+            per_epoch = loss_hist[: n_done * nb].view(n_done, nb).mean(dim=1).cpu()
+        # the reference returns a list of per-device arrays (all entries equal after the psum)
+        loss_epochs = [per_epoch[e].repeat(world) for e in range(n_done)]
+        return epoch_store, loss_epochs
+
+    # ------------------------------------------------------------------------------------------
+    # post-training evaluation (trainer.py:960-977)
+    # ------------------------------------------------------------------------------------------
+    def evaluate_solution_and_gradients(self, params: torch.Tensor, eval_gstate, chunk: int = 1 << 24):
+        L = cabi.lib()
+        n = eval_gstate.num_points()
+        net = self.net.struct()
+        with torch.cuda.device(self.device):
+            upload_params(self.net, params.to(self.device))
+            u = torch.empty(n, dtype=torch.float32, device=self.device)
+            gu = torch.empty(n * 3, dtype=torch.float32, device=self.device)
+            gn = torch.empty(n, dtype=torch.float32, device=self.device)
+            R = eval_gstate.R
+            dx, dy, dz = float(eval_gstate.dx), float(eval_gstate.dy), float(eval_gstate.dz)
+            for s in range(0, n, chunk):
+                e = min(n, s + chunk)
+                pts = R[s:e].to(self.device).contiguous()
+                cabi.check(L.nbm_evaluate_f32(C.byref(net), C.byref(self.lvl.struct), cabi.ptr(pts), e - s, dx, dy, dz,
+                                              u[s:].data_ptr(), gu[3 * s:].data_ptr(), gn[s:].data_ptr(),
+                                              cabi.stream_ptr()), "nbm_evaluate_f32")
+                torch.cuda.current_stream().synchronize()
+        return u, gu.view(n, 3), gn
+
+    def evaluate_solution_fn(self, params: torch.Tensor, R_flat: torch.Tensor) -> torch.Tensor:
+        """trainer.py:836-844"""
+        L = cabi.lib()
+        net = self.net.struct()
+        with torch.cuda.device(self.device):
+            upload_params(self.net, params.to(self.device))
+            pts = R_flat.to(self.device, torch.float32).contiguous()
+            u = torch.empty(pts.shape[0], dtype=torch.float32, device=self.device)
+            cabi.check(L.nbm_evaluate_f32(C.byref(net), C.byref(self.lvl.struct), cabi.ptr(pts), pts.shape[0], 1.0, 1.0,
+                                          1.0, cabi.ptr(u), None, None, cabi.stream_ptr()), "nbm_evaluate_f32")
+        return u
+
+
+def setup(initial_value_fn, dirichlet_bc_fn, lvl_set_fn, mu_m_fn_, mu_p_fn_, k_m_fn_, k_p_fn_, f_m_fn_, f_p_fn_,
+          alpha_fn_, beta_fn_, nonlinear_op_m=None, nonlinear_op_p=None):
+    """trainer.py:980-1137.  Returns `init_fn`."""
+    v = jnp.vmap
+    u_0_fn, dir_bc_fn, phi_fn = v(initial_value_fn), v(dirichlet_bc_fn), v(lvl_set_fn)
+    mu_m_fn, mu_p_fn, k_m_fn, k_p_fn = v(mu_m_fn_), v(mu_p_fn_), v(k_m_fn_), v(k_p_fn_)
+    f_m_fn, f_p_fn, alpha_fn, beta_fn = v(f_m_fn_), v(f_p_fn_), v(alpha_fn_), v(beta_fn_)
+    if nonlinear_op_m is None:
+        logger.warning("nonlinear_op_m(u) is not defined. Setting it to zero.")
+    if nonlinear_op_p is None:
+        logger.warning("nonlinear_op_m(u) is not defined. Setting it to zero.")
+    nonlinear_op_m = Nonlinear.coerce(nonlinear_op_m)
+    nonlinear_op_p = Nonlinear.coerce(nonlinear_op_p)
+    sim_state_fn = PoissonSimStateFn(u_0_fn, dir_bc_fn, phi_fn, mu_m_fn, mu_p_fn, k_m_fn, k_p_fn, f_m_fn, f_p_fn,
+                                     alpha_fn, beta_fn, nonlinear_op_m, nonlinear_op_p)
+
+    def init_fn(lvl_gstate=None, tr_gstate=None, eval_gstate=None, num_epochs: int = 1000, batch_size: int = 131072,
+                algorithm: int = 0, mgrad_over_pgrad_scalefactor: int = 1, multi_gpu: bool = False,
+                checkpoint_interval: int = 1000, checkpoint_dir: str = "./checkpoints", results_dir: str = "./",
+                loss_plot_name: str = "solver_loss", optimizer_dict: dict = None, model_dict: dict = None,
+                restart: bool = False, restart_checkpoint_dir: str = "./checkpoints", print_rate: int = 1,
+                **extensions) -> Tuple[PoissonSimState, Callable]:
+        """`extensions` (not in the reference): phi_interp, perturb_eps, device, init_params, use_cuda_graph."""
+        device = torch.device(extensions["device"]) if extensions.get("device") is not None else default_device()
+        optimizer_dict = optimizer_dict or {"optimizer_name": "custom", "learning_rate": 1e-3,
+                                            "sched": {"scheduler_name": "exponential", "decay_rate": 0.9}}
+        model_dict = model_dict or _DEFAULT_MODEL
+        with torch.cuda.device(device):
+            R = eval_gstate.R.to(device)
+            PHI, DIRBC, U = phi_fn(R), dir_bc_fn(R), u_0_fn(R)
+            MU_M, MU_P, K_M, K_P = mu_m_fn(R), mu_p_fn(R), k_m_fn(R), k_p_fn(R)
+            F_M, F_P, ALPHA, BETA = f_m_fn(R), f_p_fn(R), alpha_fn(R), beta_fn(R)
+            del R
+
+        def solve_fn(sim_state: PoissonSimState):
+            trainer = Trainer(lvl_gstate, tr_gstate, eval_gstate, sim_state, sim_state_fn, algorithm,
+                              mgrad_over_pgrad_scalefactor=mgrad_over_pgrad_scalefactor, lvl_set_fn=lvl_set_fn,
+                              num_epochs=num_epochs, multi_gpu=multi_gpu, batch_size=batch_size,
+                              checkpoint_dir=checkpoint_dir, checkpoint_interval=checkpoint_interval,
+                              results_dir=results_dir, loss_plot_name=loss_plot_name, optimizer_dict=optimizer_dict,
+                              restart=restart, restart_checkpoint_dir=restart_checkpoint_dir, print_rate=print_rate,
+                              model_dict=model_dict, **extensions)
+            solve_fn.trainer = trainer
+            final_solution, grad_u, grad_u_normal_to_interface, epoch_store, loss_epochs = trainer.solve()
+            return (replace(sim_state, solution=final_solution, grad_solution=grad_u,
+                            grad_normal_solution=grad_u_normal_to_interface), epoch_store, loss_epochs)
+
+        return (PoissonSimState(PHI, U, DIRBC, MU_M, MU_P, K_M, K_P, F_M, F_P, ALPHA, BETA, None, None), solve_fn)
+
+    return init_fn
