@@ -13,7 +13,11 @@
 namespace nbm {
 
 #define NBM_MAXP 1024
-__constant__ float c_P[NBM_MAXP];
+// [0, MAXP): the parameters; [MAXP, 2*MAXP): the same with the hidden layers' W and b multiplied
+// by 2*log2(e), so that the forward pass feeds ex2 directly (tanh(s) = 1 - 2/(2^(2 log2e s) + 1)).
+__constant__ __align__(16) float c_P[2 * NBM_MAXP];
+__device__ __align__(16) float g_stage[2 * NBM_MAXP];
+constexpr float kTwoLog2e = 2.8853900817779268f;
 
 constexpr int kThreads = 256;
 
@@ -61,10 +65,12 @@ struct Mlp {
     }
 
     // acc[OFF..OFF+NP) += g * d u / d theta
-    template <int OFF, int NTOT>
+    // acc[k] accumulates parameter (BASE + k); OFF is the head's offset in the constant bank
+    template <int OFF, int NTOT, int BASE>
     __device__ __forceinline__ static void backward(float x, float y, float z, const float (&a)[L][H], float g,
-                                                    float (&acc)[NTOT]) {
+                                                    float (&acc_)[NTOT]) {
         const int oo = OFF + 4 * H + (L - 1) * (H * H + H);
+        float* acc = acc_ - BASE;  // compile-time indices after unrolling: stays in registers
         float d[H];
 #pragma unroll
         for (int i = 0; i < H; ++i) {
@@ -130,31 +136,200 @@ struct Mlp {
     }
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2, sm_100+).  Measured on B200 (tools/microbench.cu):
+// FFMA2 retires the same 128 lane-FMAs/clk/SM as FFMA but takes half the issue slots, which lets the
+// MUFU (ex2, rcp) and load instructions co-issue for free.  Pairs run along the FEATURE index
+// (j, j+1): weights W[i][j], W[i][j+1] are adjacent in the (in,out) row-major layout and reach the
+// FFMA2 straight from the constant bank through a uniform register pair.
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo32(u64 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float hi32(u64 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 neg2(u64 a) { return a ^ 0x8000000080000000ull; }
+__device__ __forceinline__ u64 cpair(int idx) { return *reinterpret_cast<const u64*>(&c_P[idx]); }
+
+// two tanh for the price of 3 MUFU: t = 1 - 2/(e+1) with ONE reciprocal of (e0+1)(e1+1).
+// Input is the PRE-SCALED pre-activation s' = 2 log2(e) s.  Clamped at 63 so the product stays finite
+// (tanh is 1 to the last bit far below that).
+__device__ __forceinline__ u64 tanh2_prescaled(u64 sp) {
+    float s0 = fminf(lo32(sp), 63.0f), s1 = fminf(hi32(sp), 63.0f);
+    float e0, e1, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
+    u64 a = fadd2(pk(e0, e1), pk(1.0f, 1.0f));
+    float a0 = lo32(a), a1 = hi32(a);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a0 * a1));
+    return ffma2(pk(-2.0f, -2.0f), pk(r * a1, r * a0), pk(1.0f, 1.0f));
+}
+
+// Packed head: H even, OFF even.  Accumulators are pairs: accp[k] = (grad[2k], grad[2k+1]).
+template <int L, int H>
+struct MlpP {
+    static_assert(H % 2 == 0, "packed head needs an even width");
+    static constexpr int NP = 3 * H + H + (L - 1) * (H * H + H) + H + 1;
+    static constexpr int NPAIR = (NP + 1) / 2;
+    static constexpr int HP = H / 2;
+
+    template <int OFF>
+    __device__ __forceinline__ static float forward(float x, float y, float z, u64 (&a)[L][HP]) {
+        constexpr int S = NBM_MAXP + OFF;  // pre-scaled copy
+        const u64 x2 = pk(x, x), y2 = pk(y, y), z2 = pk(z, z);
+#pragma unroll
+        for (int j = 0; j < HP; ++j) {
+            u64 s = cpair(S + 3 * H + 2 * j);
+            s = ffma2(x2, cpair(S + 2 * j), s);
+            s = ffma2(y2, cpair(S + H + 2 * j), s);
+            s = ffma2(z2, cpair(S + 2 * H + 2 * j), s);
+            a[0][j] = tanh2_prescaled(s);
+        }
+#pragma unroll
+        for (int l = 1; l < L; ++l) {
+            const int o = S + 4 * H + (l - 1) * (H * H + H);
+            u64 acc[HP];
+#pragma unroll
+            for (int j = 0; j < HP; ++j) acc[j] = cpair(o + H * H + 2 * j);
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                float ai = (i & 1) ? hi32(a[l - 1][i / 2]) : lo32(a[l - 1][i / 2]);
+                u64 ai2 = pk(ai, ai);
+#pragma unroll
+                for (int j = 0; j < HP; ++j) acc[j] = ffma2(ai2, cpair(o + i * H + 2 * j), acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < HP; ++j) a[l][j] = tanh2_prescaled(acc[j]);
+        }
+        const int oo = OFF + 4 * H + (L - 1) * (H * H + H);  // output layer: unscaled copy
+        u64 o2 = pk(c_P[oo + H], 0.0f);
+#pragma unroll
+        for (int j = 0; j < HP; ++j) o2 = ffma2(a[L - 1][j], cpair(oo + 2 * j), o2);
+        return lo32(o2) + hi32(o2);
+    }
+
+    template <int OFF>
+    __device__ __forceinline__ static void backward(float x, float y, float z, const u64 (&a)[L][HP], float g,
+                                                    u64 (&acc)[NPAIR]) {
+        static_assert(OFF == 0, "packed accumulators are indexed from the head's own origin");
+        const int oo = 4 * H + (L - 1) * (H * H + H);
+        const u64 one = pk(1.0f, 1.0f);
+        const u64 g2 = pk(g, g);
+        u64 d[HP];
+#pragma unroll
+        for (int j = 0; j < HP; ++j) {
+            acc[(oo + 2 * j) / 2] = ffma2(a[L - 1][j], g2, acc[(oo + 2 * j) / 2]);
+            u64 om = ffma2(neg2(a[L - 1][j]), a[L - 1][j], one);
+            d[j] = fmul2(fmul2(cpair(oo + 2 * j), g2), om);
+        }
+        acc[(oo + H) / 2] = fadd2(acc[(oo + H) / 2], pk(g, 0.0f));
+#pragma unroll
+        for (int l = L - 1; l >= 1; --l) {
+            const int o = 4 * H + (l - 1) * (H * H + H);
+#pragma unroll
+            for (int j = 0; j < HP; ++j) acc[(o + H * H + 2 * j) / 2] = fadd2(acc[(o + H * H + 2 * j) / 2], d[j]);
+            u64 dn[HP];
+#pragma unroll
+            for (int ip = 0; ip < HP; ++ip) {
+                float dnv[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int i = 2 * ip + h;
+                    float ai = h ? hi32(a[l - 1][ip]) : lo32(a[l - 1][ip]);
+                    u64 ai2 = pk(ai, ai);
+                    u64 t = pk(0.0f, 0.0f);
+#pragma unroll
+                    for (int j = 0; j < HP; ++j) {
+                        acc[(o + i * H + 2 * j) / 2] = ffma2(ai2, d[j], acc[(o + i * H + 2 * j) / 2]);
+                        t = ffma2(cpair(o + i * H + 2 * j), d[j], t);
+                    }
+                    dnv[h] = lo32(t) + hi32(t);
+                }
+                u64 om = ffma2(neg2(a[l - 1][ip]), a[l - 1][ip], one);
+                dn[ip] = fmul2(pk(dnv[0], dnv[1]), om);
+            }
+#pragma unroll
+            for (int j = 0; j < HP; ++j) d[j] = dn[j];
+        }
+        const u64 x2 = pk(x, x), y2 = pk(y, y), z2 = pk(z, z);
+#pragma unroll
+        for (int j = 0; j < HP; ++j) {
+            acc[(3 * H + 2 * j) / 2] = fadd2(acc[(3 * H + 2 * j) / 2], d[j]);
+            acc[(2 * j) / 2] = ffma2(x2, d[j], acc[(2 * j) / 2]);
+            acc[(H + 2 * j) / 2] = ffma2(y2, d[j], acc[(H + 2 * j) / 2]);
+            acc[(2 * H + 2 * j) / 2] = ffma2(z2, d[j], acc[(2 * H + 2 * j) / 2]);
+        }
+    }
+};
+
 template <int LP, int HP, int LM, int HM>
 struct Net {
-    using P = Mlp<LP, HP>;
+    using P = MlpP<LP, HP>;
     using M = Mlp<LM, HM>;
     static constexpr int NP = P::NP + M::NP;
+
+    // per-thread gradient accumulators: p-head in fp32x2 pairs, m-head scalar
+    struct Acc {
+        u64 p[P::NPAIR];
+        float m[M::NP];
+        __device__ __forceinline__ void zero() {
+#pragma unroll
+            for (int i = 0; i < P::NPAIR; ++i) p[i] = 0ull;
+#pragma unroll
+            for (int i = 0; i < M::NP; ++i) m[i] = 0.0f;
+        }
+        // gradient entry i in the flat C-ABI order
+        __device__ __forceinline__ float get(int i) const {
+            return i < P::NP ? ((i & 1) ? hi32(p[i / 2]) : lo32(p[i / 2])) : m[i - P::NP];
+        }
+    };
 
     // DoubleMLP.__call__ (MLP.py:98): phi >= 0 ? mlp_p : mlp_m
     __device__ __forceinline__ static float eval(bool plus, float x, float y, float z) {
         if (plus) {
-            float a[LP][HP];
+            u64 a[LP][HP / 2];
             return P::template forward<0>(x, y, z, a);
         } else {
             float a[LM][HM];
             return M::template forward<P::NP>(x, y, z, a);
         }
     }
-    __device__ __forceinline__ static void grad(bool plus, float x, float y, float z, float g, float (&acc)[NP]) {
+    __device__ __forceinline__ static void grad(bool plus, float x, float y, float z, float g, Acc& acc) {
         if (plus) {
-            float a[LP][HP];
+            u64 a[LP][HP / 2];
             P::template forward<0>(x, y, z, a);
-            P::template backward<0, NP>(x, y, z, a, g, acc);
+            P::template backward<0>(x, y, z, a, g, acc.p);
         } else {
             float a[LM][HM];
             M::template forward<P::NP>(x, y, z, a);
-            M::template backward<P::NP, NP>(x, y, z, a, g, acc);
+            M::template backward<P::NP, M::NP, P::NP>(x, y, z, a, g, acc.m);
         }
     }
 };
@@ -221,28 +396,32 @@ __global__ void extrap_kernel(nbm_shared_step_t s) {
     s.gE[c] = 0.0f;
 }
 
-// B: residual rows, 7-point stencil on U (discretization.py:366-379 after division by diag)
+// B: residual rows, 7-point stencil on U (discretization.py:366-379 after division by diag).
+// One thread per lattice node; the (y,z) plane is flattened so every warp reads 32 consecutive floats
+// of each of the 7 weight arrays (SoA), x planes are blockIdx.y.
 __global__ void __launch_bounds__(kThreads) residual_kernel(nbm_shared_step_t s) {
-    int iz = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    int iy = blockIdx.y + 1;
-    int ix = blockIdx.z + 1;
-    if (iz >= s.ez - 1) return;
-    int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
+    int plane = s.ey * s.ez;
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    int ix = blockIdx.y + 1;
+    if (m >= plane) return;
+    int iy = m / s.ez, iz = m - iy * s.ez;
+    if (iy < 1 || iy >= s.ey - 1 || iz < 1 || iz >= s.ez - 1) return;
+    int64_t sx = plane, sy = s.ez;
     int64_t ne = sx * s.ex;
-    int64_t e = ix * sx + iy * sy + iz;
+    int64_t e = ix * sx + m;
     float u0 = s.U[e];
-    float r = s.w[e] * u0;
-    r = fmaf(s.w[1 * ne + e], s.U[e - sx], r);
-    r = fmaf(s.w[2 * ne + e], s.U[e + sx], r);
-    r = fmaf(s.w[3 * ne + e], s.U[e - sy], r);
-    r = fmaf(s.w[4 * ne + e], s.U[e + sy], r);
-    r = fmaf(s.w[5 * ne + e], s.U[e - 1], r);
-    r = fmaf(s.w[6 * ne + e], s.U[e + 1], r);
+    float r = __ldg(s.w + e) * u0;
+    r = fmaf(__ldg(s.w + 1 * ne + e), s.U[e - sx], r);
+    r = fmaf(__ldg(s.w + 2 * ne + e), s.U[e + sx], r);
+    r = fmaf(__ldg(s.w + 3 * ne + e), s.U[e - sy], r);
+    r = fmaf(__ldg(s.w + 4 * ne + e), s.U[e + sy], r);
+    r = fmaf(__ldg(s.w + 5 * ne + e), s.U[e - 1], r);
+    r = fmaf(__ldg(s.w + 6 * ne + e), s.U[e + 1], r);
     if (s.nl) {
         r = fmaf(s.nl[e], nl_apply(s.nonlinear_m, s.nl_coef_m, u0), r);
         r = fmaf(s.nl[ne + e], nl_apply(s.nonlinear_p, s.nl_coef_p, u0), r);
     }
-    s.R[e] = r - s.rhs[e];
+    s.R[e] = r - __ldg(s.rhs + e);
 }
 
 // B2: irregular rows: add the far-side (E) terms
@@ -266,22 +445,23 @@ __global__ void irregular_fwd_kernel(nbm_shared_step_t s) {
 
 // C1: G[x] = sum_k w_k[x - off_k] R[x - off_k]  (adjoint of the 7-point rows)
 __global__ void __launch_bounds__(kThreads) adjoint_kernel(nbm_shared_step_t s) {
-    int iz = blockIdx.x * blockDim.x + threadIdx.x;
-    int iy = blockIdx.y;
-    int ix = blockIdx.z;
-    if (iz >= s.ez) return;
-    int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
+    int plane = s.ey * s.ez;
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    int ix = blockIdx.y;
+    if (m >= plane) return;
+    int iy = m / s.ez, iz = m - iy * s.ez;
+    int64_t sx = plane, sy = s.ez;
     int64_t ne = sx * s.ex;
-    int64_t e = ix * sx + iy * sy + iz;
+    int64_t e = ix * sx + m;
     float r0 = s.R[e];
-    float g = s.w[e] * r0;
+    float g = __ldg(s.w + e) * r0;
     // the point p = x + e_a has x as its "minus a" site (slot 1,3,5); p = x - e_a has x as slot 2,4,6
-    if (ix + 1 < s.ex) g = fmaf(s.w[1 * ne + e + sx], s.R[e + sx], g);
-    if (ix > 0) g = fmaf(s.w[2 * ne + e - sx], s.R[e - sx], g);
-    if (iy + 1 < s.ey) g = fmaf(s.w[3 * ne + e + sy], s.R[e + sy], g);
-    if (iy > 0) g = fmaf(s.w[4 * ne + e - sy], s.R[e - sy], g);
-    if (iz + 1 < s.ez) g = fmaf(s.w[5 * ne + e + 1], s.R[e + 1], g);
-    if (iz > 0) g = fmaf(s.w[6 * ne + e - 1], s.R[e - 1], g);
+    if (ix + 1 < s.ex) g = fmaf(__ldg(s.w + 1 * ne + e + sx), s.R[e + sx], g);
+    if (ix > 0) g = fmaf(__ldg(s.w + 2 * ne + e - sx), s.R[e - sx], g);
+    if (iy + 1 < s.ey) g = fmaf(__ldg(s.w + 3 * ne + e + sy), s.R[e + sy], g);
+    if (iy > 0) g = fmaf(__ldg(s.w + 4 * ne + e - sy), s.R[e - sy], g);
+    if (iz + 1 < s.ez) g = fmaf(__ldg(s.w + 5 * ne + e + 1), s.R[e + 1], g);
+    if (iz > 0) g = fmaf(__ldg(s.w + 6 * ne + e - 1), s.R[e - 1], g);
     if (s.nl) {
         float u0 = s.U[e];
         g = fmaf(s.nl[e] * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0) +
@@ -323,22 +503,17 @@ __global__ void extrap_bwd_kernel(nbm_shared_step_t s) {
 }
 
 // block-level reduction of per-thread accumulators into partials[blockIdx.x][0..NP] (loss last)
-template <int NP>
-__device__ __forceinline__ void block_reduce_store(float (&acc)[NP], float loss, float* __restrict__ partials) {
+template <class NET>
+__device__ __forceinline__ void block_reduce_store(typename NET::Acc& acc, float loss, float* __restrict__ partials) {
+    constexpr int NP = NET::NP;
     __shared__ float sm[kThreads / 32][NP + 1];
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        float v = acc[i];
+    for (int i = 0; i <= NP; ++i) {
+        float v = i < NP ? acc.get(i) : loss;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) sm[warp][i] = v;
-    }
-    {
-        float v = loss;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) sm[warp][NP] = v;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < NP + 1; i += kThreads) {
@@ -353,9 +528,8 @@ __device__ __forceinline__ void block_reduce_store(float (&acc)[NP], float loss,
 // (value_and_grad(self.loss), trainer.py:786; mean of optax.l2_loss, :899-901)
 template <class NET>
 __global__ void __launch_bounds__(kThreads, 1) node_grad_kernel(nbm_shared_step_t s, Tasks T) {
-    float acc[NET::NP];
-#pragma unroll
-    for (int i = 0; i < NET::NP; ++i) acc[i] = 0.0f;
+    typename NET::Acc acc;
+    acc.zero();
     float loss = 0.0f;
     for (int task = blockIdx.x; task < T.total; task += gridDim.x) {
         int mb = task % T.mblocks, xc = task / T.mblocks;
@@ -364,20 +538,26 @@ __global__ void __launch_bounds__(kThreads, 1) node_grad_kernel(nbm_shared_step_
         int iy = m / s.ez, iz = m - iy * s.ez;
         float y = __ldg(s.ye + iy), z = __ldg(s.ze + iz);
         int x0 = xc * T.xchunk, x1 = min(s.ex, x0 + T.xchunk);
+        // software pipeline: the loads of plane ix+1 are in flight while plane ix is computed (only 8 warps
+        // per SM fit beside the 167 accumulators, so HBM latency has to be hidden explicitly)
+        size_t e = (size_t)x0 * T.plane + m;
+        float g_n = __ldg(s.G + e), r_n = __ldg(s.R + e);
+        uint8_t sd_n = __ldg(s.side + e);
         for (int ix = x0; ix < x1; ++ix) {
-            size_t e = (size_t)ix * T.plane + m;
-            float g = s.G[e] * s.inv_n_points;
-            float r = s.R[e];
-            loss = fmaf(0.5f * r, r, loss);
-            if (g != 0.0f) {
-                float x = __ldg(s.xe + ix);
-                bool plus = (__ldg(s.side + e) & 1) != 0;
-                NET::grad(plus, x, y, z, g, acc);
+            float g = g_n * s.inv_n_points, r = r_n;
+            bool plus = (sd_n & 1) != 0;
+            if (ix + 1 < x1) {
+                e += T.plane;
+                g_n = __ldg(s.G + e);
+                r_n = __ldg(s.R + e);
+                sd_n = __ldg(s.side + e);
             }
+            loss = fmaf(0.5f * r, r, loss);
+            if (g != 0.0f) NET::grad(plus, __ldg(s.xe + ix), y, z, g, acc);
         }
     }
     loss *= s.inv_n_points;
-    block_reduce_store<NET::NP>(acc, loss, s.partials);
+    block_reduce_store<NET>(acc, loss, s.partials);
 }
 
 // K4a: deterministic sum of the per-CTA partial rows
@@ -471,6 +651,22 @@ __global__ void evaluate_kernel(nbm_lvl_t L, const float* __restrict__ pts, int6
     }
 }
 
+
+// staging copy of the parameters: [0,MAXP) as given, [MAXP,2MAXP) with the hidden layers pre-scaled
+__global__ void prep_params_kernel(nbm_net_t net, const float* __restrict__ params, float* __restrict__ stage, int P) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float v = params[i];
+    int np = 3 * net.hidden_p + net.hidden_p + (net.layers_p - 1) * (net.hidden_p * net.hidden_p + net.hidden_p) +
+             net.hidden_p + 1;
+    int k = i < np ? i : i - np;
+    int H = i < np ? net.hidden_p : net.hidden_m;
+    int Lh = i < np ? net.layers_p : net.layers_m;
+    int hidden_len = 4 * H + (Lh - 1) * (H * H + H);  // everything before the output layer
+    stage[i] = v;
+    stage[NBM_MAXP + i] = k < hidden_len ? v * kTwoLog2e : v;
+}
+
 static int g_sm_count = 0;
 static int sm_count() {
     if (g_sm_count == 0) {
@@ -496,12 +692,12 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     if ((stages & NBM_STAGE_EXTRAP) && s.n_crossed > 0)
         extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
     if (stages & NBM_STAGE_RESIDUAL) {
-        dim3 g((s.ez - 2 + kThreads - 1) / kThreads, s.ey - 2, s.ex - 2);
+        dim3 g((s.ey * s.ez + kThreads - 1) / kThreads, s.ex - 2);
         residual_kernel<<<g, kThreads, 0, st>>>(s);
         if (s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
     }
     if (stages & NBM_STAGE_ADJOINT) {
-        dim3 g((s.ez + kThreads - 1) / kThreads, s.ey, s.ex);
+        dim3 g((s.ey * s.ez + kThreads - 1) / kThreads, s.ex);
         adjoint_kernel<<<g, kThreads, 0, st>>>(s);
         if (s.n_irr > 0) irregular_bwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
         if (s.n_crossed > 0) extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, st>>>(s);
@@ -595,9 +791,8 @@ __global__ void __launch_bounds__(kThreads) points_extrap_kernel(PointsArgs a) {
 template <class NET>
 __global__ void __launch_bounds__(kThreads, 1) points_rows_kernel(PointsArgs a) {
     const nbm_points_step_t& s = a.s;
-    float acc[NET::NP];
-#pragma unroll
-    for (int i = 0; i < NET::NP; ++i) acc[i] = 0.0f;
+    typename NET::Acc acc;
+    acc.zero();
     float loss = 0.0f;
     const int64_t N = a.n_points;
     for (int64_t p = s.p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < s.p1;
@@ -671,16 +866,15 @@ __global__ void __launch_bounds__(kThreads, 1) points_rows_kernel(PointsArgs a) 
         }
     }
     loss *= s.inv_n_points;
-    block_reduce_store<NET::NP>(acc, loss, s.partials);
+    block_reduce_store<NET>(acc, loss, s.partials);
 }
 
 // Z2: backward through the extrapolation of the crossed sites of the batch
 template <class NET>
 __global__ void __launch_bounds__(kThreads, 1) points_extrap_bwd_kernel(PointsArgs a, int row0) {
     const nbm_points_step_t& s = a.s;
-    float acc[NET::NP];
-#pragma unroll
-    for (int i = 0; i < NET::NP; ++i) acc[i] = 0.0f;
+    typename NET::Acc acc;
+    acc.zero();
     int lane = threadIdx.x & 31;
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -697,7 +891,7 @@ __global__ void __launch_bounds__(kThreads, 1) points_extrap_bwd_kernel(PointsAr
                 NET::grad(plus, s.c_pos[3 * c] + X0, s.c_pos[3 * c + 1] + X1, s.c_pos[3 * c + 2] + X2, gq, acc);
         }
     }
-    block_reduce_store<NET::NP>(acc, 0.0f, s.partials + (size_t)row0 * (NET::NP + 1));
+    block_reduce_store<NET>(acc, 0.0f, s.partials + (size_t)row0 * (NET::NP + 1));
 }
 
 template <class NET>
@@ -762,9 +956,14 @@ int nbm_upload_params(const nbm_net_t* net, const float* params, nbm_stream_t st
         set_error("parameter count %d outside (0, %d]", P, NBM_MAXP);
         return NBM_ERR_UNSUPPORTED;
     }
-    return cuda_check(
-        cudaMemcpyToSymbolAsync(c_P, params, sizeof(float) * P, 0, cudaMemcpyDeviceToDevice, as_stream(stream)),
-        "upload params");
+    cudaStream_t st = as_stream(stream);
+    float* stage = nullptr;
+    int rc = cuda_check(cudaGetSymbolAddress((void**)&stage, g_stage), "staging buffer");
+    if (rc) return rc;
+    prep_params_kernel<<<(P + 127) / 128, 128, 0, st>>>(*net, params, stage, P);
+    NBM_LAUNCH_CHECK("prep_params");
+    return cuda_check(cudaMemcpyToSymbolAsync(c_P, stage, sizeof(float) * 2 * NBM_MAXP, 0, cudaMemcpyDeviceToDevice, st),
+                      "upload params");
 }
 
 int nbm_step_partial_rows(void) { return kPartialRows; }
