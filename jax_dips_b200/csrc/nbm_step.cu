@@ -370,11 +370,19 @@ __global__ void __launch_bounds__(kThreads) fwd_nodes_kernel(nbm_shared_step_t s
         int iy = m / s.ez, iz = m - iy * s.ez;
         float y = __ldg(s.ye + iy), z = __ldg(s.ze + iz);
         int x0 = xc * T.xchunk, x1 = min(s.ex, x0 + T.xchunk);
+        size_t e = (size_t)x0 * T.plane + m;
+        float x_n = __ldg(s.xe + x0);
+        uint8_t sd_n = __ldg(s.side + e);
         for (int ix = x0; ix < x1; ++ix) {
-            size_t e = (size_t)ix * T.plane + m;
-            float x = __ldg(s.xe + ix);
-            bool plus = (__ldg(s.side + e) & 1) != 0;
-            s.U[e] = NET::eval(plus, x, y, z);
+            float x = x_n;
+            bool plus = (sd_n & 1) != 0;
+            size_t e_cur = e;
+            if (ix + 1 < x1) {
+                e += T.plane;
+                sd_n = __ldg(s.side + e);
+                x_n = __ldg(s.xe + ix + 1);
+            }
+            s.U[e_cur] = NET::eval(plus, x, y, z);
         }
     }
 }
@@ -541,19 +549,20 @@ __global__ void __launch_bounds__(kThreads, 1) node_grad_kernel(nbm_shared_step_
         // software pipeline: the loads of plane ix+1 are in flight while plane ix is computed (only 8 warps
         // per SM fit beside the 167 accumulators, so HBM latency has to be hidden explicitly)
         size_t e = (size_t)x0 * T.plane + m;
-        float g_n = __ldg(s.G + e), r_n = __ldg(s.R + e);
+        float g_n = __ldg(s.G + e), r_n = __ldg(s.R + e), x_n = __ldg(s.xe + x0);
         uint8_t sd_n = __ldg(s.side + e);
         for (int ix = x0; ix < x1; ++ix) {
-            float g = g_n * s.inv_n_points, r = r_n;
+            float g = g_n * s.inv_n_points, r = r_n, x = x_n;
             bool plus = (sd_n & 1) != 0;
             if (ix + 1 < x1) {
                 e += T.plane;
                 g_n = __ldg(s.G + e);
                 r_n = __ldg(s.R + e);
                 sd_n = __ldg(s.side + e);
+                x_n = __ldg(s.xe + ix + 1);
             }
             loss = fmaf(0.5f * r, r, loss);
-            if (g != 0.0f) NET::grad(plus, __ldg(s.xe + ix), y, z, g, acc);
+            if (g != 0.0f) NET::grad(plus, x, y, z, g, acc);
         }
     }
     loss *= s.inv_n_points;
