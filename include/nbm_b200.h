@@ -262,6 +262,7 @@ typedef struct {
     float* E; float* gE;
     float* partials; int n_partial_rows;
     float* loss_grad;
+    float* rows;                     /* optional [n_points]: lhs/diag - rhs/diag of every row of the batch (may be NULL) */
 } nbm_points_step_t;
 
 /* General path (any cell size, any contiguous batch): 7 network evaluations per point, fused

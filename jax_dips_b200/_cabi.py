@@ -78,7 +78,7 @@ class PointsStep(C.Structure):
                 ("n_irr", C.c_int64), ("irr_wE", c_fp), ("irr_c", c_fp), ("irr_nl", c_fp), ("irr_nlw", c_fp),
                 ("inv_n_points", c_f),
                 ("E", c_fp), ("gE", c_fp),
-                ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp)]
+                ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp), ("rows", c_fp)]
 
 
 class Optimizer(C.Structure):

@@ -842,6 +842,7 @@ __global__ void __launch_bounds__(kThreads, 1) points_rows_kernel(PointsArgs a) 
             }
         }
         loss = fmaf(0.5f * r, r, loss);
+        if (s.rows) s.rows[p] = r;
         float g = r * s.inv_n_points;
         if (q_irr >= 0) {
             // each crossed site belongs to exactly one (point, slot): plain stores

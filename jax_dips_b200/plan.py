@@ -467,8 +467,9 @@ class PointsPlan:
     """General path for the contiguous batch [p0, p1) of the flattened training points at the cell
     size of `level`."""
 
-    def __init__(self, level: GeneralLevel, p0: int, p1: int, n_mean: Optional[int] = None):
+    def __init__(self, level: GeneralLevel, p0: int, p1: int, n_mean: Optional[int] = None, keep_rows: bool = False):
         self.level, self.p0, self.p1 = level, int(p0), int(p1)
+        self.rows = torch.zeros(level.n_points, dtype=torch.float32, device=level.device) if keep_rows else None
         self.device = level.device
         self.n_points = self.p1 - self.p0
         net, cs = level.net, level.sites
@@ -490,6 +491,7 @@ class PointsPlan:
         s.inv_n_points = 1.0 / float(n_mean if n_mean is not None else self.n_points)
         s.E, s.gE = cabi.ptr(level.E), cabi.ptr(level.gE)
         s.partials, s.n_partial_rows, s.loss_grad = cabi.ptr(level.partials), level.rows, cabi.ptr(self.loss_grad)
+        s.rows = cabi.ptr(self.rows)
         self.step = s
 
     def loss_grad_launch(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -5,8 +5,8 @@ under /root/reference and pin the oracle against them; see oracle/make_golden.py
 Semantics reproduced: float32 default dtype unless `config.update("jax_enable_x64", True)`, weak
 python scalars, `.at[idx].set()`, stable `argsort`, `jnp.linalg.pinv`'s default cutoff
 (10*max(M,N)*eps), `nan_to_num`, `isclose`, `lax.cond`, `vmap` (a Python loop), `jit` (identity).
-Not reproduced: tracing, autodiff (`grad` raises), XLA's fusion/FMA choices, out-of-range gather
-clamping.
+out-of-range integer gathers clamp.  Not reproduced: tracing, autodiff (`grad` raises), XLA's
+fusion/FMA choices.
 """
 from . import numpy  # noqa: F401
 from . import lax  # noqa: F401

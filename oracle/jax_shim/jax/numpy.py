@@ -57,6 +57,18 @@ class Arr(_np.ndarray):
     def __array_finalize__(self, obj):
         pass
 
+    def __getitem__(self, idx):
+        # jax clamps out-of-range integer indices of a gather instead of raising
+        if isinstance(idx, tuple) and len(idx) == self.ndim and builtins.all(
+                isinstance(i, (int, _np.integer)) for i in idx):
+            idx = tuple(builtins.min(int(i), n - 1) if int(i) >= 0 else int(i) for i, n in zip(idx, self.shape))
+        return _np.ndarray.__getitem__(self, idx)
+
+    def reshape(self, *shape, **kw):
+        if not shape:  # jax: x.reshape() -> scalar-shaped array
+            return _np.ndarray.reshape(self, ())
+        return _np.ndarray.reshape(self, *shape, **kw)
+
 
 def _fix(x):
     """x64 disabled: no float64 / int64 can come out of a jnp function."""
@@ -110,6 +122,10 @@ for _name in ("sign floor ceil sqrt abs absolute exp log sin cos tan tanh sinh c
               "logical_and logical_or logical_not any all isnan isfinite clip cumsum prod outer cross "
               "expand_dims ravel take amin amax nonzero round").split():
     globals()[_name] = _wrap(getattr(_np, _name))
+
+
+def split(a, indices_or_sections, axis=0):
+    return [Arr(v) for v in _np.split(_np.asarray(a), indices_or_sections, axis=axis)]
 
 
 def nan_to_num(x, nan=0.0, posinf=None, neginf=None):

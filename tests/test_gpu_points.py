@@ -114,3 +114,65 @@ def test_training_reduces_the_error_against_the_exact_solution():
     err = float((state.solution.cpu() - exact).abs().max())
     assert float(losses[-1]) < 0.05 * float(losses[0])
     assert err < 0.2, err
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors produced by the reference's own sources (oracle/make_golden.py)
+# ---------------------------------------------------------------------------------------------
+import glob
+import os
+
+import numpy as np
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+CASE_PROBLEM = {"sphere_tri_z0": ("sphere", "trilinear"), "sphere_tri_z1": ("sphere", "trilinear"),
+                "star_tri_z0": ("star", "trilinear"), "sphere_quad_z0": ("sphere", "quadratic")}
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_rows_match_reference_golden(path):
+    """CUDA rows and cut-cell fractions at the golden points against what the REFERENCE'S OWN CODE
+    produced for the same inputs (x64 run).  Rows 1e-5; fractions 5e-5 = the reference's own
+    float32-vs-x64 spread (tests/test_oracle_pinning.py::test_reference_noise_floor)."""
+    name = os.path.basename(path)[:-4]
+    pname, interp = CASE_PROBLEM[name]
+    z = np.load(path)
+    P = problems.PROBLEMS[pname]()
+    zoom, idx = int(z["zoom"]), torch.from_numpy(z["point_idx"]).long()
+    params = torch.from_numpy(z["f32_params"]).float()
+    gold = torch.from_numpy(z["f64_lhs_rhs"])
+    coeffs = torch.from_numpy(z["f64_coeffs"])
+    d = z["f64_d"]
+    if zoom == 0:
+        tr, lv, lvl, oprob, pl, shape = build(P, int(z["n_tr"]), int(z["n_lvl"]), interp)
+        with torch.cuda.device(DEV):
+            nplan.upload_params(shape, params.to(DEV))
+            pl.loss_grad_launch()
+            torch.cuda.synchronize()
+        rhs_k = pl.point_view(pl.rhs).cpu()[idx]
+        lhs_k = pl.point_view(pl.R).cpu()[idx] + rhs_k
+        flag_k = pl.point_view(pl.sites.flag).cpu()[idx]
+        cidx = pl.point_view(pl.sites.cidx).cpu()[idx]
+        frac = pl.sites.frac.view(-1, 14).cpu()
+    else:
+        tr, oprob, level, shape, dd = general(P, int(z["n_tr"]), int(z["n_lvl"]), zoom, interp)
+        pp = nplan.PointsPlan(level, 0, tr.num_points(), keep_rows=True)
+        with torch.cuda.device(DEV):
+            nplan.upload_params(shape, params.to(DEV))
+            pp.loss_grad_launch()
+            torch.cuda.synchronize()
+        rhs_k = level.rhs.cpu()[idx]
+        lhs_k = pp.rows.cpu()[idx] + rhs_k
+        n = tr.num_points()
+        flag_k = level.sites.flag[:n].cpu()[idx]
+        cidx = level.sites.cidx[:n].cpu()[idx]
+        frac = level.sites.frac.view(-1, 14).cpu()
+    assert torch.equal(flag_k.double(), torch.from_numpy(z["f64_flag"]))
+    assert util.rel_inf(lhs_k, gold[:, 0]) < TOL_ROW
+    assert util.rel_inf(rhs_k, gold[:, 1]) < TOL_ROW
+    cr = flag_k == 0
+    if cr.any():
+        f = frac[cidx[cr].long()].double()
+        vol, area = d.prod(), d[1] * d[2]
+        assert float((f[:, 12:14] - coeffs[cr][:, 12:14]).abs().max()) / vol < 5e-5
+        assert float((f[:, 0:12] - coeffs[cr][:, 14:26]).abs().max()) / area < 5e-5

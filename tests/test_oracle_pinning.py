@@ -1,0 +1,147 @@
+"""CPU tests that PIN the oracle:
+  * against the reference's own known-answer test (sphere area / volume,
+    /root/reference/tests/test_geometric_integrations.py:181-182), and
+  * against golden vectors produced by the reference's own source files run through the numpy
+    stand-in for jax (oracle/make_golden.py -> tests/golden/*.npz).
+"""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import util
+from jax_dips_b200 import problems
+from oracle import nbm_oracle as O
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+CASE_PROBLEM = {"sphere_tri_z0": ("sphere", "trilinear"), "sphere_tri_z1": ("sphere", "trilinear"),
+                "star_tri_z0": ("star", "trilinear"), "sphere_quad_z0": ("sphere", "quadratic")}
+
+
+def test_reference_kat_sphere_area_and_volume():
+    """sphere r=0.5 in [-2,2]^3 at 128^3 through the non-oscillatory quadratic interpolant:
+    area = pi +- 0.02, volume = pi/6 +- 0.02 (the reference's only geometry assertion)."""
+    dt = torch.float64
+    g = O.make_grid([-2] * 3, [2] * 3, [128] * 3, dtype=dt)
+    phi = torch.sqrt((g.R ** 2).sum(1)) - 0.5
+    f = O.nonoscillatory_quadratic_interpolation(phi, g)
+    near = phi.abs() < 3 * float(g.dx)
+    P = g.R[near]
+    one = lambda R: torch.ones(R.shape[0], dtype=dt)
+    area = O.integrate_over_interface(P, g.dx, g.dy, g.dz, f, one).sum()
+    c = O.cell_faces_areas_values(P, g.dx, g.dy, g.dz, f, one, one)
+    vol = c[:, 12].sum() + (phi < -3 * float(g.dx)).sum() * g.dx * g.dy * g.dz
+    assert abs(float(area) - math.pi) < 0.02
+    assert abs(float(vol) - math.pi / 6) < 0.02
+
+
+def test_geometry_invariants():
+    """V^- + V^+ = cell volume; areas bounded by the nominal face; uncrossed cells are all-or-nothing."""
+    dt = torch.float64
+    P = problems.star()
+    tr, lv, phi_grid, op = util.make_case(P, 16, 32, "trilinear", dt)
+    d = [tr.dx.to(dt), tr.dy.to(dt), tr.dz.to(dt)]
+    one = lambda R: torch.ones(R.shape[0], dtype=dt)
+    c = O.cell_faces_areas_values(tr.R.to(dt), *d, op.phi_fn, one, one)
+    vol = float(d[0] * d[1] * d[2])
+    assert float((c[:, 12] + c[:, 13] - vol).abs().max()) < 1e-9 * vol + 1e-12
+    area = float(d[1] * d[2])
+    assert float(c[:, 14:26].max()) <= area * (1 + 1e-9)
+    flag = O.is_cell_crossed(tr.R.to(dt), *d, op.phi_fn)
+    un = flag != 0
+    assert bool(((c[un, 12] == 0) | (c[un, 13] == 0)).all())
+
+
+# The reference measures cut pieces with sqrt|det(E E^T)| on vertex arrays it casts to float32 EVEN in
+# x64 mode (`jnp.array([...], dtype=f32)`, geometric_integrations_per_point.py:81-89, 148-178): for sliver
+# pieces that Gram form loses half the digits, and the reference's own float32 and x64 runs differ by up to
+# 3.0e-5 of the cell measure (sphere_tri_z0; see test_reference_noise_floor).  Fractions are therefore
+# pinned at 5e-5, everything downstream (rows) at 1e-5.
+TOL_FRAC_REF = 5e-5
+
+
+def test_reference_noise_floor():
+    worst = 0.0
+    for path in GOLDEN:
+        z = np.load(path)
+        d = z["f64_d"]
+        a, b = z["f32_coeffs"].astype(np.float64), z["f64_coeffs"]
+        worst = max(worst, np.abs(a[:, 12:14] - b[:, 12:14]).max() / d.prod(),
+                    np.abs(a[:, 14:] - b[:, 14:]).max() / (d[1] * d[2]))
+    assert 1e-5 < worst < TOL_FRAC_REF   # the reference does not meet 1e-5 against itself
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+@pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-5), ("f32", torch.float32, 1e-5)])
+def test_oracle_matches_reference_sources(path, tag, dtype, tol):
+    """rows, 26-vector of face coefficients, crossing flags, Gamma integral, u^-/u^+ and the
+    regression weights (zeta, gamma) against the reference's own code on the same inputs."""
+    name = os.path.basename(path)[:-4]
+    pname, interp = CASE_PROBLEM[name]
+    z = np.load(path)
+    P = problems.PROBLEMS[pname]()
+    tr, lv, phi_grid, op = util.make_case(P, int(z["n_tr"]), int(z["n_lvl"]), interp, dtype)
+    assert np.array_equal(phi_grid.numpy(), z[f"{tag}_phi_grid"])
+    pts = torch.from_numpy(z[f"{tag}_points"]).to(dtype)
+    d = [torch.tensor(float(v), dtype=dtype) for v in z[f"{tag}_d"]]
+    params = torch.from_numpy(z[f"{tag}_params"]).to(dtype)
+    g = lambda k: torch.from_numpy(z[f"{tag}_{k}"]).to(torch.float64)
+
+    flag = O.is_cell_crossed(pts, *d, op.phi_fn)
+    assert torch.equal(flag.double(), g("flag"))
+    coeffs = O.cell_faces_areas_values(pts, *d, op.phi_fn, op.mu_m_fn, op.mu_p_fn)
+    vol, area = float(d[0] * d[1] * d[2]), float(d[1] * d[2])
+    assert util.rel_inf(coeffs[:, :12], g("coeffs")[:, :12]) < TOL_FRAC_REF                      # mu*A/d
+    assert float((coeffs[:, 12:14].double() - g("coeffs")[:, 12:14]).abs().max()) / vol < TOL_FRAC_REF   # volumes
+    assert float((coeffs[:, 14:].double() - g("coeffs")[:, 14:]).abs().max()) / area < TOL_FRAC_REF      # areas
+    bg = O.integrate_over_interface(pts, *d, op.phi_fn, op.beta_fn).double()
+    gb = g("beta_gamma")
+    assert torch.equal(torch.isnan(bg), torch.isnan(gb))
+    fin = ~torch.isnan(gb)
+    if fin.any() and float(gb[fin].abs().max()) > 0:
+        assert util.rel_inf(bg[fin], gb[fin]) < TOL_FRAC_REF
+    um, up = O.u_mp_at_sites(params, pts, *d, op)
+    assert util.rel_inf(torch.stack((um, up), 1), g("u_mp")) < tol
+    rc = O.regression_coeffs(pts, *d, op)
+    mine = torch.cat([rc[k].reshape(pts.shape[0], -1) for k in
+                      ("gamma_m", "gamma_m_pqm", "gamma_p", "gamma_p_pqm", "zeta_m", "zeta_m_pqm", "zeta_p",
+                       "zeta_p_pqm")], dim=1).double()
+    ref = g("zeta_gamma")
+    crossed = flag == 0     # only crossed sites ever use them (discretization.py:518)
+    if crossed.any():
+        assert util.rel_inf(mine[crossed], ref[crossed]) < 1e-3   # pinv in float32: conditioning of X^T W X
+    lhs, rhs = O.compute_Ax_and_b(params, pts, *d, op)
+    assert util.rel_inf(lhs, g("lhs_rhs")[:, 0]) < tol
+    assert util.rel_inf(rhs, g("lhs_rhs")[:, 1]) < tol
+
+
+def test_gradient_matches_finite_differences():
+    """autograd of the pinned rows == central differences of the loss (float64)."""
+    dt = torch.float64
+    P = problems.sphere()
+    tr, lv, phi_grid, op = util.make_case(P, 8, 16, "trilinear", dt)
+    d = [tr.dx.to(dt), tr.dy.to(dt), tr.dz.to(dt)]
+    params = O.init_params(op.shape, seed=3, dtype=dt)
+    pts = tr.R.to(dt)[::3]
+    loss, grad = O.loss_and_grad(params, pts, *d, op)
+    rng = np.random.default_rng(0)
+    for i in rng.choice(params.numel(), 12, replace=False):
+        e = torch.zeros_like(params); e[i] = 1e-6
+        fd = (O.loss_fn(params + e, pts, *d, op) - O.loss_fn(params - e, pts, *d, op)) / 2e-6
+        assert abs(float(fd) - float(grad[i])) < 1e-6 * max(1.0, abs(float(grad[i]))) + 1e-9
+
+
+def test_optax_chain_known_values():
+    """clip -> adam -> schedule -> -1 on a hand-computed first step (optax 0.1.5 semantics)."""
+    opt = O.OptaxCustom(3, learning_rate=1e-2, decay_rate=0.5, dtype=torch.float64)
+    g = torch.tensor([3.0, 0.0, 4.0], dtype=torch.float64)          # norm 5 -> clipped to norm 1
+    u = opt.update(g)
+    gc = g / 5.0
+    m = 0.1 * gc; v = 0.001 * gc * gc
+    want = -1e-2 * (m / 0.1) / (torch.sqrt(v / 0.001) + 1e-8)
+    assert torch.allclose(u, want, rtol=1e-12, atol=1e-15)
+    u2 = opt.update(torch.tensor([0.1, 0.1, 0.1], dtype=torch.float64))  # not clipped; lr decayed by 0.5**(1/1000)
+    assert float(u2[1]) < 0
