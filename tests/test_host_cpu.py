@@ -1,0 +1,185 @@
+"""CPU tests of the host side: C-ABI surface, reference-API mirror (names, defaults, errors),
+batching arithmetic, and the N>1 partition + psum semantics over gloo (world_size 2)."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from jax_dips_b200 import data_management, mesh, optimizers, problems
+from jax_dips_b200 import numpy as jnp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from jax_dips_b200 import build as b
+    lib_path = b.build()                       # nvcc cross-compiles for sm_100a without a GPU
+    header = open(os.path.join(ROOT, "include", "nbm_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(nbm_\w+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 15
+    L = ctypes.CDLL(lib_path)
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    from jax_dips_b200 import _cabi
+    assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
+    _cabi.lib()
+    assert _cabi.lib().nbm_version() >= 100
+    # struct layouts agree with the compiler's (sizes as nvcc's host compiler sees them)
+    net = _cabi.Net(2, 10, 1, 1)
+    assert _cabi.lib().nbm_net_num_params(ctypes.byref(net)) == 167
+    net3 = _cabi.Net(2, 10, 1, 3)
+    assert _cabi.lib().nbm_net_num_params(ctypes.byref(net3)) == 177          # README.md:137-142
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "jax_dips_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("oracle's", ""), fn
+
+
+def test_mesh_is_z_fastest_like_the_reference():
+    init_mesh_fn, coord_at = mesh.construct(3)
+    x = torch.linspace(0, 1, 3); y = torch.linspace(0, 2, 4); z = torch.linspace(0, 3, 5)
+    g = init_mesh_fn(x, y, z)
+    assert g.shape() == (3, 4, 5)
+    R = g.R.reshape(3, 4, 5, 3)
+    assert torch.equal(R[1, 2, 3], torch.stack((x[1], y[2], z[3])))            # index = (i*Ny + j)*Nz + k
+    assert g.R_zmax_boundary.shape == (12, 3) and float(g.R_zmax_boundary[:, 2].min()) == 3.0
+    assert float(g.dx) == pytest.approx(0.5)
+    assert coord_at(g, (2, 3, 4)) == [x[2], y[3], z[4]]
+    with pytest.raises(NotImplementedError):
+        mesh.construct(2)
+
+
+def test_vmap_of_per_point_callables():
+    g = mesh.linspace_grid([-1] * 3, [1] * 3, [4, 5, 6])
+    f = jnp.vmap(lambda r: jnp.exp(r[2]) * r[1] + jnp.where(r[0] > 0, 1.0, 0.0))
+    want = torch.exp(g.R[:, 2]) * g.R[:, 1] + (g.R[:, 0] > 0).float()
+    assert torch.allclose(f(g.R), want)
+    assert jnp.vmap(lambda r: 0.0)(g.R).shape == (120,)
+    P = problems.sphere()
+    beta = jnp.vmap(P.beta_fn)(g.R)
+    assert beta.shape == (120,) and torch.isfinite(beta).all()
+
+
+def test_dataset_dict_ranges_follow_the_reference_arithmetic():
+    # single device: contiguous batches (data_management.py:121-130)
+    DD = data_management.DatasetDict(num_points=64 ** 3, batch_size=131072)
+    assert DD.num_batches == 2 and DD.ranges(0) == [(0, 131072), (131072, 262144)]
+    # batch larger than the data is clipped (:90-91)
+    assert data_management.DatasetDict(num_points=4096, batch_size=131072).ranges(0) == [(0, 4096)]
+    # multi device: per-device batch = min(n_dev*batch, ceil(N/n_dev)) (trainer.py:733-737), x-slabs
+    DD = data_management.DatasetDict(num_points=32 ** 3, batch_size=8 * 131072, num_gpus=8)
+    assert [DD.ranges(r) for r in range(8)] == [[(r * 4096, (r + 1) * 4096)] for r in range(8)]
+    with pytest.raises(NotImplementedError):
+        data_management.DatasetDict(num_points=1000, batch_size=300)            # would need random padding
+
+
+def test_zoom_schedule():
+    g = mesh.linspace_grid([-1] * 3, [1] * 3, [9, 9, 9])
+    TD = data_management.TrainData(g)
+    assert [TD.zoom_level(8, e) for e in range(8)] == [0, 0, 1, 1, 2, 2, 3, 3]   # data_management.py:320-326
+    assert TD.zoom_level(10, 9) == 4                                             # num_epochs % 4 != 0 reaches 4
+    assert TD.zoom_cell(2)[0] == pytest.approx(0.25 * 0.25)
+    with pytest.raises(ZeroDivisionError):
+        TD.zoom_level(3, 0)
+
+
+def test_optimizer_factory_mirrors_the_reference():
+    o = optimizers.get_optimizer("custom", "exponential", 1e-3, 0.975)
+    assert o.kind == 0 and o.scheduler(1000) == pytest.approx(1e-3 * 0.975)
+    assert optimizers.get_optimizer("adam", learning_rate=1e-2).kind == 1
+    assert optimizers.get_optimizer("rmsprop", learning_rate=1e-2).kind == 2
+    with pytest.raises(ValueError):
+        optimizers.get_optimizer("sgd")                                           # optimizers.py:95-97
+    sig = inspect.signature(optimizers.get_optimizer)
+    assert list(sig.parameters)[:5] == ["optimizer_name", "scheduler_name", "learning_rate", "decay_rate", "max_norm"]
+
+
+def test_trainer_api_signature_matches_the_reference():
+    from jax_dips_b200 import trainer
+    sig = inspect.signature(trainer.setup)
+    assert list(sig.parameters) == ["initial_value_fn", "dirichlet_bc_fn", "lvl_set_fn", "mu_m_fn_", "mu_p_fn_",
+                                    "k_m_fn_", "k_p_fn_", "f_m_fn_", "f_p_fn_", "alpha_fn_", "beta_fn_",
+                                    "nonlinear_op_m", "nonlinear_op_p"]                 # trainer.py:980-994
+    init_fn = trainer.setup(*problems.sphere().setup_args())
+    p = inspect.signature(init_fn).parameters
+    for name, default in (("num_epochs", 1000), ("batch_size", 131072), ("algorithm", 0), ("multi_gpu", False),
+                          ("checkpoint_interval", 1000), ("restart", False), ("print_rate", 1)):
+        assert p[name].default == default                                                 # trainer.py:1035-1076
+    net = trainer.NetShape.from_model_dict(trainer._DEFAULT_MODEL)
+    p0 = trainer.haiku_init(net)
+    assert p0.numel() == 167
+    tree = trainer.params_to_tree(net, p0)
+    assert set(tree) == {"double_mlp/~mlp_p_fn/linear", "double_mlp/~mlp_p_fn/linear_1", "double_mlp/~mlp_p_fn/linear_2",
+                         "double_mlp/~mlp_m_fn/linear", "double_mlp/~mlp_m_fn/linear_1", "preconditioner"}
+    assert tree["double_mlp/~mlp_p_fn/linear_1"]["w"].shape == (10, 10)
+    assert torch.equal(trainer.tree_to_params(net, tree), p0)
+    with pytest.raises(NotImplementedError):
+        trainer.NetShape.from_model_dict({"model_type": "resnet", "mlp": {}})
+    from jax_dips_b200.plan import Nonlinear
+    with pytest.raises(NotImplementedError):
+        Nonlinear.coerce(lambda u: u ** 3)
+    assert Nonlinear.coerce(lambda u: 0.0).kind == 0
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import sys
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    from oracle import nbm_oracle as O
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    P = problems.sphere()
+    tr, lv, phi_grid, op = util.make_case(P, 8, 16, "trilinear", torch.float64)
+    DD = data_management.DatasetDict(num_points=tr.num_points(), batch_size=world * 131072, num_gpus=world)
+    (p0, p1), = DD.ranges(rank)
+    params = O.init_params(op.shape, seed=2, dtype=torch.float64)
+    d = [tr.dx.double(), tr.dy.double(), tr.dz.double()]
+    loss, grad = O.loss_and_grad(params, tr.R.double()[p0:p1], *d, op)      # per-device MEAN over its slab
+    buf = torch.cat((grad, loss.reshape(1)))
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)                               # psum (trainer.py:829-830)
+    if rank == 0:
+        q.put((p0, p1, buf.numpy()))
+    else:
+        q.put((p0, p1, None))
+    dist.destroy_process_group()
+
+
+def test_two_rank_partition_and_psum_over_gloo():
+    import socket
+    import torch.multiprocessing as mp
+    import util
+    from oracle import nbm_oracle as O
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    ranges = sorted((a, b) for a, b, _ in got)
+    assert ranges == [(0, 256), (256, 512)]                                   # contiguous x-slabs of the 8^3 grid
+    buf = next(v for _, _, v in got if v is not None)
+    # the oracle's own multi-device loop (sum over devices of per-device means)
+    P = problems.sphere()
+    tr, lv, phi_grid, op = util.make_case(P, 8, 16, "trilinear", torch.float64)
+    params = O.init_params(op.shape, seed=2, dtype=torch.float64)
+    d = [tr.dx.double(), tr.dy.double(), tr.dz.double()]
+    gsum, lsum = torch.zeros_like(params), 0.0
+    for dev in range(2):
+        l, g = O.loss_and_grad(params, tr.R.double()[dev * 256:(dev + 1) * 256], *d, op)
+        gsum += g; lsum += float(l)
+    assert np.allclose(buf[:-1], gsum.numpy(), rtol=1e-12, atol=1e-15)
+    assert buf[-1] == pytest.approx(lsum, rel=1e-12)
+    # and it is NOT the global mean: psum of means = world_size x the single-device mean gradient
+    l1, g1 = O.loss_and_grad(params, tr.R.double(), *d, op)
+    assert np.allclose(buf[:-1], 2 * g1.numpy(), rtol=1e-9, atol=1e-14)

@@ -1,0 +1,54 @@
+"""torchrun --nproc-per-node N tools/check_multigpu.py : the multi-GPU training loop (one process per GPU,
+NCCL all-reduce of [grad, loss]) against the oracle's multi-device loop (psum = SUM of per-device means,
+trainer.py:829-830) from the same initial parameters."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import torch.distributed as dist
+
+import util
+from jax_dips_b200 import mesh, problems, trainer as ntrainer
+from oracle import nbm_oracle as O
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P = problems.sphere()
+    n_tr, n_lvl, epochs = 16, 32, 4
+    tr, lv, phi_grid, oprob = util.make_case(P, n_tr, n_lvl, "trilinear", torch.float64)
+    p0 = O.init_params(oprob.shape, seed=42, dtype=torch.float64)
+    od = {"optimizer_name": "custom", "learning_rate": 1e-2, "sched": {"scheduler_name": "exponential", "decay_rate": 0.975}}
+    ev = mesh.linspace_grid(*P.box, [16] * 3)
+    init_fn = ntrainer.setup(*P.setup_args())
+    sim_state, solve_fn = init_fn(lvl_gstate=lv, tr_gstate=tr, eval_gstate=ev, num_epochs=epochs, batch_size=131072,
+                                  multi_gpu=True, checkpoint_dir=None, optimizer_dict=od, init_params=p0.float(),
+                                  print_rate=0)
+    (state, epoch_store, loss_epochs) = solve_fn(sim_state)
+    T = solve_fn.trainer
+    if rank == 0:
+        grid_d = [tr.dx.double(), tr.dy.double(), tr.dz.double()]
+        p_o, losses_o = O.multi_gpu_train(p0.clone(), tr.R.double(), grid_d, oprob, epochs, 131072, world, od)
+        lk = torch.stack([l[0] for l in loss_epochs]).double()
+        lo = torch.tensor(losses_o, dtype=torch.float64)
+        e_l = float(((lk - lo).abs() / lo).max())
+        e_p = util.rel_inf(T.params.cpu(), p_o)
+        print(f"world {world}: loss trajectory rel err {e_l:.3e}, final params rel-inf {e_p:.3e}, "
+              f"losses {lk.tolist()} oracle {losses_o}")
+        assert e_l < 1e-3 and e_p < 1e-3
+        assert len(loss_epochs[0]) == world
+    # every rank must hold identical parameters
+    allp = [torch.zeros_like(T.params) for _ in range(world)]
+    dist.all_gather(allp, T.params)
+    assert all(torch.equal(a, allp[0]) for a in allp)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTIGPU OK")
+
+
+if __name__ == "__main__":
+    main()
