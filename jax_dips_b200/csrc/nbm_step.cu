@@ -478,6 +478,105 @@ __global__ void __launch_bounds__(kThreads) adjoint_kernel(nbm_shared_step_t s) 
     s.G[e] = g;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Vectorised forms of the two HBM-bound stencil kernels (used when the (y,z) plane is a multiple of 4
+// and ez is even): one thread owns 4 consecutive cells of the flattened plane, the 7 weight arrays and
+// rhs are read with 16-byte streaming loads (ld.global.cs: the 553 MB row table is touched once per
+// kernel and must not evict U / R / G, which fit in the 126 MB L2), z neighbours come from the same
+// registers, y neighbours from two 8-byte loads, x neighbours from aligned 16-byte loads.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldcs4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld22(const float* p) {  // 8-byte aligned
+    float2 a = *reinterpret_cast<const float2*>(p), b = *reinterpret_cast<const float2*>(p + 2);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
+    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+
+__global__ void __launch_bounds__(kThreads) residual4_kernel(nbm_shared_step_t s) {
+    const int plane = s.ey * s.ez;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int ix = blockIdx.y + 1;
+    if (m >= plane) return;
+    const int64_t sx = plane, sy = s.ez;
+    const int64_t ne = sx * s.ex;
+    const int64_t e = ix * sx + m;
+    // rows of the first / last y line and the z ends do not exist: their weights are zero in the table, and
+    // the neighbour reads below stay inside the lattice because 1 <= ix <= ex-2 and the plane has a halo line.
+    const bool first = (m == 0), last = (m + 4 >= plane);
+    float4 u0 = ld4(s.U + e);
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        float4 w = ldcs4(s.w + e);
+        r = make_float4(w.x * u0.x, w.y * u0.y, w.z * u0.z, w.w * u0.w);
+    }
+    r = fma4(ldcs4(s.w + 1 * ne + e), ld4(s.U + e - sx), r);
+    r = fma4(ldcs4(s.w + 2 * ne + e), ld4(s.U + e + sx), r);
+    {
+        float4 w3 = ldcs4(s.w + 3 * ne + e), w4 = ldcs4(s.w + 4 * ne + e);
+        float4 um = (m >= sy) ? ld22(s.U + e - sy) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 up = (m + 4 + sy <= plane) ? ld22(s.U + e + sy) : make_float4(0.f, 0.f, 0.f, 0.f);
+        r = fma4(w3, um, r);
+        r = fma4(w4, up, r);
+    }
+    {
+        float4 w5 = ldcs4(s.w + 5 * ne + e), w6 = ldcs4(s.w + 6 * ne + e);
+        float ul = first ? 0.f : s.U[e - 1], ur = last ? 0.f : s.U[e + 4];
+        r = fma4(w5, make_float4(ul, u0.x, u0.y, u0.z), r);
+        r = fma4(w6, make_float4(u0.y, u0.z, u0.w, ur), r);
+    }
+    if (s.nl) {
+        float4 a = ld4(s.nl + e), b = ld4(s.nl + ne + e);
+        r.x += a.x * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.x) + b.x * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.x);
+        r.y += a.y * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.y) + b.y * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.y);
+        r.z += a.z * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.z) + b.z * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.z);
+        r.w += a.w * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.w) + b.w * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.w);
+    }
+    float4 rh = ldcs4(s.rhs + e);
+    *reinterpret_cast<float4*>(s.R + e) = make_float4(r.x - rh.x, r.y - rh.y, r.z - rh.z, r.w - rh.w);
+}
+
+__global__ void __launch_bounds__(kThreads) adjoint4_kernel(nbm_shared_step_t s) {
+    const int plane = s.ey * s.ez;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int ix = blockIdx.y;
+    if (m >= plane) return;
+    const int64_t sx = plane, sy = s.ez;
+    const int64_t ne = sx * s.ex;
+    const int64_t e = ix * sx + m;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 r0 = ld4(s.R + e);
+    float4 w0 = ldcs4(s.w + e);
+    float4 g = make_float4(w0.x * r0.x, w0.y * r0.y, w0.z * r0.z, w0.w * r0.w);
+    // slot 1 (x-) of the row at x + e_x, slot 2 (x+) of the row at x - e_x, and so on
+    if (ix + 1 < s.ex) g = fma4(ldcs4(s.w + 1 * ne + e + sx), ld4(s.R + e + sx), g);
+    if (ix > 0) g = fma4(ldcs4(s.w + 2 * ne + e - sx), ld4(s.R + e - sx), g);
+    if (m + 4 + sy <= plane) g = fma4(ld22(s.w + 3 * ne + e + sy), ld22(s.R + e + sy), g);
+    if (m >= sy) g = fma4(ld22(s.w + 4 * ne + e - sy), ld22(s.R + e - sy), g);
+    {
+        // z neighbours: rows at x+1 (their slot 5) and x-1 (their slot 6); a row at the end of a y line has zero
+        // weights toward the wrapped-around cell, so the flattened +-1 access is harmless
+        const bool first = (m == 0), last = (m + 4 >= plane);
+        float4 w5 = ldcs4(s.w + 5 * ne + e), w6 = ldcs4(s.w + 6 * ne + e);
+        float w5r = last ? 0.f : s.w[5 * ne + e + 4], rr = last ? 0.f : s.R[e + 4];
+        float w6l = first ? 0.f : s.w[6 * ne + e - 1], rl = first ? 0.f : s.R[e - 1];
+        g = fma4(make_float4(w5.y, w5.z, w5.w, w5r), make_float4(r0.y, r0.z, r0.w, rr), g);
+        g = fma4(make_float4(w6l, w6.x, w6.y, w6.z), make_float4(rl, r0.x, r0.y, r0.z), g);
+    }
+    if (s.nl) {
+        float4 u0 = ld4(s.U + e), a = ld4(s.nl + e), b = ld4(s.nl + ne + e);
+        g.x += (a.x * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.x) + b.x * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.x)) * r0.x;
+        g.y += (a.y * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.y) + b.y * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.y)) * r0.y;
+        g.z += (a.z * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.z) + b.z * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.z)) * r0.z;
+        g.w += (a.w * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.w) + b.w * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.w)) * r0.w;
+    }
+    (void)z4;
+    *reinterpret_cast<float4*>(s.G + e) = g;
+}
+
 // C0: adjoint of the irregular rows: gE[c] += wE * R[p]
 __global__ void irregular_bwd_kernel(nbm_shared_step_t s) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -694,20 +793,34 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     const int sms = sm_count();
     const int stages = s.stages == 0 ? 0x3f : s.stages;
     Tasks T = make_tasks(s.ex, s.ey, s.ez, 16);
+    // 16-byte paths need aligned rows: plane % 4 == 0, ez even, and 16-byte aligned array bases
+    const bool vec4 = ((s.ey * s.ez) % 4 == 0) && (s.ez % 2 == 0) &&
+                      ((((uintptr_t)s.w | (uintptr_t)s.rhs | (uintptr_t)s.U | (uintptr_t)s.R | (uintptr_t)s.G |
+                         (uintptr_t)s.nl) & 15) == 0);
     if (stages & NBM_STAGE_FWD) {
-        int gridA = min(T.total, sms * 4);
+        int gridA = min(T.total, sms * 8);
         fwd_nodes_kernel<NET><<<gridA, kThreads, 0, st>>>(s, T);
     }
     if ((stages & NBM_STAGE_EXTRAP) && s.n_crossed > 0)
         extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
     if (stages & NBM_STAGE_RESIDUAL) {
-        dim3 g((s.ey * s.ez + kThreads - 1) / kThreads, s.ex - 2);
-        residual_kernel<<<g, kThreads, 0, st>>>(s);
+        if (vec4) {
+            dim3 g((s.ey * s.ez / 4 + kThreads - 1) / kThreads, s.ex - 2);
+            residual4_kernel<<<g, kThreads, 0, st>>>(s);
+        } else {
+            dim3 g((s.ey * s.ez + kThreads - 1) / kThreads, s.ex - 2);
+            residual_kernel<<<g, kThreads, 0, st>>>(s);
+        }
         if (s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
     }
     if (stages & NBM_STAGE_ADJOINT) {
-        dim3 g((s.ey * s.ez + kThreads - 1) / kThreads, s.ex);
-        adjoint_kernel<<<g, kThreads, 0, st>>>(s);
+        if (vec4) {
+            dim3 g((s.ey * s.ez / 4 + kThreads - 1) / kThreads, s.ex);
+            adjoint4_kernel<<<g, kThreads, 0, st>>>(s);
+        } else {
+            dim3 g((s.ey * s.ez + kThreads - 1) / kThreads, s.ex);
+            adjoint_kernel<<<g, kThreads, 0, st>>>(s);
+        }
         if (s.n_irr > 0) irregular_bwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
         if (s.n_crossed > 0) extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, st>>>(s);
     }

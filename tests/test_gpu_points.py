@@ -176,3 +176,132 @@ def test_cuda_rows_match_reference_golden(path):
         vol, area = d.prod(), d[1] * d[2]
         assert float((f[:, 12:14] - coeffs[cr][:, 12:14]).abs().max()) / vol < 5e-5
         assert float((f[:, 0:12] - coeffs[cr][:, 14:26]).abs().max()) / area < 5e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# nonlinear operator (Poisson-Boltzmann), other network shapes, optimizers, checkpoints
+# ---------------------------------------------------------------------------------------------
+def _pb_small():
+    P = problems.poisson_boltzmann(n_atoms=6, seed=3, half_width=1.0)
+    # strong operators on BOTH sides so that the nonlinear terms are a visible part of every row
+    P.nonlinear_op_p = nplan.Nonlinear.sinh(3000.0)
+    P.nonlinear_op_m = nplan.Nonlinear.sinh(400.0)
+    return P
+
+
+@pytest.mark.parametrize("path_kind", ["shared", "general"])
+def test_nonlinear_sinh_operator(path_kind):
+    """N^+(u) = kappa^2 sinh(u) (examples/biomolecules/coefficients.py:126-131) in rows, loss and gradient."""
+    P = _pb_small()
+    dt = torch.float64
+    if path_kind == "shared":
+        tr, lv, lvl, oprob, pl, shape = build(P, 16, 32)
+        dd = [tr.dx.to(dt), tr.dy.to(dt), tr.dz.to(dt)]
+    else:
+        tr, oprob, level, shape, d32 = general(P, 12, 32, 1)
+        pl = nplan.PointsPlan(level, 0, tr.num_points())
+        dd = [torch.tensor(v, dtype=dt) for v in d32]
+    params = O.init_params(oprob.shape, seed=9, dtype=dt) * 3.0      # larger u so that sinh is not ~linear
+    loss_o, grad_o = O.loss_and_grad(params, tr.R.to(dt), *dd, oprob)
+    # the nonlinear term must matter in this test
+    lin = O.OracleProblem(oprob.phi_fn, oprob.mu_m_fn, oprob.mu_p_fn, oprob.k_m_fn, oprob.k_p_fn, oprob.f_m_fn,
+                          oprob.f_p_fn, oprob.alpha_fn, oprob.beta_fn, oprob.dir_bc_fn, oprob.bounds, oprob.shape)
+    loss_lin, _ = O.loss_and_grad(params, tr.R.to(dt), *dd, lin)
+    assert abs(float(loss_lin) - float(loss_o)) / float(loss_o) > 1e-3
+    with torch.cuda.device(DEV):
+        nplan.upload_params(shape, params.float().to(DEV))
+        lg = pl.loss_grad_launch().cpu()
+    assert abs(float(lg[-1]) - float(loss_o)) / float(loss_o) < TOL_LOSS
+    assert util.rel_inf(lg[:-1], grad_o) < TOL_LOSS
+
+
+@pytest.mark.parametrize("shape_args", [(2, 10, 1, 3), (1, 10, 1, 1), (3, 10, 1, 1)])
+def test_other_network_shapes(shape_args):
+    P = problems.sphere()
+    net = O.NetShape(*shape_args)
+    tr, lv, lvl, oprob, pl, shape = build(P, 12, 24, net=net)
+    dt = torch.float64
+    params = O.init_params(net, seed=4, dtype=dt)
+    dd = [tr.dx.to(dt), tr.dy.to(dt), tr.dz.to(dt)]
+    loss_o, grad_o = O.loss_and_grad(params, tr.R.to(dt), *dd, oprob)
+    with torch.cuda.device(DEV):
+        nplan.upload_params(shape, params.float().to(DEV))
+        lg = pl.loss_grad_launch().cpu()
+    assert lg.numel() == net.n_params + 1
+    assert abs(float(lg[-1]) - float(loss_o)) / float(loss_o) < TOL_LOSS
+    assert util.rel_inf(lg[:-1], grad_o) < TOL_LOSS
+
+
+def test_unsupported_network_shape_fails_loudly():
+    from jax_dips_b200 import _cabi
+    P = problems.sphere()
+    with pytest.raises(_cabi.NbmError):
+        tr, lv, lvl, oprob, pl, shape = build(P, 8, 16, net=O.NetShape(2, 7, 1, 1))
+        with torch.cuda.device(DEV):
+            nplan.upload_params(shape, O.init_params(O.NetShape(2, 7, 1, 1)).to(DEV))
+            pl.loss_grad_launch()
+
+
+@pytest.mark.parametrize("name", ["custom", "adam", "rmsprop"])
+def test_update_kernel_matches_optax_semantics(name):
+    """nbm_apply_update_f32 against a float64 restatement of the optax chains (optimizers.py:33-54, 76-88)."""
+    import ctypes as C
+    from jax_dips_b200 import _cabi as cabi
+    n, steps = 167, 5
+    g = torch.Generator().manual_seed(0)
+    params0 = torch.randn(n, generator=g, dtype=torch.float64) * 0.1
+    grads = [torch.randn(n, generator=g, dtype=torch.float64) * s for s in (5.0, 0.01, 1.0, 0.2, 3.0)]
+    lr, decay = 1e-2, 0.9
+    # float64 restatement
+    p = params0.clone(); m = torch.zeros(n, dtype=torch.float64); v = torch.zeros(n, dtype=torch.float64)
+    for t, gr in enumerate(grads):
+        if name == "custom":
+            gn = gr.norm()
+            gr = gr if gn < 1.0 else gr / gn
+        if name == "rmsprop":
+            v = 0.9 * v + 0.1 * gr * gr
+            upd = gr / torch.sqrt(v + 1e-8)
+            step = lr
+        else:
+            m = 0.9 * m + 0.1 * gr; v = 0.999 * v + 0.001 * gr * gr
+            upd = (m / (1 - 0.9 ** (t + 1))) / (torch.sqrt(v / (1 - 0.999 ** (t + 1))) + 1e-8)
+            step = lr * decay ** (t / 1000) if name == "custom" else lr
+        p = p - step * upd
+    kind = {"custom": 0, "adam": 1, "rmsprop": 2}[name]
+    o = cabi.Optimizer(n, lr, decay, 1000.0, 1.0, 0.9, 0.9 if name == "rmsprop" else 0.999, 1e-8, kind, 0)
+    with torch.cuda.device(DEV):
+        pk = params0.float().to(DEV); st = torch.zeros(2 * n, device=DEV); cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+        hist = torch.zeros(8, device=DEV)
+        for t, gr in enumerate(grads):
+            lg = torch.cat((gr.float(), torch.tensor([float(t)]))).to(DEV)
+            cabi.check(cabi.lib().nbm_apply_update_f32(C.byref(o), cabi.ptr(lg), cabi.ptr(pk), cabi.ptr(st), cabi.ptr(cnt),
+                                                       cabi.ptr(hist), cabi.stream_ptr()))
+        torch.cuda.synchronize()
+    assert int(cnt.item()) == steps
+    assert torch.equal(hist[:steps].cpu(), torch.arange(steps).float())
+    assert util.rel_inf(pk.cpu(), p) < 1e-5
+
+
+def test_checkpoint_roundtrip_and_restart(tmp_path):
+    """same dict keys as the reference's pickle (trainer.py:340-351); restart restores weights and optimizer state."""
+    import pickle
+    P = problems.no_jump()
+    lo, hi = P.box
+    tr = mesh.linspace_grid(lo, hi, [8] * 3); lv = mesh.linspace_grid(lo, hi, [12] * 3); ev = mesh.linspace_grid(lo, hi, [8] * 3)
+    init_fn = ntrainer.setup(*P.setup_args())
+    ck = str(tmp_path / "ck")
+    kw = dict(lvl_gstate=lv, tr_gstate=tr, eval_gstate=ev, num_epochs=8, batch_size=512, device=DEV, print_rate=0)
+    s0, solve = init_fn(checkpoint_dir=ck, **kw)
+    solve(s0)
+    T = solve.trainer
+    files = sorted(os.listdir(ck))
+    assert files == ["checkpoint_8"]
+    state = pickle.load(open(os.path.join(ck, files[0]), "rb"))
+    assert set(state) == {"opt_state", "params", "epoch", "batch_size", "resolution"}
+    assert "double_mlp/~mlp_p_fn/linear_1" in state["params"]
+    s1, solve2 = init_fn(checkpoint_dir=None, restart=True, restart_checkpoint_dir=ck, **kw)
+    T2 = ntrainer.Trainer(lv, tr, ev, s1, T.sim_state_fn, num_epochs=8, batch_size=512, restart=True,
+                          restart_checkpoint_dir=ck, device=DEV, checkpoint_dir=None)
+    assert torch.equal(T2.params.cpu(), T.params.cpu())
+    assert torch.equal(T2.opt_state.cpu(), T.opt_state.cpu())
+    assert int(T2.opt_count.item()) == int(T.opt_count.item()) == 8
