@@ -42,8 +42,10 @@ def parse():
     ap.add_argument("--workload", default="sphere", choices=["sphere", "star", "stars", "dragon_like", "poisson_boltzmann"])
     ap.add_argument("--grid", type=int, default=256, help="training points per axis per GPU-slab (x grows with N: weak scaling)")
     ap.add_argument("--lvl", type=int, default=128)
+    ap.add_argument("--interp", default="trilinear", choices=["trilinear", "quadratic"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=12288)
     return ap.parse_args()
 
@@ -123,7 +125,7 @@ def cpu_baseline(problem, args, n_sample, steps=1, warmup=0):
     import util
     from oracle import nbm_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    tr, lv, phi_grid, oprob = util.make_case(problem, [args.grid] * 3, args.lvl, "trilinear", torch.float32)
+    tr, lv, phi_grid, oprob = util.make_case(problem, [args.grid] * 3, args.lvl, args.interp, torch.float32)
     n = tr.num_points()
     stride = max(1, n // n_sample)
     # build the sample without materialising the whole (n,3) point list
@@ -196,7 +198,7 @@ def main():
     net = nplan.NetShape()
     P = net.n_params
     phi_lvl = fns.phi_fn(lv.R.to(dev))
-    lvl = nplan.LevelSet(lv, phi_lvl, interp="trilinear", perturb_eps=1e-10, device=dev)
+    lvl = nplan.LevelSet(lv, phi_lvl, interp=args.interp, perturb_eps=1e-10, device=dev)
     t_setup = time.time()
     pl = nplan.SharedPlan(lvl, tr, xa, xb, fns, net, nplan.Nonlinear.coerce(problem.nonlinear_op_m),
                           nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=dev)
@@ -222,6 +224,30 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # the step is a fixed sequence of launches on device-resident state: replay it as a CUDA graph (what
+    # Trainer.single_GPU_train does); eager launches remain for --no-graph and if capture is not possible
+    eager_step = step
+    used_graph = False
+    if not args.no_graph:
+        try:
+            for _ in range(2):
+                eager_step()
+            barrier()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    eager_step()
+            torch.cuda.current_stream().wait_stream(side)
+            step = graph.replay
+            used_graph = True
+        except Exception as exc:  # noqa: BLE001
+            if rank == 0:
+                print(f"# CUDA graph capture failed ({exc!r}); launching eagerly", file=sys.stderr)
+            step = eager_step
+            torch.cuda.synchronize()
 
     launches_per_step = 5 + (1 if pl.sites.n > 0 else 0) * 2 + (1 if pl.n_irr > 0 else 0) * 2 + 1  # + update kernel
 
@@ -344,9 +370,10 @@ def main():
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{args.workload}: train grid {Nx}x{Ny}x{Nz} ({n_points_total} points, "
                                        f"x-slabs of {per} planes per GPU), level set on {args.lvl}^3 lvl grid "
-                                       "(trilinear), MLP p 3-10-10-1 | m 3-1-1 tanh, optimizer custom(adam), "
+                                       f"({args.interp}), MLP p 3-10-10-1 | m 3-1-1 tanh, optimizer custom(adam), "
                                        "one batch per GPU",
                            "l2": "row tables (553 MB at 256^3) exceed the 126 MB L2; no flush needed",
+                           "cuda_graph": used_graph,
                            "crossed_sites": int(pl.sites.n), "irregular_rows": int(pl.n_irr),
                            "setup_seconds": t_setup, "loss": loss_now},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,

@@ -792,7 +792,14 @@ template <class NET>
 static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     const int sms = sm_count();
     const int stages = s.stages == 0 ? 0x3f : s.stages;
-    Tasks T = make_tasks(s.ex, s.ey, s.ez, 16);
+    // x-chunk length: 16 planes on large lattices (amortises the task set-up and the exposed first load); shorter on
+    // small ones so that every SM still gets >= 2 tasks
+    int xchunk = 16;
+    {
+        int mblocks = (s.ey * s.ez + kThreads - 1) / kThreads;
+        while (xchunk > 2 && (int64_t)mblocks * ((s.ex + xchunk - 1) / xchunk) < 2 * (int64_t)sms) xchunk >>= 1;
+    }
+    Tasks T = make_tasks(s.ex, s.ey, s.ez, xchunk);
     // 16-byte paths need aligned rows: plane % 4 == 0, ez even, and 16-byte aligned array bases
     const bool vec4 = ((s.ey * s.ez) % 4 == 0) && (s.ez % 2 == 0) &&
                       ((((uintptr_t)s.w | (uintptr_t)s.rhs | (uintptr_t)s.U | (uintptr_t)s.R | (uintptr_t)s.G |
