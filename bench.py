@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--lvl", type=int, default=128)
     ap.add_argument("--interp", default="trilinear", choices=["trilinear", "quadratic"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
+                    help="peer: partial-row reduction fused with the all-reduce over NVLink peer memory; nccl: ncclAllReduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=12288)
@@ -211,12 +213,28 @@ def main():
     spec = get_optimizer("custom", "exponential", 1e-3, 0.975)
     ostruct = cabi.Optimizer(P, 1e-3, 0.975, 1000.0, 1.0, 0.9, 0.999, 1e-8, 0, 0)
     lg = pl.loss_grad
+    comm = None
+    if world > 1 and args.allreduce == "peer":
+        from jax_dips_b200.comm import PeerComm
+        try:
+            comm = PeerComm(dev)
+            ok = 1
+        except Exception as exc:  # noqa: BLE001  (no CUDA IPC in this container, ...)
+            print(f"# rank {rank}: peer all-reduce unavailable ({exc!r})", file=sys.stderr)
+            comm, ok = None, 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # all ranks take the same path
+        if int(flag.item()) == 0:
+            comm = None
 
     def step():
         nplan.upload_params(net, params)
-        pl.loss_grad_launch()
-        if world > 1:
-            dist.all_reduce(lg, op=dist.ReduceOp.SUM)
+        if comm is not None:
+            pl.loss_grad_launch(comm=comm)
+        else:
+            pl.loss_grad_launch()
+            if world > 1:
+                dist.all_reduce(lg, op=dist.ReduceOp.SUM)
         cabi.check(L.nbm_apply_update_f32(C.byref(ostruct), cabi.ptr(lg), cabi.ptr(params), cabi.ptr(opt_state),
                                           cabi.ptr(opt_count), None, cabi.stream_ptr()))
 
@@ -229,7 +247,7 @@ def main():
     # Trainer.single_GPU_train does); eager launches remain for --no-graph and if capture is not possible
     eager_step = step
     used_graph = False
-    if not args.no_graph:
+    if not args.no_graph and world == 1:  # NCCL collectives are launched eagerly between the two graphs' worth of kernels
         try:
             for _ in range(2):
                 eager_step()
@@ -374,11 +392,17 @@ def main():
                                        "one batch per GPU",
                            "l2": "row tables (553 MB at 256^3) exceed the 126 MB L2; no flush needed",
                            "cuda_graph": used_graph,
+                           "allreduce": ("peer-memory kernel fused with the partial reduction" if comm is not None
+                                         else ("nccl" if world > 1 else "none")),
                            "crossed_sites": int(pl.sites.n), "irregular_rows": int(pl.n_irr),
                            "setup_seconds": t_setup, "loss": loss_now},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        if comm.error():
+            raise SystemExit("peer all-reduce reported a timeout")
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 

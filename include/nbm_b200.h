@@ -285,6 +285,33 @@ int nbm_apply_update_f32(const nbm_optimizer_t* opt, const float* loss_grad, flo
                          float* state, int32_t* count, float* loss_hist, nbm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K4 (multi-GPU): partial-row reduction FUSED with the gradient all-reduce over NVLink peer memory.
+ * Replaces jax.lax.psum(grads) / psum(loss) (trainer.py:829-830) = SUM over devices.
+ *
+ * Every rank owns one small communication block (allocated by the library with cudaMalloc because it
+ * must be exportable through CUDA IPC); the blocks of all ranks of the node are mapped into every
+ * process.  One single-CTA kernel per rank: sum the per-CTA partial rows -> store [grad, loss] into the
+ * own block (slot = step parity) -> release a step flag -> acquire the flags of all peers -> read all
+ * slots over NVLink and add them in rank order (bitwise identical result on every rank) -> out.
+ * A spin that lasts longer than ~2 s sets comm error state instead of hanging (nbm_comm_error()).
+ * ---------------------------------------------------------------------------------------- */
+#define NBM_IPC_HANDLE_BYTES 64
+#define NBM_COMM_MAX_RANKS 8
+/* allocate + zero the local block on the current device, export its IPC handle */
+int nbm_comm_alloc(void** local_block, unsigned char handle[NBM_IPC_HANDLE_BYTES]);
+/* map a peer's block (handle obtained from that peer's nbm_comm_alloc) */
+int nbm_comm_open_peer(const unsigned char handle[NBM_IPC_HANDLE_BYTES], void** peer_block);
+int nbm_comm_close_peer(void* peer_block);
+int nbm_comm_free(void* local_block);
+/* blocks_host[world]: device pointers of all ranks' blocks as seen from THIS process (own block at [rank]).
+ * partials[rows][np1]; step_dev: device int32 step counter of this rank (starts at 0, incremented here);
+ * out[np1] receives the sum over ranks.  np1 <= 1025. */
+int nbm_reduce_allreduce_f32(const float* partials, int rows, int np1, int rank, int world,
+                             void* const* blocks_host, int32_t* step_dev, float* out, nbm_stream_t stream);
+/* nonzero once a peer wait timed out on this device's block (host read of the block's error word) */
+int nbm_comm_error(void* local_block);
+
+/* ------------------------------------------------------------------------------------------
  * K5: post-training evaluation (trainer.py:960-977): u, grad u (analytic Jacobian of the
  * selected head), d u / d n with the central-difference normal (discretization.py:199-218).
  * pts (n,3); outputs u[n], grad_u[n*3], grad_n[n]  (grad_u / grad_n may be NULL)

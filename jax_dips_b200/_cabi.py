@@ -106,6 +106,12 @@ SYMBOLS = {
     "nbm_ffma_probe_f32": (C.c_int, [C.c_int, c_fp, _P(C.c_double), c_fp]),
     "nbm_loss_grad_shared_f32": (C.c_int, [_P(SharedStep), c_fp]),
     "nbm_loss_grad_points_f32": (C.c_int, [_P(PointsStep), c_fp]),
+    "nbm_comm_alloc": (C.c_int, [_P(C.c_void_p), C.c_char_p]),
+    "nbm_comm_open_peer": (C.c_int, [C.c_char_p, _P(C.c_void_p)]),
+    "nbm_comm_close_peer": (C.c_int, [C.c_void_p]),
+    "nbm_comm_free": (C.c_int, [C.c_void_p]),
+    "nbm_comm_error": (C.c_int, [C.c_void_p]),
+    "nbm_reduce_allreduce_f32": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_void_p), c_fp, c_fp, c_fp]),
     "nbm_apply_update_f32": (C.c_int, [_P(Optimizer), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "nbm_evaluate_f32": (C.c_int, [_P(Net), _P(Lvl), c_fp, C.c_int64, c_f, c_f, c_f, c_fp, c_fp, c_fp, c_fp]),
 }

@@ -8,6 +8,7 @@
 //
 // The network parameters live in __constant__ memory so that every FFMA takes its weight as a
 // constant-bank operand (no load, no register).
+#include <string.h>
 #include "nbm_common.cuh"
 
 namespace nbm {
@@ -775,6 +776,77 @@ __global__ void prep_params_kernel(nbm_net_t net, const float* __restrict__ para
     stage[NBM_MAXP + i] = k < hidden_len ? v * kTwoLog2e : v;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fused partial-row reduction + all-reduce over NVLink peer memory (one process per GPU, CUDA IPC)
+// ---------------------------------------------------------------------------------------------
+struct CommBlock {
+    unsigned int flag[2];   // step+1 of the last slot written, per parity
+    unsigned int error;     // set when a peer wait timed out
+    unsigned int pad;
+    float data[2][NBM_MAXP + 8];
+};
+
+struct CommPeers {
+    CommBlock* b[NBM_COMM_MAX_RANKS];
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024) reduce_allreduce_kernel(const float* __restrict__ partials, int rows, int np1,
+                                                                int rank, int world, CommPeers peers,
+                                                                int32_t* __restrict__ step_dev, float* __restrict__ out) {
+    const int i = threadIdx.x;
+    const unsigned int step = (unsigned int)*step_dev;
+    const int par = step & 1;
+    CommBlock* mine = peers.b[rank];
+    if (i < np1) {
+        float v = 0.0f;
+        for (int r = 0; r < rows; ++r) v += partials[(size_t)r * np1 + i];
+        mine->data[par][i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_fail;
+    if (i == 0) {
+        s_fail = 0;
+        st_release_sys(&mine->flag[par], step + 1);
+    }
+    // one waiting thread per peer
+    if (i > 0 && i <= world && (i - 1) != rank) {
+        const unsigned int* f = &peers.b[i - 1]->flag[par];
+        long long t0 = clock64();
+        while ((int)(ld_acquire_sys(f) - (step + 1)) < 0) {
+            if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz: report instead of hanging the device
+                atomicExch(&mine->error, 1u);
+                atomicExch(&s_fail, 1);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (i < np1) {
+        float v = 0.0f;
+        for (int r = 0; r < world; ++r) v += (r == rank) ? mine->data[par][i] : ld_relaxed_sys(&peers.b[r]->data[par][i]);
+        out[i] = s_fail ? __int_as_float(0x7fc00000) : v;
+    }
+    __syncthreads();
+    if (i == 0) *step_dev = (int32_t)(step + 1);
+}
+
 static int g_sm_count = 0;
 static int sm_count() {
     if (g_sm_count == 0) {
@@ -1134,6 +1206,55 @@ int nbm_loss_grad_points_f32(const nbm_points_step_t* s, nbm_stream_t stream) {
     NBM_REQUIRE((s->nonlinear_m == NBM_NL_NONE && s->nonlinear_p == NBM_NL_NONE) || s->nl,
                 "nonlinear operator needs the nl table");
     return dispatch_points(*s, as_stream(stream));
+}
+
+
+int nbm_comm_alloc(void** local_block, unsigned char handle[NBM_IPC_HANDLE_BYTES]) {
+    NBM_REQUIRE(local_block && handle, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == NBM_IPC_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    int rc = cuda_check(cudaMalloc(&p, sizeof(CommBlock)), "cudaMalloc(comm block)");
+    if (rc) return rc;
+    rc = cuda_check(cudaMemset(p, 0, sizeof(CommBlock)), "memset(comm block)");
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    rc = cuda_check(cudaIpcGetMemHandle(&h, p), "cudaIpcGetMemHandle");
+    if (rc) return rc;
+    memcpy(handle, &h, sizeof(h));
+    *local_block = p;
+    return NBM_OK;
+}
+
+int nbm_comm_open_peer(const unsigned char handle[NBM_IPC_HANDLE_BYTES], void** peer_block) {
+    NBM_REQUIRE(handle && peer_block, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    return cuda_check(cudaIpcOpenMemHandle(peer_block, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+int nbm_comm_close_peer(void* peer_block) { return cuda_check(cudaIpcCloseMemHandle(peer_block), "cudaIpcCloseMemHandle"); }
+int nbm_comm_free(void* local_block) { return cuda_check(cudaFree(local_block), "cudaFree(comm block)"); }
+
+int nbm_comm_error(void* local_block) {
+    if (!local_block) return -1;
+    unsigned int e = 0;
+    if (cudaMemcpy(&e, &reinterpret_cast<CommBlock*>(local_block)->error, sizeof(e), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    return (int)e;
+}
+
+int nbm_reduce_allreduce_f32(const float* partials, int rows, int np1, int rank, int world, void* const* blocks_host,
+                             int32_t* step_dev, float* out, nbm_stream_t stream) {
+    NBM_REQUIRE(partials && blocks_host && step_dev && out, "null pointer");
+    NBM_REQUIRE(rows > 0 && np1 > 0 && np1 <= NBM_MAXP + 1, "bad sizes");
+    NBM_REQUIRE(world >= 1 && world <= NBM_COMM_MAX_RANKS && rank >= 0 && rank < world, "bad rank/world");
+    CommPeers peers;
+    for (int r = 0; r < NBM_COMM_MAX_RANKS; ++r) peers.b[r] = r < world ? reinterpret_cast<CommBlock*>(blocks_host[r]) : nullptr;
+    for (int r = 0; r < world; ++r) NBM_REQUIRE(peers.b[r], "null peer block");
+    int threads = ((max(np1, world + 1) + 31) / 32) * 32;
+    reduce_allreduce_kernel<<<1, threads, 0, as_stream(stream)>>>(partials, rows, np1, rank, world, peers, step_dev, out);
+    NBM_LAUNCH_CHECK("reduce_allreduce");
+    return NBM_OK;
 }
 
 int nbm_apply_update_f32(const nbm_optimizer_t* opt, const float* loss_grad, float* params, float* state,

@@ -350,14 +350,25 @@ class SharedPlan:
             for name in ("tri", "tri_area", "pos", "proj", "Cm", "Cp"):
                 pass  # kept: tests read them back; they are O(crossed sites)
 
-    def loss_grad_launch(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def loss_grad_launch(self, out: Optional[torch.Tensor] = None, comm=None) -> torch.Tensor:
         """Enqueue loss and d loss/d params for this plan's rows (parameters must have been uploaded
-        with `upload_params`).  Returns the device buffer [grad(P), loss]."""
+        with `upload_params`).  Returns the device buffer [grad(P), loss].  With `comm` (a PeerComm) the
+        final partial-row reduction is fused with the all-reduce over the ranks (SUM, psum semantics)."""
         if out is not None:
             self.step.loss_grad = cabi.ptr(out)
-        cabi.check(cabi.lib().nbm_loss_grad_shared_f32(C.byref(self.step), cabi.stream_ptr()),
-                   "nbm_loss_grad_shared_f32")
-        return out if out is not None else self.loss_grad
+        target = out if out is not None else self.loss_grad
+        if comm is None:
+            cabi.check(cabi.lib().nbm_loss_grad_shared_f32(C.byref(self.step), cabi.stream_ptr()),
+                       "nbm_loss_grad_shared_f32")
+            return target
+        self.step.stages = 0x1f            # everything but the reduction
+        try:
+            cabi.check(cabi.lib().nbm_loss_grad_shared_f32(C.byref(self.step), cabi.stream_ptr()),
+                       "nbm_loss_grad_shared_f32")
+        finally:
+            self.step.stages = 0
+        comm.reduce_allreduce(self.partials, self.step.n_partial_rows, self.net.n_params + 1, target)
+        return target
 
     # ---- read-backs for tests -----------------------------------------------------------------
     def point_view(self, t: torch.Tensor) -> torch.Tensor:

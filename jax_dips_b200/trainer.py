@@ -135,7 +135,8 @@ class Trainer:
                  results_dir: str = "./", loss_plot_name: str = "solver_loss", optimizer_dict: dict = None,
                  restart: bool = False, restart_checkpoint_dir: str = "./checkpoints", print_rate: int = 1,
                  model_dict: dict = None, phi_interp: str = "trilinear", perturb_eps: float = 1e-10,
-                 device=None, init_params: Optional[torch.Tensor] = None, use_cuda_graph: bool = True):
+                 device=None, init_params: Optional[torch.Tensor] = None, use_cuda_graph: bool = True,
+                 allreduce: str = "peer"):
         global stop_training
         if algorithm != 0:
             # discretization.py:146-148 references undefined attributes for algorithm=1
@@ -151,6 +152,10 @@ class Trainer:
         self.mgrad_over_pgrad_scalefactor = mgrad_over_pgrad_scalefactor
         self.restart_checkpoint_dir = restart_checkpoint_dir
         self.use_cuda_graph = use_cuda_graph
+        if allreduce not in ("peer", "nccl"):
+            raise ValueError("allreduce must be 'peer' (fused NVLink peer-memory kernel) or 'nccl'")
+        self.allreduce_kind = allreduce
+        self._comm = None
         cabi.lib()  # fail here, loudly, if the CUDA library is not built
 
         self.TD = data_management.TrainData(tr_gstate, lvl_set_fn, refine=False, refine_lod=False,
@@ -277,15 +282,38 @@ class Trainer:
 
     def _step(self, plan, loss_hist: Optional[torch.Tensor], allreduce: bool):
         """update (trainer.py:783-789) / update_multi_gpu (:824-834) on the current stream"""
-        lg = self.loss_and_grad(self.params, plan)
-        if allreduce:
-            d = _dist()
-            if d is not None and d.get_world_size() > 1:
+        d = _dist() if allreduce else None
+        if d is not None and d.get_world_size() > 1:
+            comm = self._peer_comm() if (self.allreduce_kind == "peer" and isinstance(plan, SharedPlan)) else None
+            upload_params(self.net, self.params)
+            if comm is not None:
+                lg = plan.loss_grad_launch(comm=comm)    # reduction fused with the psum over NVLink peer memory
+            else:
+                lg = plan.loss_grad_launch()
                 d.all_reduce(lg, op=d.ReduceOp.SUM)      # psum of grads and loss (:829-830)
+        else:
+            lg = self.loss_and_grad(self.params, plan)
         cabi.check(cabi.lib().nbm_apply_update_f32(C.byref(self._optimizer_struct()), cabi.ptr(lg),
                                                    cabi.ptr(self.params), cabi.ptr(self.opt_state),
                                                    cabi.ptr(self.opt_count), cabi.ptr(loss_hist),
                                                    cabi.stream_ptr()), "nbm_apply_update_f32")
+
+    def _peer_comm(self):
+        if self._comm is None:
+            from .comm import PeerComm
+            d = _dist()
+            try:
+                comm, ok = PeerComm(self.device), 1
+            except Exception as exc:  # noqa: BLE001
+                logger.warning("peer all-reduce unavailable (%s); using NCCL", exc)
+                comm, ok = None, 0
+            flag = torch.tensor([ok], device=self.device)
+            d.all_reduce(flag, op=d.ReduceOp.MIN)        # every rank must take the same path
+            if int(flag.item()) == 0:
+                self.allreduce_kind = "nccl"
+                return None
+            self._comm = comm
+        return self._comm
 
     def _graph_step(self, plan, loss_hist, allreduce: bool):
         """replay the step as a CUDA graph (launch-bound at small grids)"""
