@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--lvl", type=int, default=128)
     ap.add_argument("--interp", default="trilinear", choices=["trilinear", "quadratic"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--zoom", type=int, default=0, help=">0: time the general per-point path at cell size = spacing/2^zoom")
     ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
                     help="peer: partial-row reduction fused with the all-reduce over NVLink peer memory; nccl: ncclAllReduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -202,6 +203,30 @@ def main():
     phi_lvl = fns.phi_fn(lv.R.to(dev))
     lvl = nplan.LevelSet(lv, phi_lvl, interp=args.interp, perturb_eps=1e-10, device=dev)
     t_setup = time.time()
+    if args.zoom > 0:
+        if world != 1:
+            raise SystemExit("--zoom is a single-GPU measurement")
+        f = 0.5 ** args.zoom
+        level = nplan.GeneralLevel(lvl, tr, (float(tr.dx) * f, float(tr.dy) * f, float(tr.dz) * f), fns, net,
+                                   nplan.Nonlinear.coerce(problem.nonlinear_op_m),
+                                   nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=dev)
+        gp = nplan.PointsPlan(level, 0, tr.num_points())
+        torch.cuda.synchronize()
+        nplan.upload_params(net, haiku_init(net, 42).to(dev))
+        for _ in range(3):
+            gp.loss_grad_launch()
+        torch.cuda.synchronize()
+        z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        z0.record()
+        for _ in range(args.steps):
+            gp.loss_grad_launch()
+        z1.record()
+        torch.cuda.synchronize()
+        msz = z0.elapsed_time(z1) / args.steps
+        print(json.dumps({"metric": METRIC, "value": tr.num_points() / (msz * 1e-3), "unit": UNIT, "n_gpus": 1,
+                          "ms_per_step": msz, "config": {"workload": f"{args.workload} {args.grid}^3 general path zoom {args.zoom}",
+                                                         "crossed_sites": int(level.sites.n), "irregular_rows": int(level.n_irr)}}))
+        return
     pl = nplan.SharedPlan(lvl, tr, xa, xb, fns, net, nplan.Nonlinear.coerce(problem.nonlinear_op_m),
                           nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=dev)
     torch.cuda.synchronize()

@@ -263,10 +263,14 @@ typedef struct {
     float* partials; int n_partial_rows;
     float* loss_grad;
     float* rows;                     /* optional [n_points]: lhs/diag - rhs/diag of every row of the batch (may be NULL) */
+    /* the 7 displaced lattices: coordinates [7][nx], [7][ny], [7][nz] (slot k = grid + shift_k, formed in fp32 like
+     * `point[0] - dx`, discretization.py:348-353) and work arrays [7][n_points] */
+    const float* xs7; const float* ys7; const float* zs7;
+    float* U7; float* G7;
 } nbm_points_step_t;
 
-/* General path (any cell size, any contiguous batch): 7 network evaluations per point, fused
- * forward + backward, no neighbour sharing. */
+/* General path (any cell size, any contiguous batch): 7 network evaluations per point (the reference
+ * does 197), no neighbour sharing: the node kernels of the shared path run over the 7 displaced lattices. */
 int nbm_loss_grad_points_f32(const nbm_points_step_t* s, nbm_stream_t stream);
 
 /* optax chain of solvers/optimizers.py:33-54 on device: clip_by_global_norm(max_norm) ->

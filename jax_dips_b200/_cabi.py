@@ -78,7 +78,8 @@ class PointsStep(C.Structure):
                 ("n_irr", C.c_int64), ("irr_wE", c_fp), ("irr_c", c_fp), ("irr_nl", c_fp), ("irr_nlw", c_fp),
                 ("inv_n_points", c_f),
                 ("E", c_fp), ("gE", c_fp),
-                ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp), ("rows", c_fp)]
+                ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp), ("rows", c_fp),
+                ("xs7", c_fp), ("ys7", c_fp), ("zs7", c_fp), ("U7", c_fp), ("G7", c_fp)]
 
 
 class Optimizer(C.Structure):

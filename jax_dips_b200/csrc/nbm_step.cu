@@ -361,29 +361,64 @@ __host__ __device__ inline Tasks make_tasks(int ex, int ey, int ez, int xchunk) 
     return t;
 }
 
+// What the two network kernels see: `nrep` replicas of a lattice (1 for the shared path; 7 displaced copies of
+// the training grid for the general path), each with its own coordinate arrays and its own slice of side/U/G.
+struct NodeView {
+    const float *xe, *ye, *ze;   // [nrep][ex], [nrep][ey], [nrep][ez]
+    int ex, ey, ez;
+    int x_begin, x_end;          // planes walked
+    int64_t lo, hi;              // only nodes lo <= e < hi (index inside a replica) are touched
+    int64_t rep_nodes;           // replica stride of side / U / G
+    const uint8_t* side;
+    float* U;
+    const float* G;
+    const float* R;              // may be null (no loss accumulation)
+    float inv_n;
+    float* partials;
+    int row0;
+};
+
+static NodeView view_of(const nbm_shared_step_t& s) {
+    NodeView v;
+    v.xe = s.xe; v.ye = s.ye; v.ze = s.ze;
+    v.ex = s.ex; v.ey = s.ey; v.ez = s.ez;
+    v.x_begin = 0; v.x_end = s.ex;
+    v.lo = 0; v.hi = (int64_t)s.ex * s.ey * s.ez;
+    v.rep_nodes = v.hi;
+    v.side = s.side; v.U = s.U; v.G = s.G; v.R = s.R;
+    v.inv_n = s.inv_n_points; v.partials = s.partials; v.row0 = 0;
+    return v;
+}
+
 // A: U[e] = u(node e)   (evaluate_solution_fn, trainer.py:836-844)
 template <class NET>
-__global__ void __launch_bounds__(kThreads) fwd_nodes_kernel(nbm_shared_step_t s, Tasks T) {
+__global__ void __launch_bounds__(kThreads) fwd_nodes_kernel(NodeView v, Tasks T) {
+    const int rep = blockIdx.y;
+    const float* xe = v.xe + (size_t)rep * v.ex;
+    const float* ye = v.ye + (size_t)rep * v.ey;
+    const float* ze = v.ze + (size_t)rep * v.ez;
+    const uint8_t* side = v.side + rep * v.rep_nodes;
+    float* U = v.U + rep * v.rep_nodes;
     for (int task = blockIdx.x; task < T.total; task += gridDim.x) {
         int mb = task % T.mblocks, xc = task / T.mblocks;
         int m = mb * kThreads + threadIdx.x;
         if (m >= T.plane) continue;
-        int iy = m / s.ez, iz = m - iy * s.ez;
-        float y = __ldg(s.ye + iy), z = __ldg(s.ze + iz);
-        int x0 = xc * T.xchunk, x1 = min(s.ex, x0 + T.xchunk);
-        size_t e = (size_t)x0 * T.plane + m;
-        float x_n = __ldg(s.xe + x0);
-        uint8_t sd_n = __ldg(s.side + e);
+        int iy = m / v.ez, iz = m - iy * v.ez;
+        float y = __ldg(ye + iy), z = __ldg(ze + iz);
+        int x0 = v.x_begin + xc * T.xchunk, x1 = min(v.x_end, x0 + T.xchunk);
+        int64_t e = (int64_t)x0 * T.plane + m;
+        float x_n = __ldg(xe + x0);
+        uint8_t sd_n = __ldg(side + e);
         for (int ix = x0; ix < x1; ++ix) {
             float x = x_n;
             bool plus = (sd_n & 1) != 0;
-            size_t e_cur = e;
+            int64_t e_cur = e;
             if (ix + 1 < x1) {
                 e += T.plane;
-                sd_n = __ldg(s.side + e);
-                x_n = __ldg(s.xe + ix + 1);
+                sd_n = __ldg(side + e);
+                x_n = __ldg(xe + ix + 1);
             }
-            s.U[e_cur] = NET::eval(plus, x, y, z);
+            if (e_cur >= v.lo && e_cur < v.hi) U[e_cur] = NET::eval(plus, x, y, z);
         }
     }
 }
@@ -635,38 +670,47 @@ __device__ __forceinline__ void block_reduce_store(typename NET::Acc& acc, float
 // C2: d loss/d theta = sum_nodes (G/n) d u(node)/d theta, loss = sum_rows 0.5 R^2 / n
 // (value_and_grad(self.loss), trainer.py:786; mean of optax.l2_loss, :899-901)
 template <class NET>
-__global__ void __launch_bounds__(kThreads, 1) node_grad_kernel(nbm_shared_step_t s, Tasks T) {
+__global__ void __launch_bounds__(kThreads, 1) node_grad_kernel(NodeView v, Tasks T) {
     typename NET::Acc acc;
     acc.zero();
     float loss = 0.0f;
+    const int rep = blockIdx.y;
+    const float* xe = v.xe + (size_t)rep * v.ex;
+    const float* ye = v.ye + (size_t)rep * v.ey;
+    const float* ze = v.ze + (size_t)rep * v.ez;
+    const uint8_t* side = v.side + rep * v.rep_nodes;
+    const float* G = v.G + rep * v.rep_nodes;
+    const float* R = v.R;  // only the shared path (one replica) accumulates the loss here
     for (int task = blockIdx.x; task < T.total; task += gridDim.x) {
         int mb = task % T.mblocks, xc = task / T.mblocks;
         int m = mb * kThreads + threadIdx.x;
         if (m >= T.plane) continue;
-        int iy = m / s.ez, iz = m - iy * s.ez;
-        float y = __ldg(s.ye + iy), z = __ldg(s.ze + iz);
-        int x0 = xc * T.xchunk, x1 = min(s.ex, x0 + T.xchunk);
+        int iy = m / v.ez, iz = m - iy * v.ez;
+        float y = __ldg(ye + iy), z = __ldg(ze + iz);
+        int x0 = v.x_begin + xc * T.xchunk, x1 = min(v.x_end, x0 + T.xchunk);
         // software pipeline: the loads of plane ix+1 are in flight while plane ix is computed (only 8 warps
         // per SM fit beside the 167 accumulators, so HBM latency has to be hidden explicitly)
-        size_t e = (size_t)x0 * T.plane + m;
-        float g_n = __ldg(s.G + e), r_n = __ldg(s.R + e), x_n = __ldg(s.xe + x0);
-        uint8_t sd_n = __ldg(s.side + e);
+        int64_t e = (int64_t)x0 * T.plane + m;
+        bool in_n = e >= v.lo && e < v.hi;
+        float g_n = in_n ? __ldg(G + e) : 0.0f, r_n = (R && in_n) ? __ldg(R + e) : 0.0f, x_n = __ldg(xe + x0);
+        uint8_t sd_n = __ldg(side + e);
         for (int ix = x0; ix < x1; ++ix) {
-            float g = g_n * s.inv_n_points, r = r_n, x = x_n;
+            float g = g_n * v.inv_n, r = r_n, x = x_n;
             bool plus = (sd_n & 1) != 0;
             if (ix + 1 < x1) {
                 e += T.plane;
-                g_n = __ldg(s.G + e);
-                r_n = __ldg(s.R + e);
-                sd_n = __ldg(s.side + e);
-                x_n = __ldg(s.xe + ix + 1);
+                in_n = e >= v.lo && e < v.hi;
+                g_n = in_n ? __ldg(G + e) : 0.0f;
+                r_n = (R && in_n) ? __ldg(R + e) : 0.0f;
+                sd_n = __ldg(side + e);
+                x_n = __ldg(xe + ix + 1);
             }
             loss = fmaf(0.5f * r, r, loss);
             if (g != 0.0f) NET::grad(plus, x, y, z, g, acc);
         }
     }
-    loss *= s.inv_n_points;
-    block_reduce_store<NET>(acc, loss, s.partials);
+    loss *= v.inv_n;
+    block_reduce_store<NET>(acc, loss, v.partials + (size_t)(v.row0 + rep * gridDim.x) * (NET::NP + 1));
 }
 
 // K4a: deterministic sum of the per-CTA partial rows
@@ -858,7 +902,7 @@ static int sm_count() {
     return g_sm_count;
 }
 
-constexpr int kPartialRows = 148 * 2;  // upper bound on the node_grad grid
+constexpr int kPartialRows = 148 * 9;  // shared path: <= 148 rows; general path: 7 replicas x 148 + rows + extrap rows
 
 template <class NET>
 static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
@@ -878,7 +922,7 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
                          (uintptr_t)s.nl) & 15) == 0);
     if (stages & NBM_STAGE_FWD) {
         int gridA = min(T.total, sms * 8);
-        fwd_nodes_kernel<NET><<<gridA, kThreads, 0, st>>>(s, T);
+        fwd_nodes_kernel<NET><<<gridA, kThreads, 0, st>>>(view_of(s), T);
     }
     if ((stages & NBM_STAGE_EXTRAP) && s.n_crossed > 0)
         extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
@@ -905,7 +949,7 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     }
     int gridC = min(T.total, min(kPartialRows, sms));
     if (gridC > s.n_partial_rows) gridC = s.n_partial_rows;
-    if (stages & NBM_STAGE_GRAD) node_grad_kernel<NET><<<gridC, kThreads, 0, st>>>(s, T);
+    if (stages & NBM_STAGE_GRAD) node_grad_kernel<NET><<<gridC, kThreads, 0, st>>>(view_of(s), T);
     if (stages & NBM_STAGE_REDUCE)
         reduce_partials_kernel<<<(NET::NP + 1 + 127) / 128, 128, 0, st>>>(s.partials, gridC, NET::NP + 1, s.loss_grad);
     return cuda_check(cudaGetLastError(), "shared step launch");
@@ -988,28 +1032,21 @@ __global__ void __launch_bounds__(kThreads) points_extrap_kernel(PointsArgs a) {
     }
 }
 
-// Z1: rows of the batch
-template <class NET>
-__global__ void __launch_bounds__(kThreads, 1) points_rows_kernel(PointsArgs a) {
+// Z1: rows of the batch, pointwise on the 7 site values U7[k][p] (written by fwd_nodes over the 7 displaced
+// lattices): residual, loss partial, and d loss / d u(site) into G7[k][p] for the per-site backward kernel
+__global__ void __launch_bounds__(kThreads) points_rows_kernel(PointsArgs a, const float* __restrict__ U7,
+                                                               float* __restrict__ G7, int row0, int np1) {
     const nbm_points_step_t& s = a.s;
-    typename NET::Acc acc;
-    acc.zero();
-    float loss = 0.0f;
     const int64_t N = a.n_points;
+    float loss = 0.0f;
     for (int64_t p = s.p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < s.p1;
          p += (int64_t)gridDim.x * blockDim.x) {
-        int k = (int)(p % s.nz);
-        int64_t t = p / s.nz;
-        int j = (int)(t % s.ny), i = (int)(t / s.ny);
-        float x = __ldg(s.xs + i), y = __ldg(s.ys + j), z = __ldg(s.zs + k);
         float u[7], w[7];
-        float r = -s.rhs[p];
+        float r = -__ldg(s.rhs + p);
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
-            w[q] = s.w[q * N + p];
-            bool plus = (s.side[q * N + p] & 1) != 0;
-            u[q] = (w[q] != 0.0f || q == 0) ? NET::eval(plus, x + a.shift[q][0], y + a.shift[q][1], z + a.shift[q][2])
-                                            : 0.0f;
+            w[q] = __ldg(s.w + q * N + p);
+            u[q] = U7[q * N + p];
             r = fmaf(w[q], u[q], r);
         }
         float nlw0 = 0.0f, nlw1 = 0.0f;
@@ -1035,40 +1072,49 @@ __global__ void __launch_bounds__(kThreads, 1) points_rows_kernel(PointsArgs a) 
         }
         loss = fmaf(0.5f * r, r, loss);
         if (s.rows) s.rows[p] = r;
-        float g = r * s.inv_n_points;
         if (q_irr >= 0) {
-            // each crossed site belongs to exactly one (point, slot): plain stores
+            // each crossed site belongs to exactly one (point, slot): plain stores (gE carries the un-normalised
+            // residual weight; the 1/n of the mean is applied by the backward kernels)
 #pragma unroll
             for (int q = 0; q < 7; ++q) {
                 int32_t c = s.irr_c[(int64_t)q_irr * 7 + q];
                 if (c >= 0) {
-                    float ge = s.irr_wE[(int64_t)q_irr * 7 + q] * g;
+                    float ge = s.irr_wE[(int64_t)q_irr * 7 + q] * r;
                     if (q == 0) {
                         uint8_t nlr = s.irr_nl[q_irr];
                         if (nlr) {
                             float Ec = s.E[c];
                             ge = fmaf(s.irr_nlw[q_irr] * (nlr == 1 ? nl_deriv(s.nonlinear_m, s.nl_coef_m, Ec)
-                                                                   : nl_deriv(s.nonlinear_p, s.nl_coef_p, Ec)), g, ge);
+                                                                   : nl_deriv(s.nonlinear_p, s.nl_coef_p, Ec)), r, ge);
                         }
                     }
-                    s.gE[c] = ge;
+                    s.gE[c] = ge * s.inv_n_points;
                 }
             }
         }
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
-            float gq = w[q] * g;
+            float gq = w[q] * r;
             if (q == 0 && s.nl)
                 gq = fmaf(nlw0 * nl_deriv(s.nonlinear_m, s.nl_coef_m, u[0]) +
-                              nlw1 * nl_deriv(s.nonlinear_p, s.nl_coef_p, u[0]), g, gq);
-            if (gq != 0.0f) {
-                bool plus = (s.side[q * N + p] & 1) != 0;
-                NET::grad(plus, x + a.shift[q][0], y + a.shift[q][1], z + a.shift[q][2], gq, acc);
-            }
+                              nlw1 * nl_deriv(s.nonlinear_p, s.nl_coef_p, u[0]), r, gq);
+            G7[q * N + p] = gq;
         }
     }
-    loss *= s.inv_n_points;
-    block_reduce_store<NET>(acc, loss, s.partials);
+    // loss partial: one row per CTA, gradient entries zero
+    __shared__ float red[kThreads / 32];
+    float v = loss * s.inv_n_points;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float* row = s.partials + (size_t)(row0 + blockIdx.x) * np1;
+    for (int i = threadIdx.x; i < np1 - 1; i += kThreads) row[i] = 0.0f;
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int wv = 0; wv < kThreads / 32; ++wv) t += red[wv];
+        row[np1 - 1] = t;
+    }
 }
 
 // Z2: backward through the extrapolation of the crossed sites of the batch
@@ -1099,29 +1145,51 @@ __global__ void __launch_bounds__(kThreads, 1) points_extrap_bwd_kernel(PointsAr
 template <class NET>
 static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     const int sms = sm_count();
+    const int np1 = NET::NP + 1;
     PointsArgs a;
     a.s = s;
     const float sh[7][3] = {{0, 0, 0}, {-s.dx, 0, 0}, {s.dx, 0, 0}, {0, -s.dy, 0}, {0, s.dy, 0}, {0, 0, -s.dz}, {0, 0, s.dz}};
     for (int q = 0; q < 7; ++q)
         for (int c = 0; c < 3; ++c) a.shift[q][c] = sh[q][c];
     a.n_points = (int64_t)s.nx * s.ny * s.nz;
-    int64_t nb = s.p1 - s.p0;
-    int rows_max = s.n_partial_rows;
-    int gridE = 0;
-    if (s.n_crossed > 0) {
-        gridE = (int)min((int64_t)sms, (s.n_crossed * 32 + kThreads - 1) / kThreads);
-        points_extrap_kernel<NET><<<(unsigned)min((int64_t)sms * 4, (s.n_crossed * 32 + kThreads - 1) / kThreads),
-                                    kThreads, 0, st>>>(a);
+    const int64_t nb = s.p1 - s.p0;
+    const int plane = s.ny * s.nz;
+    // the x planes that hold the batch
+    NodeView v;
+    v.xe = s.xs7; v.ye = s.ys7; v.ze = s.zs7;
+    v.ex = s.nx; v.ey = s.ny; v.ez = s.nz;
+    v.x_begin = (int)(s.p0 / plane);
+    v.x_end = (int)((s.p1 + plane - 1) / plane);
+    v.lo = s.p0; v.hi = s.p1;
+    v.rep_nodes = a.n_points;
+    v.side = s.side; v.U = s.U7; v.G = s.G7; v.R = nullptr;
+    v.inv_n = s.inv_n_points; v.partials = s.partials;
+    int xchunk = 16;
+    {
+        int mblocks = (plane + kThreads - 1) / kThreads;
+        int nxp = v.x_end - v.x_begin;
+        while (xchunk > 2 && (int64_t)mblocks * ((nxp + xchunk - 1) / xchunk) * 7 < 2 * (int64_t)sms) xchunk >>= 1;
     }
-    int gridR = (int)min((int64_t)sms, (nb + kThreads - 1) / kThreads);
-    if (gridR + gridE > rows_max) {
-        set_error("partials buffer has %d rows, %d needed", rows_max, gridR + gridE);
+    Tasks T = make_tasks(v.x_end - v.x_begin, s.ny, s.nz, xchunk);
+    const int gridF = min(T.total, sms * 2);
+    const int gridG = min(T.total, max(1, sms / 4));         // x 7 replicas: ~2 waves of the 1-CTA/SM backward kernel
+    const int gridR = (int)min((int64_t)sms * 2, (nb + kThreads - 1) / kThreads);
+    int gridE = 0;
+    if (s.n_crossed > 0) gridE = (int)min((int64_t)sms, (s.n_crossed * 32 + kThreads - 1) / kThreads);
+    const int rows_needed = 7 * gridG + gridR + gridE;
+    if (rows_needed > s.n_partial_rows) {
+        set_error("partials buffer has %d rows, %d needed", s.n_partial_rows, rows_needed);
         return NBM_ERR_WORKSPACE;
     }
-    points_rows_kernel<NET><<<gridR, kThreads, 0, st>>>(a);
-    if (gridE > 0) points_extrap_bwd_kernel<NET><<<gridE, kThreads, 0, st>>>(a, gridR);
-    reduce_partials_kernel<<<(NET::NP + 1 + 127) / 128, 128, 0, st>>>(s.partials, gridR + gridE, NET::NP + 1,
-                                                                      s.loss_grad);
+    if (s.n_crossed > 0)
+        points_extrap_kernel<NET><<<(unsigned)min((int64_t)sms * 4, (s.n_crossed * 32 + kThreads - 1) / kThreads),
+                                    kThreads, 0, st>>>(a);
+    fwd_nodes_kernel<NET><<<dim3(gridF, 7), kThreads, 0, st>>>(v, T);
+    points_rows_kernel<<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, 7 * gridG, np1);
+    v.row0 = 0;
+    node_grad_kernel<NET><<<dim3(gridG, 7), kThreads, 0, st>>>(v, T);
+    if (gridE > 0) points_extrap_bwd_kernel<NET><<<gridE, kThreads, 0, st>>>(a, 7 * gridG + gridR);
+    reduce_partials_kernel<<<(np1 + 127) / 128, 128, 0, st>>>(s.partials, rows_needed, np1, s.loss_grad);
     return cuda_check(cudaGetLastError(), "points step launch");
 }
 
@@ -1200,6 +1268,7 @@ int nbm_loss_grad_points_f32(const nbm_points_step_t* s, nbm_stream_t stream) {
     NBM_REQUIRE(s->p0 >= 0 && s->p1 > s->p0 && s->p1 <= (int64_t)s->nx * s->ny * s->nz, "bad batch range");
     NBM_REQUIRE(s->dx > 0 && s->dy > 0 && s->dz > 0, "cell size must be positive");
     NBM_REQUIRE(s->partials && s->loss_grad && s->n_partial_rows >= 2, "null work buffers");
+    NBM_REQUIRE(s->U7 && s->G7 && s->xs7 && s->ys7 && s->zs7, "null site work buffers / displaced coordinate arrays");
     NBM_REQUIRE(s->n_crossed == 0 || (s->c_site && s->c_pos && s->c_cube_side && s->B && s->E && s->gE),
                 "null crossed-site tables");
     NBM_REQUIRE(s->n_irr == 0 || (s->irr_wE && s->irr_c && s->irr_nl && s->irr_nlw), "null irregular-row tables");

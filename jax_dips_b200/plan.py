@@ -327,7 +327,8 @@ class SharedPlan:
             self.G = torch.zeros(ne, dtype=torch.float32, device=dev)
             self.E = torch.zeros(max(cs.n, 1), dtype=torch.float32, device=dev)
             self.gE = torch.zeros(max(cs.n, 1), dtype=torch.float32, device=dev)
-            rows = L.nbm_step_partial_rows()
+            # the shared path launches at most one gradient CTA per SM: that many partial rows
+            rows = min(L.nbm_step_partial_rows(), torch.cuda.get_device_properties(dev).multi_processor_count)
             self.partials = torch.zeros(rows * (P + 1), dtype=torch.float32, device=dev)
             self.loss_grad = torch.zeros(P + 1, dtype=torch.float32, device=dev)
             s = cabi.SharedStep()
@@ -469,6 +470,12 @@ class GeneralLevel:
             self.irr_nl, self.irr_nlw = irr_nl[:m].clone(), irr_nlw[:m].clone()
             self.E = torch.zeros(max(cs.n, 1), dtype=torch.float32, device=dev)
             self.gE = torch.zeros(max(cs.n, 1), dtype=torch.float32, device=dev)
+            sh = torch.tensor(shifts, dtype=torch.float32, device=dev)                  # (7,3)
+            self.xs7 = (self.xs[None, :] + sh[:, 0:1]).contiguous()                      # fp32 add, like point[0] - dx
+            self.ys7 = (self.ys[None, :] + sh[:, 1:2]).contiguous()
+            self.zs7 = (self.zs[None, :] + sh[:, 2:3]).contiguous()
+            self.U7 = torch.zeros(7 * N, dtype=torch.float32, device=dev)
+            self.G7 = torch.zeros(7 * N, dtype=torch.float32, device=dev)
             rows = L.nbm_step_partial_rows()
             self.rows = rows
             self.partials = torch.zeros(rows * (net.n_params + 1), dtype=torch.float32, device=dev)
@@ -503,6 +510,8 @@ class PointsPlan:
         s.E, s.gE = cabi.ptr(level.E), cabi.ptr(level.gE)
         s.partials, s.n_partial_rows, s.loss_grad = cabi.ptr(level.partials), level.rows, cabi.ptr(self.loss_grad)
         s.rows = cabi.ptr(self.rows)
+        s.xs7, s.ys7, s.zs7 = cabi.ptr(level.xs7), cabi.ptr(level.ys7), cabi.ptr(level.zs7)
+        s.U7, s.G7 = cabi.ptr(level.U7), cabi.ptr(level.G7)
         self.step = s
 
     def loss_grad_launch(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
