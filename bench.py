@@ -272,7 +272,8 @@ def main():
     # Trainer.single_GPU_train does); eager launches remain for --no-graph and if capture is not possible
     eager_step = step
     used_graph = False
-    if not args.no_graph and world == 1:  # NCCL collectives are launched eagerly between the two graphs' worth of kernels
+    # (with NCCL the collective stays an eager launch; the peer-memory all-reduce is an ordinary kernel and is captured)
+    if not args.no_graph and (world == 1 or comm is not None):
         try:
             for _ in range(2):
                 eager_step()
