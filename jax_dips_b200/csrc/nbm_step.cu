@@ -15,9 +15,11 @@ namespace nbm {
 
 #define NBM_MAXP 1024
 // [0, MAXP): the parameters; [MAXP, 2*MAXP): the same with the hidden layers' W and b multiplied
-// by 2*log2(e), so that the forward pass feeds ex2 directly (tanh(s) = 1 - 2/(2^(2 log2e s) + 1)).
-__constant__ __align__(16) float c_P[2 * NBM_MAXP];
-__device__ __align__(16) float g_stage[2 * NBM_MAXP];
+// by 2*log2(e), so that the forward pass feeds ex2 directly (tanh(s) = 1 - 2/(2^(2 log2e s) + 1));
+// [2*MAXP, 3*MAXP): the parameters with every hidden HxH matrix TRANSPOSED, so that the backward
+// product W delta also runs as 5 independent fp32x2 chains with adjacent constant-bank pairs.
+__constant__ __align__(16) float c_P[3 * NBM_MAXP];
+__device__ __align__(16) float g_stage[3 * NBM_MAXP];
 constexpr float kTwoLog2e = 2.8853900817779268f;
 
 constexpr int kThreads = 256;
@@ -256,25 +258,30 @@ struct MlpP {
             const int o = 4 * H + (l - 1) * (H * H + H);
 #pragma unroll
             for (int j = 0; j < HP; ++j) acc[(o + H * H + 2 * j) / 2] = fadd2(acc[(o + H * H + 2 * j) / 2], d[j]);
+            // outer product  dW[i][j] += a_i delta_j  (pairs along j)
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                float ai = (i & 1) ? hi32(a[l - 1][i / 2]) : lo32(a[l - 1][i / 2]);
+                u64 ai2 = pk(ai, ai);
+#pragma unroll
+                for (int j = 0; j < HP; ++j)
+                    acc[(o + i * H + 2 * j) / 2] = ffma2(ai2, d[j], acc[(o + i * H + 2 * j) / 2]);
+            }
+            // delta_prev = (W delta) (1 - a^2): pairs along i through the transposed copy -> HP independent chains
             u64 dn[HP];
 #pragma unroll
+            for (int ip = 0; ip < HP; ++ip) dn[ip] = 0ull;
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                float dj = (j & 1) ? hi32(d[j / 2]) : lo32(d[j / 2]);
+                u64 dj2 = pk(dj, dj);
+#pragma unroll
+                for (int ip = 0; ip < HP; ++ip) dn[ip] = ffma2(cpair(2 * NBM_MAXP + o + j * H + 2 * ip), dj2, dn[ip]);
+            }
+#pragma unroll
             for (int ip = 0; ip < HP; ++ip) {
-                float dnv[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int i = 2 * ip + h;
-                    float ai = h ? hi32(a[l - 1][ip]) : lo32(a[l - 1][ip]);
-                    u64 ai2 = pk(ai, ai);
-                    u64 t = pk(0.0f, 0.0f);
-#pragma unroll
-                    for (int j = 0; j < HP; ++j) {
-                        acc[(o + i * H + 2 * j) / 2] = ffma2(ai2, d[j], acc[(o + i * H + 2 * j) / 2]);
-                        t = ffma2(cpair(o + i * H + 2 * j), d[j], t);
-                    }
-                    dnv[h] = lo32(t) + hi32(t);
-                }
                 u64 om = ffma2(neg2(a[l - 1][ip]), a[l - 1][ip], one);
-                dn[ip] = fmul2(pk(dnv[0], dnv[1]), om);
+                dn[ip] = fmul2(dn[ip], om);
             }
 #pragma unroll
             for (int j = 0; j < HP; ++j) d[j] = dn[j];
@@ -391,7 +398,7 @@ static NodeView view_of(const nbm_shared_step_t& s) {
 }
 
 // A: U[e] = u(node e)   (evaluate_solution_fn, trainer.py:836-844)
-template <class NET>
+template <class NET, bool GENERAL>
 __global__ void __launch_bounds__(kThreads) fwd_nodes_kernel(NodeView v, Tasks T) {
     const int rep = blockIdx.y;
     const float* xe = v.xe + (size_t)rep * v.ex;
@@ -418,7 +425,7 @@ __global__ void __launch_bounds__(kThreads) fwd_nodes_kernel(NodeView v, Tasks T
                 sd_n = __ldg(side + e);
                 x_n = __ldg(xe + ix + 1);
             }
-            if (e_cur >= v.lo && e_cur < v.hi) U[e_cur] = NET::eval(plus, x, y, z);
+            if (!GENERAL || (e_cur >= v.lo && e_cur < v.hi)) U[e_cur] = NET::eval(plus, x, y, z);
         }
     }
 }
@@ -669,7 +676,9 @@ __device__ __forceinline__ void block_reduce_store(typename NET::Acc& acc, float
 
 // C2: d loss/d theta = sum_nodes (G/n) d u(node)/d theta, loss = sum_rows 0.5 R^2 / n
 // (value_and_grad(self.loss), trainer.py:786; mean of optax.l2_loss, :899-901)
-template <class NET>
+// GENERAL = false: the shared path (one replica, every node of the lattice, loss from R);
+// GENERAL = true : the 7 displaced lattices of the general path (node range filter, no R)
+template <class NET, bool GENERAL>
 __global__ void __launch_bounds__(kThreads, 1) node_grad_kernel(NodeView v, Tasks T) {
     typename NET::Acc acc;
     acc.zero();
@@ -691,17 +700,17 @@ __global__ void __launch_bounds__(kThreads, 1) node_grad_kernel(NodeView v, Task
         // software pipeline: the loads of plane ix+1 are in flight while plane ix is computed (only 8 warps
         // per SM fit beside the 167 accumulators, so HBM latency has to be hidden explicitly)
         int64_t e = (int64_t)x0 * T.plane + m;
-        bool in_n = e >= v.lo && e < v.hi;
-        float g_n = in_n ? __ldg(G + e) : 0.0f, r_n = (R && in_n) ? __ldg(R + e) : 0.0f, x_n = __ldg(xe + x0);
+        bool in_n = !GENERAL || (e >= v.lo && e < v.hi);
+        float g_n = in_n ? __ldg(G + e) : 0.0f, r_n = GENERAL ? 0.0f : __ldg(R + e), x_n = __ldg(xe + x0);
         uint8_t sd_n = __ldg(side + e);
         for (int ix = x0; ix < x1; ++ix) {
             float g = g_n * v.inv_n, r = r_n, x = x_n;
             bool plus = (sd_n & 1) != 0;
             if (ix + 1 < x1) {
                 e += T.plane;
-                in_n = e >= v.lo && e < v.hi;
+                in_n = !GENERAL || (e >= v.lo && e < v.hi);
                 g_n = in_n ? __ldg(G + e) : 0.0f;
-                r_n = (R && in_n) ? __ldg(R + e) : 0.0f;
+                if (!GENERAL) r_n = __ldg(R + e);
                 sd_n = __ldg(side + e);
                 x_n = __ldg(xe + ix + 1);
             }
@@ -818,6 +827,13 @@ __global__ void prep_params_kernel(nbm_net_t net, const float* __restrict__ para
     int hidden_len = 4 * H + (Lh - 1) * (H * H + H);  // everything before the output layer
     stage[i] = v;
     stage[NBM_MAXP + i] = k < hidden_len ? v * kTwoLog2e : v;
+    // third copy: hidden HxH matrices transposed in place
+    int dst = i;
+    if (k >= 4 * H && k < hidden_len) {
+        int q = (k - 4 * H) % (H * H + H);
+        if (q < H * H) dst = i - q + (q % H) * H + q / H;
+    }
+    stage[2 * NBM_MAXP + dst] = v;
 }
 
 
@@ -922,7 +938,7 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
                          (uintptr_t)s.nl) & 15) == 0);
     if (stages & NBM_STAGE_FWD) {
         int gridA = min(T.total, sms * 8);
-        fwd_nodes_kernel<NET><<<gridA, kThreads, 0, st>>>(view_of(s), T);
+        fwd_nodes_kernel<NET, false><<<gridA, kThreads, 0, st>>>(view_of(s), T);
     }
     if ((stages & NBM_STAGE_EXTRAP) && s.n_crossed > 0)
         extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
@@ -949,7 +965,7 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     }
     int gridC = min(T.total, min(kPartialRows, sms));
     if (gridC > s.n_partial_rows) gridC = s.n_partial_rows;
-    if (stages & NBM_STAGE_GRAD) node_grad_kernel<NET><<<gridC, kThreads, 0, st>>>(view_of(s), T);
+    if (stages & NBM_STAGE_GRAD) node_grad_kernel<NET, false><<<gridC, kThreads, 0, st>>>(view_of(s), T);
     if (stages & NBM_STAGE_REDUCE)
         reduce_partials_kernel<<<(NET::NP + 1 + 127) / 128, 128, 0, st>>>(s.partials, gridC, NET::NP + 1, s.loss_grad);
     return cuda_check(cudaGetLastError(), "shared step launch");
@@ -1184,10 +1200,10 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     if (s.n_crossed > 0)
         points_extrap_kernel<NET><<<(unsigned)min((int64_t)sms * 4, (s.n_crossed * 32 + kThreads - 1) / kThreads),
                                     kThreads, 0, st>>>(a);
-    fwd_nodes_kernel<NET><<<dim3(gridF, 7), kThreads, 0, st>>>(v, T);
+    fwd_nodes_kernel<NET, true><<<dim3(gridF, 7), kThreads, 0, st>>>(v, T);
     points_rows_kernel<<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, 7 * gridG, np1);
     v.row0 = 0;
-    node_grad_kernel<NET><<<dim3(gridG, 7), kThreads, 0, st>>>(v, T);
+    node_grad_kernel<NET, true><<<dim3(gridG, 7), kThreads, 0, st>>>(v, T);
     if (gridE > 0) points_extrap_bwd_kernel<NET><<<gridE, kThreads, 0, st>>>(a, 7 * gridG + gridR);
     reduce_partials_kernel<<<(np1 + 127) / 128, 128, 0, st>>>(s.partials, rows_needed, np1, s.loss_grad);
     return cuda_check(cudaGetLastError(), "points step launch");
@@ -1232,7 +1248,7 @@ int nbm_upload_params(const nbm_net_t* net, const float* params, nbm_stream_t st
     if (rc) return rc;
     prep_params_kernel<<<(P + 127) / 128, 128, 0, st>>>(*net, params, stage, P);
     NBM_LAUNCH_CHECK("prep_params");
-    return cuda_check(cudaMemcpyToSymbolAsync(c_P, stage, sizeof(float) * 2 * NBM_MAXP, 0, cudaMemcpyDeviceToDevice, st),
+    return cuda_check(cudaMemcpyToSymbolAsync(c_P, stage, sizeof(float) * 3 * NBM_MAXP, 0, cudaMemcpyDeviceToDevice, st),
                       "upload params");
 }
 
