@@ -238,6 +238,63 @@ struct MlpP {
         return lo32(o2) + hi32(o2);
     }
 
+    // forward of NB nodes that share (y, z): every constant-bank pair is fetched once and used NB times, and the
+    // NB dependency chains interleave (more ILP for the ex2/rcp latency)
+    // the part of the first layer that does not depend on x: b1 + y W1[1] + z W1[2] (pre-scaled); a thread that
+    // marches along x with fixed (y, z) computes it once per task
+    template <int OFF>
+    __device__ __forceinline__ static void first_layer_yz(float y, float z, u64 (&yz)[HP]) {
+        constexpr int S = NBM_MAXP + OFF;
+        const u64 y2 = pk(y, y), z2 = pk(z, z);
+#pragma unroll
+        for (int j = 0; j < HP; ++j)
+            yz[j] = ffma2(z2, cpair(S + 2 * H + 2 * j), ffma2(y2, cpair(S + H + 2 * j), cpair(S + 3 * H + 2 * j)));
+    }
+
+    template <int OFF, int NB>
+    __device__ __forceinline__ static void forward_many(const float (&x)[NB], const u64 (&yz)[HP], float (&out)[NB]) {
+        constexpr int S = NBM_MAXP + OFF;
+        u64 a[NB][HP], b[NB][HP];
+#pragma unroll
+        for (int j = 0; j < HP; ++j) {
+            const u64 wx = cpair(S + 2 * j);
+#pragma unroll
+            for (int n = 0; n < NB; ++n) a[n][j] = tanh2_prescaled(ffma2(pk(x[n], x[n]), wx, yz[j]));
+        }
+#pragma unroll
+        for (int l = 1; l < L; ++l) {
+            const int o = S + 4 * H + (l - 1) * (H * H + H);
+#pragma unroll
+            for (int n = 0; n < NB; ++n)
+#pragma unroll
+                for (int j = 0; j < HP; ++j) b[n][j] = cpair(o + H * H + 2 * j);
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+#pragma unroll
+                for (int j = 0; j < HP; ++j) {
+                    const u64 w = cpair(o + i * H + 2 * j);
+#pragma unroll
+                    for (int n = 0; n < NB; ++n) {
+                        float ai = (i & 1) ? hi32(a[n][i / 2]) : lo32(a[n][i / 2]);
+                        b[n][j] = ffma2(pk(ai, ai), w, b[n][j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < NB; ++n)
+#pragma unroll
+                for (int j = 0; j < HP; ++j) a[n][j] = tanh2_prescaled(b[n][j]);
+        }
+        const int oo = OFF + 4 * H + (L - 1) * (H * H + H);
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+            u64 o2 = pk(c_P[oo + H], 0.0f);
+#pragma unroll
+            for (int j = 0; j < HP; ++j) o2 = ffma2(a[n][j], cpair(oo + 2 * j), o2);
+            out[n] = lo32(o2) + hi32(o2);
+        }
+    }
+
     template <int OFF>
     __device__ __forceinline__ static void backward(float x, float y, float z, const u64 (&a)[L][HP], float g,
                                                     u64 (&acc)[NPAIR]) {
@@ -329,6 +386,24 @@ struct Net {
             return M::template forward<P::NP>(x, y, z, a);
         }
     }
+    // two nodes (x0, y, z), (x1, y, z) at once; falls back to two single evaluations when the heads differ
+    using YZ = u64[HP / 2];
+    __device__ __forceinline__ static void first_layer_yz(float y, float z, u64 (&yz)[HP / 2]) {
+        P::template first_layer_yz<0>(y, z, yz);
+    }
+    __device__ __forceinline__ static void eval2(bool plus0, bool plus1, float x0, float x1, float y, float z,
+                                                 const u64 (&yz)[HP / 2], float& u0, float& u1) {
+        if (plus0 && plus1) {
+            const float xs[2] = {x0, x1};
+            float out[2];
+            P::template forward_many<0, 2>(xs, yz, out);
+            u0 = out[0];
+            u1 = out[1];
+        } else {
+            u0 = eval(plus0, x0, y, z);
+            u1 = eval(plus1, x1, y, z);
+        }
+    }
     __device__ __forceinline__ static void grad(bool plus, float x, float y, float z, float g, Acc& acc) {
         if (plus) {
             u64 a[LP][HP / 2];
@@ -412,20 +487,36 @@ __global__ void __launch_bounds__(kThreads) fwd_nodes_kernel(NodeView v, Tasks T
         if (m >= T.plane) continue;
         int iy = m / v.ez, iz = m - iy * v.ez;
         float y = __ldg(ye + iy), z = __ldg(ze + iz);
+        typename NET::YZ yz;
+        NET::first_layer_yz(y, z, yz);
         int x0 = v.x_begin + xc * T.xchunk, x1 = min(v.x_end, x0 + T.xchunk);
         int64_t e = (int64_t)x0 * T.plane + m;
-        float x_n = __ldg(xe + x0);
-        uint8_t sd_n = __ldg(side + e);
-        for (int ix = x0; ix < x1; ++ix) {
-            float x = x_n;
-            bool plus = (sd_n & 1) != 0;
-            int64_t e_cur = e;
-            if (ix + 1 < x1) {
-                e += T.plane;
-                sd_n = __ldg(side + e);
-                x_n = __ldg(xe + ix + 1);
+        // two x planes per iteration (they share y, z and every weight fetch); loads one pair ahead
+        float xa_n = __ldg(xe + x0), xb_n = (x0 + 1 < x1) ? __ldg(xe + x0 + 1) : 0.0f;
+        uint8_t sa_n = __ldg(side + e), sb_n = (x0 + 1 < x1) ? __ldg(side + e + T.plane) : (uint8_t)0;
+        for (int ix = x0; ix < x1; ix += 2) {
+            const float xa = xa_n, xb = xb_n;
+            const bool pa = (sa_n & 1) != 0, pb = (sb_n & 1) != 0;
+            const int64_t e_cur = e;
+            const bool has_b = ix + 1 < x1;
+            if (ix + 2 < x1) {
+                e += 2 * (int64_t)T.plane;
+                sa_n = __ldg(side + e);
+                xa_n = __ldg(xe + ix + 2);
+                if (ix + 3 < x1) {
+                    sb_n = __ldg(side + e + T.plane);
+                    xb_n = __ldg(xe + ix + 3);
+                }
             }
-            if (!GENERAL || (e_cur >= v.lo && e_cur < v.hi)) U[e_cur] = NET::eval(plus, x, y, z);
+            float ua, ub;
+            if (has_b) {
+                NET::eval2(pa, pb, xa, xb, y, z, yz, ua, ub);
+            } else {
+                ua = NET::eval(pa, xa, y, z);
+                ub = 0.0f;
+            }
+            if (!GENERAL || (e_cur >= v.lo && e_cur < v.hi)) U[e_cur] = ua;
+            if (has_b && (!GENERAL || (e_cur + T.plane >= v.lo && e_cur + T.plane < v.hi))) U[e_cur + T.plane] = ub;
         }
     }
 }
