@@ -82,11 +82,13 @@ def _jump_beta(mu_m_fn, mu_p_fn, u_m_fn, u_p_fn, phi_fn, sign=-1.0, nan_safe=Fal
     return beta_fn
 
 
-def sphere() -> Problem:
-    """experiment_configs.py:21-186"""
+def sphere(center=(0.0, 0.0, 0.0), radius: float = 0.5) -> Problem:
+    """experiment_configs.py:21-186 (centre and radius are the reference's (0,0,0), 0.5 by default; other values give
+    test variants, e.g. an interface that reaches the box boundary)"""
+    cx, cy, cz = center
     def exact_sol_m_fn(r): return jnp.exp(r[2])
     def exact_sol_p_fn(r): return jnp.sin(r[1]) * jnp.cos(r[0])
-    def unperturbed_phi_fn(r): return jnp.sqrt(r[0] ** 2 + r[1] ** 2 + r[2] ** 2) - 0.5
+    def unperturbed_phi_fn(r): return jnp.sqrt((r[0] - cx) ** 2 + (r[1] - cy) ** 2 + (r[2] - cz) ** 2) - radius
     phi_fn = perturb_level_set_fn(unperturbed_phi_fn)
     def mu_m_fn(r): return r[1] * r[1] * jnp.log(r[0] + 2.0) + 4.0
     def mu_p_fn(r): return jnp.exp(-1.0 * r[2])
@@ -298,5 +300,13 @@ def poisson_boltzmann(n_atoms: int = 200, seed: int = 2, half_width: float = 2.5
                    box=((-hw, -hw, -hw), (hw, hw, hw)), name="poisson_boltzmann")
 
 
-PROBLEMS = {"sphere": sphere, "star": star, "no_jump": no_jump, "stars": stars, "dragon_like": dragon_like,
+def sphere_at_boundary() -> Problem:
+    """the sphere problem with the interface pushed against the x+ face of the box: crossed cells whose
+    27-point regression cube leaves the box (the halo layer of the lattice)"""
+    P = sphere(center=(0.62, 0.1, -0.05), radius=0.36)
+    P.name = "sphere_at_boundary"
+    return P
+
+
+PROBLEMS = {"sphere": sphere, "sphere_at_boundary": sphere_at_boundary, "star": star, "no_jump": no_jump, "stars": stars, "dragon_like": dragon_like,
             "poisson_boltzmann": poisson_boltzmann}

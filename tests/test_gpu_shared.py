@@ -122,6 +122,50 @@ def test_rows_loss_and_gradient(name, n, nl):
     assert ((grad_k.double()[big] - grad_o[big]).abs() / grad_o[big].abs()).max() < 10 * TOL_LOSS
 
 
+def test_anisotropic_grid_and_interface_at_the_box_boundary():
+    """ragged sizes (Nx != Ny != Nz, dx != dy != dz) and crossed cells next to the Dirichlet boundary
+    (regression cubes that reach the halo layer outside the box)"""
+    P = problems.sphere_at_boundary()
+    dt = torch.float64
+    tr, lv, phi_grid, oprob = util.make_case(P, [14, 10, 12], [30, 22, 26], "trilinear", dt)
+    lvl = nplan.LevelSet(lv, phi_grid, device=DEV)
+    shape = nplan.NetShape()
+    pl = nplan.SharedPlan(lvl, tr, 0, 14, fns_of(P), shape, nplan.Nonlinear(), nplan.Nonlinear(), device=DEV)
+    d = [tr.dx.to(dt), tr.dy.to(dt), tr.dz.to(dt)]
+    assert len({round(float(v), 6) for v in d}) == 3
+    flag_o = O.is_cell_crossed(tr.R.to(dt), *d, oprob.phi_fn)
+    R3 = tr.R.reshape(14, 10, 12, 3)
+    near_face = (flag_o.reshape(14, 10, 12)[-2, :, :] == 0).sum()
+    assert int(near_face) > 0, "the test problem must put crossed cells next to the x+ boundary"
+    assert torch.equal(pl.point_view(pl.sites.flag).cpu().to(dt), flag_o)
+    params = O.init_params(oprob.shape, seed=21, dtype=dt)
+    lhs_o, rhs_o = O.compute_Ax_and_b(params, tr.R.to(dt), *d, oprob)
+    loss_o, grad_o = O.loss_and_grad(params, tr.R.to(dt), *d, oprob)
+    with torch.cuda.device(DEV):
+        nplan.upload_params(shape, params.float().to(DEV))
+        lg = pl.loss_grad_launch().cpu()
+    rhs_k = pl.point_view(pl.rhs).cpu()
+    lhs_k = pl.point_view(pl.R).cpu() + rhs_k
+    assert util.rel_inf(lhs_k, lhs_o) < TOL_ROW and util.rel_inf(rhs_k, rhs_o) < TOL_ROW
+    assert abs(float(lg[-1]) - float(loss_o)) / float(loss_o) < TOL_LOSS
+    assert util.rel_inf(lg[:-1], grad_o) < TOL_LOSS
+    # the general path on the same problem, zoom level 1
+    d1 = [float(torch.tensor(float(v), dtype=torch.float32) * 0.5) for v in (tr.dx, tr.dy, tr.dz)]
+    level = nplan.GeneralLevel(lvl, tr, d1, fns_of(P), shape, nplan.Nonlinear(), nplan.Nonlinear(), device=DEV)
+    pp = nplan.PointsPlan(level, 0, tr.num_points())
+    dd = [torch.tensor(v, dtype=dt) for v in d1]
+    loss_1, grad_1 = O.loss_and_grad(params, tr.R.to(dt), *dd, oprob)
+    with torch.cuda.device(DEV):
+        lg1 = pp.loss_grad_launch().cpu()
+    assert abs(float(lg1[-1]) - float(loss_1)) / float(loss_1) < TOL_LOSS
+    assert util.rel_inf(lg1[:-1], grad_1) < TOL_LOSS
+
+
+def test_smoke_entry_point():
+    import __graft_entry__ as g
+    g.smoke()
+
+
 def test_slab_plans_sum_to_the_whole_grid():
     """x-slabs (the multi-GPU partition, data_management.py:121-130) : sum of per-slab
     n_slab*mean-gradients equals the whole-grid n*mean-gradient."""
