@@ -179,6 +179,19 @@ typedef struct {
     int32_t* irr_c;                  /* [cap][7] crossed index of site k or -1 */
     uint8_t* irr_nl;                 /* [cap] 0: none, 1: N^-(E(centre)), 2: N^+(E(centre)) enters the row */
     float* irr_nlw;                  /* [cap] its weight V/diag */
+    /* faces = 1 (shared layout only, needs k_m = k_p = 0): instead of the 7 row weights `w`, store per node the
+     * UN-normalised coefficient mu A / d of its +x, +y, +z faces (the FV matrix is symmetric between regular
+     * neighbours: one value per face serves the rows on both sides), 1/diag, and move every irregular row
+     * (a crossed stencil site, or a neighbour on the other side of the interface) completely into the
+     * list (irr_wU, irr_rhs).  12 + 4 bytes per node instead of 28.
+     *   cface[3][n_out];  dinv[n_out]: > 0 regular row, 0 no dense row, -1 Dirichlet row (r = u - rhs);
+     *   kv[n_out] = k^- V^- + k^+ V^+ (un-normalised), may be NULL when k_m = k_p = 0 everywhere */
+    int faces;
+    float* cface;
+    float* dinv;
+    float* irr_wU;                   /* [cap][7] (faces mode) weight on u(site k) */
+    float* irr_rhs;                  /* [cap]    (faces mode) */
+    float* kv;                       /* [n_out]  (faces mode) or NULL */
 } nbm_assemble_t;
 
 int nbm_assemble_f32(const nbm_assemble_t* a, nbm_stream_t stream);
@@ -219,6 +232,10 @@ typedef struct {
     int n_partial_rows;              /* >= nbm_step_partial_rows() */
     float* loss_grad;                /* [P+1]: grad[0..P), loss at [P] */
     int stages;                      /* 0 = the whole step; else a bit mask of nbm_stage (profiling / timing) */
+    /* faces mode (see nbm_assemble_t): w is unused, rows come from cface/dinv, irregular rows from the list */
+    int faces;
+    const float* cface; const float* dinv; const float* irr_wU; const float* irr_rhs;
+    const float* kv;                 /* may be NULL */
 } nbm_shared_step_t;
 
 /* stages of the shared-evaluation step, in launch order */

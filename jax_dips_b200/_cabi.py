@@ -45,7 +45,9 @@ class Assemble(C.Structure):
                 ("w", c_fp), ("rhs", c_fp), ("nl", c_fp), ("irr", c_fp),
                 ("n_out", C.c_int64), ("out_stride", C.c_int64 * 3), ("out_off", C.c_int64),
                 ("irr_capacity", C.c_int64), ("irr_count", c_fp), ("irr_point", c_fp),
-                ("irr_wE", c_fp), ("irr_c", c_fp), ("irr_nl", c_fp), ("irr_nlw", c_fp)]
+                ("irr_wE", c_fp), ("irr_c", c_fp), ("irr_nl", c_fp), ("irr_nlw", c_fp),
+                ("faces", C.c_int), ("cface", c_fp), ("dinv", c_fp), ("irr_wU", c_fp), ("irr_rhs", c_fp),
+                ("kv", c_fp)]
 
 
 class Net(C.Structure):
@@ -63,7 +65,9 @@ class SharedStep(C.Structure):
                 ("irr_nl", c_fp), ("irr_nlw", c_fp),
                 ("inv_n_points", c_f),
                 ("U", c_fp), ("R", c_fp), ("G", c_fp), ("E", c_fp), ("gE", c_fp),
-                ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp), ("stages", C.c_int)]
+                ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp), ("stages", C.c_int),
+                ("faces", C.c_int), ("cface", c_fp), ("dinv", c_fp), ("irr_wU", c_fp), ("irr_rhs", c_fp),
+                ("kv", c_fp)]
 
 
 class PointsStep(C.Structure):

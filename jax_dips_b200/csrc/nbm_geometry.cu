@@ -492,7 +492,7 @@ __global__ void assemble_kernel(nbm_assemble_t a) {
     bool bnd = fabsf(x - a.bounds[0]) < 1e-6f * dx || fabsf(x - a.bounds[1]) < 1e-6f * dx ||
                fabsf(y - a.bounds[2]) < 1e-6f * dy || fabsf(y - a.bounds[3]) < 1e-6f * dy ||
                fabsf(z - a.bounds[4]) < 1e-6f * dz || fabsf(z - a.bounds[5]) < 1e-6f * dz;
-    if (bnd) {
+    if (bnd && !a.faces) {
         // lhs = u*vol, diag = vol, rhs = g*vol (:389-393, :410-411)
         a.w[out] = 1.0f;
         for (int s = 1; s < 7; ++s) a.w[s * a.n_out + out] = 0.0f;
@@ -561,6 +561,8 @@ __global__ void assemble_kernel(nbm_assemble_t a) {
             cE[s] = a.cidx[sid[s]];
             irregular = true;
         }
+        // the one-coefficient-per-face table assumes the row couples nodes of its own side only
+        if (a.faces && fs != f0) irregular = true;
         wU[s] = ok ? u_w * inv : 0.0f;
         wE[s] = ok ? e_w * inv : 0.0f;
     }
@@ -574,13 +576,39 @@ __global__ void assemble_kernel(nbm_assemble_t a) {
             nl0 = Vm * inv; nl1 = Vp * inv;
         }
     }
-    for (int s = 0; s < 7; ++s) a.w[s * a.n_out + out] = wU[s];
     // nan_to_num(rhs/diag) (:419): NaN -> 0, +-inf -> +-FLT_MAX
     float rn = ok ? rhs * inv : 0.0f;
     if (isnan(rn)) rn = 0.0f;
     else if (isinf(rn)) rn = rn > 0.0f ? 3.4028234664e38f : -3.4028234664e38f;
-    a.rhs[out] = rn;
-    if (a.nl) { a.nl[out] = nl0; a.nl[a.n_out + out] = nl1; }
+    if (a.faces) {
+        // one coefficient per face, on the node's own side (0 for crossed cells: any row that touches one is in
+        // the irregular list).  The -x face of the first plane of the slab belongs to the halo node.
+        float own[6];
+        for (int f = 0; f < 6; ++f) own[f] = f0 < 0 ? cm[f] : (f0 > 0 ? cp[f] : 0.0f);
+        a.cface[out] = own[1];
+        a.cface[a.n_out + out] = own[3];
+        a.cface[2 * a.n_out + out] = own[5];
+        if (i == 0) a.cface[out - a.out_stride[0]] = own[0];
+        if (j == 0) a.cface[a.n_out + out - a.out_stride[1]] = own[2];
+        if (k == 0) a.cface[2 * a.n_out + out - a.out_stride[2]] = own[4];
+        if (bnd) {
+            a.dinv[out] = -1.0f;                 // Dirichlet row: r = u - g (:389-393, :410-411)
+            if (a.kv) a.kv[out] = 0.0f;
+            a.rhs[out] = a.g_dir[p];
+            if (a.nl) { a.nl[out] = 0.0f; a.nl[a.n_out + out] = 0.0f; }
+            a.irr[out] = -1;
+            return;
+        }
+        const bool dense = ok && !irregular;
+        if (a.kv) a.kv[out] = dense ? (kp * Vp + km * Vm) : 0.0f;
+        a.dinv[out] = dense ? inv : 0.0f;
+        a.rhs[out] = dense ? rn : 0.0f;
+        if (a.nl) { a.nl[out] = dense ? nl0 : 0.0f; a.nl[a.n_out + out] = dense ? nl1 : 0.0f; }
+    } else {
+        for (int s = 0; s < 7; ++s) a.w[s * a.n_out + out] = wU[s];
+        a.rhs[out] = rn;
+        if (a.nl) { a.nl[out] = nl0; a.nl[a.n_out + out] = nl1; }
+    }
     int32_t slot = -1;
     if (irregular && ok) {
         unsigned long long q = atomicAdd((unsigned long long*)a.irr_count, 1ULL);
@@ -590,6 +618,12 @@ __global__ void assemble_kernel(nbm_assemble_t a) {
             for (int s = 0; s < 7; ++s) { a.irr_wE[q * 7 + s] = wE[s]; a.irr_c[q * 7 + s] = cE[s]; }
             a.irr_nl[q] = nlr;
             a.irr_nlw[q] = nlw;
+            if (a.faces) {
+                for (int s = 0; s < 7; ++s) a.irr_wU[q * 7 + s] = wU[s];
+                a.irr_rhs[q] = rn;
+                // the U-part of the nonlinear term of an irregular row stays in the dense nl table
+                if (a.nl) { a.nl[out] = nl0; a.nl[a.n_out + out] = nl1; }
+            }
         }
     }
     a.irr[out] = slot;
@@ -748,7 +782,13 @@ int nbm_assemble_f32(const nbm_assemble_t* a, nbm_stream_t stream) {
     NBM_REQUIRE(a->flag && a->side && a->cidx, "null site tables");
     NBM_REQUIRE(a->mu_m_faces && a->mu_p_faces && a->k_m && a->k_p && a->f_m && a->f_p && a->g_dir,
                 "null coefficient samples");
-    NBM_REQUIRE(a->w && a->rhs && a->irr, "null outputs");
+    NBM_REQUIRE(a->rhs && a->irr, "null outputs");
+    if (a->faces) {
+        NBM_REQUIRE(a->shared, "faces mode needs the shared (lattice) layout");
+        NBM_REQUIRE(a->cface && a->dinv && a->irr_wU && a->irr_rhs, "null face-table outputs");
+    } else {
+        NBM_REQUIRE(a->w, "null outputs");
+    }
     NBM_REQUIRE(a->irr_count && a->irr_point && a->irr_wE && a->irr_c && a->irr_nl && a->irr_nlw,
                 "null irregular-row buffers");
     NBM_REQUIRE(a->dx > 0 && a->dy > 0 && a->dz > 0, "cell size must be positive");

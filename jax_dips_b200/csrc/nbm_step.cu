@@ -352,6 +352,142 @@ struct MlpP {
             acc[(2 * H + 2 * j) / 2] = ffma2(z2, d[j], acc[(2 * H + 2 * j) / 2]);
         }
     }
+    // -----------------------------------------------------------------------------------------
+    // Pair-split backward (node_grad): the two lanes of a pair (lane ^ 1) walk neighbouring nodes; the
+    // H x H outer-product accumulators of every hidden layer are split between them by ROW PARITY (lane
+    // parity b owns rows i = 2k + b) and each lane accumulates its rows for BOTH nodes, receiving the
+    // partner's delta (H values) and the partner's activations of its rows (H/2 values) by shuffle.
+    // That halves the largest accumulator block (100 -> 50 registers for H = 10).  The first layer is
+    // hoisted along the x march: (y, z) are fixed per task, so only sum(delta1) and sum(x delta1) are
+    // kept per node; the y, z rows and the bias follow from sum(delta1) at the end of the task.
+    // -----------------------------------------------------------------------------------------
+    static constexpr int LH = (L > 1) ? (L - 1) : 1;
+    struct AccS {
+        u64 w3[HP];
+        float b3;
+        u64 w2[LH][HP][HP];   // [layer][k: row 2k + parity][pair of columns]
+        u64 b2[LH][HP];
+        u64 w1x[HP];
+        u64 t[HP];            // task-local sum of delta1
+        __device__ __forceinline__ void zero() {
+            b3 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < HP; ++j) { w3[j] = 0ull; w1x[j] = 0ull; t[j] = 0ull; }
+#pragma unroll
+            for (int l = 0; l < LH; ++l)
+#pragma unroll
+                for (int k = 0; k < HP; ++k) {
+                    b2[l][k] = 0ull;
+#pragma unroll
+                    for (int j = 0; j < HP; ++j) w2[l][k][j] = 0ull;
+                }
+        }
+    };
+
+    __device__ __forceinline__ static u64 shfl1(u64 v) {
+        float a = __shfl_xor_sync(0xffffffffu, lo32(v), 1), b = __shfl_xor_sync(0xffffffffu, hi32(v), 1);
+        return pk(a, b);
+    }
+
+    // forward recompute (first layer from the hoisted yz part) + backward with g = d loss / d u(node).
+    // Must be called by all 32 lanes (g = 0 for lanes that have nothing to add).
+    __device__ __forceinline__ static void grad_split(float x, const u64 (&yz)[HP], float g, AccS& A, bool par) {
+        constexpr int S = NBM_MAXP;
+        u64 a[L][HP];
+        const u64 x2 = pk(x, x);
+#pragma unroll
+        for (int j = 0; j < HP; ++j) a[0][j] = tanh2_prescaled(ffma2(x2, cpair(S + 2 * j), yz[j]));
+#pragma unroll
+        for (int l = 1; l < L; ++l) {
+            const int o = S + 4 * H + (l - 1) * (H * H + H);
+            u64 acc[HP];
+#pragma unroll
+            for (int j = 0; j < HP; ++j) acc[j] = cpair(o + H * H + 2 * j);
+#pragma unroll
+            for (int i = 0; i < H; ++i) {
+                float ai = (i & 1) ? hi32(a[l - 1][i / 2]) : lo32(a[l - 1][i / 2]);
+                u64 ai2 = pk(ai, ai);
+#pragma unroll
+                for (int j = 0; j < HP; ++j) acc[j] = ffma2(ai2, cpair(o + i * H + 2 * j), acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < HP; ++j) a[l][j] = tanh2_prescaled(acc[j]);
+        }
+        const int oo = 4 * H + (L - 1) * (H * H + H);
+        const u64 one = pk(1.0f, 1.0f);
+        const u64 g2 = pk(g, g);
+        u64 d[HP];
+#pragma unroll
+        for (int j = 0; j < HP; ++j) {
+            A.w3[j] = ffma2(a[L - 1][j], g2, A.w3[j]);
+            u64 om = ffma2(neg2(a[L - 1][j]), a[L - 1][j], one);
+            d[j] = fmul2(fmul2(cpair(oo + 2 * j), g2), om);
+        }
+        A.b3 += g;
+#pragma unroll
+        for (int l = L - 1; l >= 1; --l) {
+            const int o = 4 * H + (l - 1) * (H * H + H);
+            u64 dP[HP];
+            float aown[HP], apart[HP];
+#pragma unroll
+            for (int j = 0; j < HP; ++j) {
+                A.b2[l - 1][j] = fadd2(A.b2[l - 1][j], d[j]);
+                dP[j] = shfl1(d[j]);
+                const float lo = lo32(a[l - 1][j]), hi = hi32(a[l - 1][j]);
+                aown[j] = par ? hi : lo;
+                apart[j] = __shfl_xor_sync(0xffffffffu, par ? lo : hi, 1);
+            }
+#pragma unroll
+            for (int k = 0; k < HP; ++k) {
+                const u64 ao = pk(aown[k], aown[k]), ap = pk(apart[k], apart[k]);
+#pragma unroll
+                for (int j = 0; j < HP; ++j)
+                    A.w2[l - 1][k][j] = ffma2(ap, dP[j], ffma2(ao, d[j], A.w2[l - 1][k][j]));
+            }
+            u64 dn[HP];
+#pragma unroll
+            for (int ip = 0; ip < HP; ++ip) dn[ip] = 0ull;
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                float dj = (j & 1) ? hi32(d[j / 2]) : lo32(d[j / 2]);
+                u64 dj2 = pk(dj, dj);
+#pragma unroll
+                for (int ip = 0; ip < HP; ++ip) dn[ip] = ffma2(cpair(2 * NBM_MAXP + o + j * H + 2 * ip), dj2, dn[ip]);
+            }
+#pragma unroll
+            for (int ip = 0; ip < HP; ++ip) {
+                u64 om = ffma2(neg2(a[l - 1][ip]), a[l - 1][ip], one);
+                d[ip] = fmul2(dn[ip], om);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < HP; ++j) {
+            A.t[j] = fadd2(A.t[j], d[j]);
+            A.w1x[j] = ffma2(x2, d[j], A.w1x[j]);
+        }
+    }
+
+    // the value this lane contributes to flat gradient entry i of the head (compile-time i); `hs` are the
+    // thread's 3H hoisted sums in shared memory: [0,H) bias, [H,2H) y row, [2H,3H) z row (stride `hstride`)
+    __device__ __forceinline__ static float split_get(const AccS& A, int i, bool par, const float* hs, int hstride) {
+        const int oo = 4 * H + (L - 1) * (H * H + H);
+        if (i < H) return (i & 1) ? hi32(A.w1x[i / 2]) : lo32(A.w1x[i / 2]);
+        if (i < 3 * H) return hs[i * hstride];
+        if (i < 4 * H) return hs[(i - 3 * H) * hstride];
+        if (i < oo) {
+            const int l = (i - 4 * H) / (H * H + H), r = (i - 4 * H) - l * (H * H + H);
+            if (r >= H * H) {
+                const int j = r - H * H;
+                return (j & 1) ? hi32(A.b2[l][j / 2]) : lo32(A.b2[l][j / 2]);
+            }
+            const int row = r / H, j = r - row * H;
+            const u64 v = A.w2[l][row / 2][j / 2];
+            const float f = (j & 1) ? hi32(v) : lo32(v);
+            return (par == ((row & 1) != 0)) ? f : 0.0f;
+        }
+        if (i < oo + H) return ((i - oo) & 1) ? hi32(A.w3[(i - oo) / 2]) : lo32(A.w3[(i - oo) / 2]);
+        return A.b3;
+    }
 };
 
 template <int LP, int HP, int LM, int HM>
@@ -359,6 +495,7 @@ struct Net {
     using P = MlpP<LP, HP>;
     using M = Mlp<LM, HM>;
     static constexpr int NP = P::NP + M::NP;
+    static constexpr int HPW = HP, LMD = LM, HMW = HM;
 
     // per-thread gradient accumulators: p-head in fp32x2 pairs, m-head scalar
     struct Acc {
@@ -433,10 +570,10 @@ __device__ __forceinline__ float nl_deriv(int kind, float coef, float u) {
 struct Tasks {
     int plane, mblocks, xchunk, nxch, total;
 };
-__host__ __device__ inline Tasks make_tasks(int ex, int ey, int ez, int xchunk) {
+__host__ __device__ inline Tasks make_tasks(int ex, int ey, int ez, int xchunk, int threads = kThreads) {
     Tasks t;
     t.plane = ey * ez;
-    t.mblocks = (t.plane + kThreads - 1) / kThreads;
+    t.mblocks = (t.plane + threads - 1) / threads;
     t.xchunk = xchunk;
     t.nxch = (ex + xchunk - 1) / xchunk;
     t.total = t.mblocks * t.nxch;
@@ -582,7 +719,23 @@ __global__ void irregular_fwd_kernel(nbm_shared_step_t s) {
         r = fmaf(s.irr_nlw[q],
                  nlr == 1 ? nl_apply(s.nonlinear_m, s.nl_coef_m, Ec) : nl_apply(s.nonlinear_p, s.nl_coef_p, Ec), r);
     }
-    s.R[s.irr_point[q]] += r;
+    const int64_t e = s.irr_point[q];
+    if (s.faces) {
+        // the whole row lives in the list: weights on the 7 sites, rhs; the U-part of the nonlinear term from nl
+        const int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
+        const int64_t off[7] = {0, -sx, sx, -sy, sy, -1, 1};
+        const float u0 = s.U[e];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) r = fmaf(s.irr_wU[q * 7 + k], s.U[e + off[k]], r);
+        if (s.nl) {
+            const int64_t ne = sx * s.ex;
+            r = fmaf(s.nl[e], nl_apply(s.nonlinear_m, s.nl_coef_m, u0), r);
+            r = fmaf(s.nl[ne + e], nl_apply(s.nonlinear_p, s.nl_coef_p, u0), r);
+        }
+        s.R[e] = r - s.irr_rhs[q];
+    } else {
+        s.R[e] += r;
+    }
 }
 
 // C1: G[x] = sum_k w_k[x - off_k] R[x - off_k]  (adjoint of the 7-point rows)
@@ -711,15 +864,144 @@ __global__ void __launch_bounds__(kThreads) adjoint4_kernel(nbm_shared_step_t s)
     *reinterpret_cast<float4*>(s.G + e) = g;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// "faces" table (nbm_assemble_t.faces): the finite-volume matrix of regular rows is symmetric, so one
+// un-normalised coefficient per FACE (3 per node) + 1/diag replaces the 7 row weights: 28 B/node in the
+// residual pass and 24 B/node in the adjoint pass instead of 40 / 36.  Irregular rows live entirely in
+// the list, Dirichlet rows are dinv = -1.
+//   regular row:  r = dinv * ( (sum_f c_f) u_p - sum_f c_f u_nb(f) ) - rhs          (discretization.py:366-386)
+// ---------------------------------------------------------------------------------------------
+struct Faces4 {
+    float4 cxp, cxm, cyp, cym, czp, czm;
+};
+__device__ __forceinline__ Faces4 load_faces4(const nbm_shared_step_t& s, int64_t e, int m, int ix, int64_t sx,
+                                              int64_t sy, int64_t ne, int plane) {
+    Faces4 f;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    f.cxp = ld4(s.cface + e);
+    f.cxm = ix > 0 ? ld4(s.cface + e - sx) : z4;
+    f.cyp = ld4(s.cface + ne + e);
+    f.cym = m >= sy ? ld22(s.cface + ne + e - sy) : z4;
+    f.czp = ld4(s.cface + 2 * ne + e);
+    float l = (m == 0 && ix == 0) ? 0.f : s.cface[2 * ne + e - 1];
+    f.czm = make_float4(l, f.czp.x, f.czp.y, f.czp.z);
+    (void)plane;
+    return f;
+}
+#define NBM_DIAG(F, c) ((((((F).cxm.c + (F).cxp.c) + (F).cym.c) + (F).cyp.c) + (F).czm.c) + (F).czp.c)
+
+__global__ void __launch_bounds__(kThreads) residual_faces4_kernel(nbm_shared_step_t s) {
+    const int plane = s.ey * s.ez;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int ix = blockIdx.y + 1;
+    if (m >= plane) return;
+    const int64_t sx = plane, sy = s.ez;
+    const int64_t ne = sx * s.ex;
+    const int64_t e = ix * sx + m;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool first = (m == 0), last = (m + 4 >= plane);
+    const float4 di = ldcs4(s.dinv + e);
+    const float4 rh = ldcs4(s.rhs + e);
+    const Faces4 F = load_faces4(s, e, m, ix, sx, sy, ne, plane);
+    const float4 kv = s.kv ? ldcs4(s.kv + e) : z4;
+    const float4 u0 = ld4(s.U + e);
+    const float4 uxm = ld4(s.U + e - sx), uxp = ld4(s.U + e + sx);
+    const float4 uym = (m >= sy) ? ld22(s.U + e - sy) : z4;
+    const float4 uyp = (m + 4 + sy <= plane) ? ld22(s.U + e + sy) : z4;
+    const float ul = first ? 0.f : s.U[e - 1], ur = last ? 0.f : s.U[e + 4];
+    const float4 uzm = make_float4(ul, u0.x, u0.y, u0.z), uzp = make_float4(u0.y, u0.z, u0.w, ur);
+    float4 r;
+#define NBM_ROW(c)                                                                                                   \
+    {                                                                                                                \
+        float acc = (NBM_DIAG(F, c) + kv.c) * u0.c;                                                                         \
+        acc = fmaf(-F.cxm.c, uxm.c, acc); acc = fmaf(-F.cxp.c, uxp.c, acc);                                          \
+        acc = fmaf(-F.cym.c, uym.c, acc); acc = fmaf(-F.cyp.c, uyp.c, acc);                                          \
+        acc = fmaf(-F.czm.c, uzm.c, acc); acc = fmaf(-F.czp.c, uzp.c, acc);                                          \
+        r.c = di.c > 0.f ? fmaf(di.c, acc, -rh.c) : (di.c < 0.f ? u0.c - rh.c : 0.f);                                \
+    }
+    NBM_ROW(x) NBM_ROW(y) NBM_ROW(z) NBM_ROW(w)
+#undef NBM_ROW
+    if (s.nl) {
+        float4 a = ld4(s.nl + e), b = ld4(s.nl + ne + e);
+        r.x += a.x * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.x) + b.x * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.x);
+        r.y += a.y * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.y) + b.y * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.y);
+        r.z += a.z * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.z) + b.z * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.z);
+        r.w += a.w * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.w) + b.w * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.w);
+    }
+    *reinterpret_cast<float4*>(s.R + e) = r;
+}
+
+// T = dinv * R for regular rows (0 otherwise): d loss / d (un-normalised row)
+__device__ __forceinline__ float4 tval4(float4 di, float4 r) {
+    return make_float4(di.x > 0.f ? di.x * r.x : 0.f, di.y > 0.f ? di.y * r.y : 0.f, di.z > 0.f ? di.z * r.z : 0.f,
+                       di.w > 0.f ? di.w * r.w : 0.f);
+}
+__device__ __forceinline__ float tval(float di, float r) { return di > 0.f ? di * r : 0.f; }
+
+__global__ void __launch_bounds__(kThreads) adjoint_faces4_kernel(nbm_shared_step_t s) {
+    const int plane = s.ey * s.ez;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int ix = blockIdx.y;
+    if (m >= plane) return;
+    const int64_t sx = plane, sy = s.ez;
+    const int64_t ne = sx * s.ex;
+    const int64_t e = ix * sx + m;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool first = (m == 0 && ix == 0), last = (m + 4 >= plane && ix + 1 >= s.ex);
+    const float4 di = ldcs4(s.dinv + e);
+    const float4 r0 = ld4(s.R + e);
+    const Faces4 F = load_faces4(s, e, m, ix, sx, sy, ne, plane);
+    const float4 t0 = tval4(di, r0);
+    const float4 txm = ix > 0 ? tval4(ld4(s.dinv + e - sx), ld4(s.R + e - sx)) : z4;
+    const float4 txp = ix + 1 < s.ex ? tval4(ld4(s.dinv + e + sx), ld4(s.R + e + sx)) : z4;
+    const float4 tym = m >= sy ? tval4(ld22(s.dinv + e - sy), ld22(s.R + e - sy)) : z4;
+    const float4 typ = m + 4 + sy <= plane ? tval4(ld22(s.dinv + e + sy), ld22(s.R + e + sy)) : z4;
+    const float tl = first ? 0.f : tval(s.dinv[e - 1], s.R[e - 1]);
+    const float tr = last ? 0.f : tval(s.dinv[e + 4], s.R[e + 4]);
+    const float4 tzm = make_float4(tl, t0.x, t0.y, t0.z), tzp = make_float4(t0.y, t0.z, t0.w, tr);
+    const float4 kv = s.kv ? ldcs4(s.kv + e) : z4;
+    float4 g;
+#define NBM_ADJ(c)                                                                                                   \
+    {                                                                                                                \
+        float acc = di.c > 0.f ? (NBM_DIAG(F, c) + kv.c) * t0.c : (di.c < 0.f ? r0.c : 0.f);                                 \
+        acc = fmaf(-F.cxm.c, txm.c, acc); acc = fmaf(-F.cxp.c, txp.c, acc);                                          \
+        acc = fmaf(-F.cym.c, tym.c, acc); acc = fmaf(-F.cyp.c, typ.c, acc);                                          \
+        acc = fmaf(-F.czm.c, tzm.c, acc); acc = fmaf(-F.czp.c, tzp.c, acc);                                          \
+        g.c = acc;                                                                                                   \
+    }
+    NBM_ADJ(x) NBM_ADJ(y) NBM_ADJ(z) NBM_ADJ(w)
+#undef NBM_ADJ
+    if (s.nl) {
+        float4 u0 = ld4(s.U + e), a = ld4(s.nl + e), b = ld4(s.nl + ne + e);
+        g.x += (a.x * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.x) + b.x * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.x)) * r0.x;
+        g.y += (a.y * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.y) + b.y * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.y)) * r0.y;
+        g.z += (a.z * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.z) + b.z * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.z)) * r0.z;
+        g.w += (a.w * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.w) + b.w * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.w)) * r0.w;
+    }
+    *reinterpret_cast<float4*>(s.G + e) = g;
+}
+
 // C0: adjoint of the irregular rows: gE[c] += wE * R[p]
 __global__ void irregular_bwd_kernel(nbm_shared_step_t s) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= s.n_irr) return;
-    float r = s.R[s.irr_point[q]];
+    const int64_t e = s.irr_point[q];
+    float r = s.R[e];
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         int32_t c = s.irr_c[q * 7 + k];
         if (c >= 0) atomicAdd(s.gE + c, s.irr_wE[q * 7 + k] * r);
+    }
+    if (s.faces) {
+        const int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
+        const int64_t off[7] = {0, -sx, sx, -sy, sy, -1, 1};
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            float w = s.irr_wU[q * 7 + k];
+            if (w != 0.0f) atomicAdd(s.G + e + off[k], w * r);
+        }
+        // (the U-part of the nonlinear term is in the dense nl table: the dense adjoint pass already added it)
     }
     uint8_t nlr = s.irr_nl[q];
     if (nlr) {
@@ -769,11 +1051,33 @@ __device__ __forceinline__ void block_reduce_store(typename NET::Acc& acc, float
 // (value_and_grad(self.loss), trainer.py:786; mean of optax.l2_loss, :899-901)
 // GENERAL = false: the shared path (one replica, every node of the lattice, loss from R);
 // GENERAL = true : the 7 displaced lattices of the general path (node range filter, no R)
+//
+// 12 warps per SM (168 registers): the p-head accumulators are pair-split (MlpP::AccS), the y/z rows and
+// the bias of the first layer live in shared memory and are touched once per task.
+constexpr int kGradThreads = 384;
+
+template <class NET>
+constexpr int grad_smem_bytes() {
+    return (3 * NET::HPW * kGradThreads + (kGradThreads / 32) * (NET::NP + 1)) * (int)sizeof(float);
+}
+
 template <class NET, bool GENERAL>
-__global__ void __launch_bounds__(kThreads, 1) node_grad_kernel(NodeView v, Tasks T) {
-    typename NET::Acc acc;
+__global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, Tasks T) {
+    using P = typename NET::P;
+    using M = typename NET::M;
+    constexpr int H = NET::HPW, HP2 = H / 2, NP = NET::NP;
+    extern __shared__ float dsm[];
+    float* hs = dsm + threadIdx.x;                      // [3H] hoisted sums of this thread, stride kGradThreads
+    float* red = dsm + 3 * H * kGradThreads;            // [warps][NP + 1]
+#pragma unroll
+    for (int i = 0; i < 3 * H; ++i) hs[i * kGradThreads] = 0.0f;
+    typename P::AccS acc;
     acc.zero();
+    float accm[M::NP];
+#pragma unroll
+    for (int i = 0; i < M::NP; ++i) accm[i] = 0.0f;
     float loss = 0.0f;
+    const bool par = (threadIdx.x & 1) != 0;
     const int rep = blockIdx.y;
     const float* xe = v.xe + (size_t)rep * v.ex;
     const float* ye = v.ye + (size_t)rep * v.ey;
@@ -782,35 +1086,85 @@ __global__ void __launch_bounds__(kThreads, 1) node_grad_kernel(NodeView v, Task
     const float* G = v.G + rep * v.rep_nodes;
     const float* R = v.R;  // only the shared path (one replica) accumulates the loss here
     for (int task = blockIdx.x; task < T.total; task += gridDim.x) {
-        int mb = task % T.mblocks, xc = task / T.mblocks;
-        int m = mb * kThreads + threadIdx.x;
-        if (m >= T.plane) continue;
-        int iy = m / v.ez, iz = m - iy * v.ez;
-        float y = __ldg(ye + iy), z = __ldg(ze + iz);
-        int x0 = v.x_begin + xc * T.xchunk, x1 = min(v.x_end, x0 + T.xchunk);
-        // software pipeline: the loads of plane ix+1 are in flight while plane ix is computed (only 8 warps
-        // per SM fit beside the 167 accumulators, so HBM latency has to be hidden explicitly)
+        const int mb = task % T.mblocks, xc = task / T.mblocks;
+        const int m_raw = mb * kGradThreads + threadIdx.x;
+        const bool valid = m_raw < T.plane;             // lanes past the plane stay in the warp (shuffles) with g = 0
+        const int m = valid ? m_raw : T.plane - 1;
+        const int iy = m / v.ez, iz = m - iy * v.ez;
+        const float y = __ldg(ye + iy), z = __ldg(ze + iz);
+        u64 yz[HP2];
+        P::template first_layer_yz<0>(y, z, yz);
+        const int x0 = v.x_begin + xc * T.xchunk, x1 = min(v.x_end, x0 + T.xchunk);
+        // software pipeline: the loads of plane ix+1 are in flight while plane ix is computed
         int64_t e = (int64_t)x0 * T.plane + m;
-        bool in_n = !GENERAL || (e >= v.lo && e < v.hi);
-        float g_n = in_n ? __ldg(G + e) : 0.0f, r_n = GENERAL ? 0.0f : __ldg(R + e), x_n = __ldg(xe + x0);
+        bool in_n = valid && (!GENERAL || (e >= v.lo && e < v.hi));
+        float g_n = in_n ? __ldg(G + e) : 0.0f, r_n = (GENERAL || !valid) ? 0.0f : __ldg(R + e), x_n = __ldg(xe + x0);
         uint8_t sd_n = __ldg(side + e);
         for (int ix = x0; ix < x1; ++ix) {
-            float g = g_n * v.inv_n, r = r_n, x = x_n;
-            bool plus = (sd_n & 1) != 0;
+            const float g = g_n * v.inv_n, r = r_n, x = x_n;
+            const bool plus = (sd_n & 1) != 0;
             if (ix + 1 < x1) {
                 e += T.plane;
-                in_n = !GENERAL || (e >= v.lo && e < v.hi);
+                in_n = valid && (!GENERAL || (e >= v.lo && e < v.hi));
                 g_n = in_n ? __ldg(G + e) : 0.0f;
-                if (!GENERAL) r_n = __ldg(R + e);
+                if (!GENERAL) r_n = valid ? __ldg(R + e) : 0.0f;
                 sd_n = __ldg(side + e);
                 x_n = __ldg(xe + ix + 1);
             }
             loss = fmaf(0.5f * r, r, loss);
-            if (g != 0.0f) NET::grad(plus, x, y, z, g, acc);
+            const bool do_p = plus && g != 0.0f;
+            if (__any_sync(0xffffffffu, do_p)) P::grad_split(x, yz, do_p ? g : 0.0f, acc, par);
+            if (!plus && g != 0.0f) {
+                float a[NET::LMD][NET::HMW];
+                M::template forward<P::NP>(x, y, z, a);
+                M::template backward<P::NP, M::NP, P::NP>(x, y, z, a, g, accm);
+            }
         }
+        // fold the task's sum(delta1) into the bias and the y, z rows of the first layer
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const float t = (j & 1) ? hi32(acc.t[j / 2]) : lo32(acc.t[j / 2]);
+            hs[j * kGradThreads] += t;
+            hs[(H + j) * kGradThreads] = fmaf(y, t, hs[(H + j) * kGradThreads]);
+            hs[(2 * H + j) * kGradThreads] = fmaf(z, t, hs[(2 * H + j) * kGradThreads]);
+        }
+#pragma unroll
+        for (int j = 0; j < HP2; ++j) acc.t[j] = 0ull;
     }
     loss *= v.inv_n;
-    block_reduce_store<NET>(acc, loss, v.partials + (size_t)(v.row0 + rep * gridDim.x) * (NET::NP + 1));
+    // block reduction into partials[row][0..NP] (loss last)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i <= NP; ++i) {
+        float val;
+        if (i < P::NP) val = P::split_get(acc, i, par, hs, kGradThreads);
+        else if (i < NP) val = accm[i < NP ? i - P::NP : 0];
+        else val = loss;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        if (lane == 0) red[warp * (NP + 1) + i] = val;
+    }
+    __syncthreads();
+    float* partials = v.partials + (size_t)(v.row0 + rep * gridDim.x) * (NP + 1);
+    for (int i = threadIdx.x; i < NP + 1; i += kGradThreads) {
+        float val = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kGradThreads / 32; ++w) val += red[w * (NP + 1) + i];
+        partials[(size_t)blockIdx.x * (NP + 1) + i] = val;
+    }
+}
+
+template <class NET, bool GENERAL>
+static cudaError_t launch_node_grad(dim3 grid, const NodeView& v, const Tasks& T, cudaStream_t st) {
+    static bool configured = false;   // per instantiation; the attribute is a property of the function
+    constexpr int bytes = grad_smem_bytes<NET>();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(node_grad_kernel<NET, GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    node_grad_kernel<NET, GENERAL><<<grid, kGradThreads, bytes, st>>>(v, T);
+    return cudaSuccess;
 }
 
 // K4a: deterministic sum of the per-CTA partial rows
@@ -1034,7 +1388,10 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     if ((stages & NBM_STAGE_EXTRAP) && s.n_crossed > 0)
         extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
     if (stages & NBM_STAGE_RESIDUAL) {
-        if (vec4) {
+        if (s.faces) {
+            dim3 g((s.ey * s.ez / 4 + kThreads - 1) / kThreads, s.ex - 2);
+            residual_faces4_kernel<<<g, kThreads, 0, st>>>(s);
+        } else if (vec4) {
             dim3 g((s.ey * s.ez / 4 + kThreads - 1) / kThreads, s.ex - 2);
             residual4_kernel<<<g, kThreads, 0, st>>>(s);
         } else {
@@ -1044,7 +1401,10 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
         if (s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
     }
     if (stages & NBM_STAGE_ADJOINT) {
-        if (vec4) {
+        if (s.faces) {
+            dim3 g((s.ey * s.ez / 4 + kThreads - 1) / kThreads, s.ex);
+            adjoint_faces4_kernel<<<g, kThreads, 0, st>>>(s);
+        } else if (vec4) {
             dim3 g((s.ey * s.ez / 4 + kThreads - 1) / kThreads, s.ex);
             adjoint4_kernel<<<g, kThreads, 0, st>>>(s);
         } else {
@@ -1054,9 +1414,19 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
         if (s.n_irr > 0) irregular_bwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
         if (s.n_crossed > 0) extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, st>>>(s);
     }
-    int gridC = min(T.total, min(kPartialRows, sms));
+    // the gradient kernel runs one 384-thread CTA per SM: its own strips, x chunks sized for >= 2 tasks per CTA
+    int xchunk_g = 16;
+    {
+        int mblocks = (s.ey * s.ez + kGradThreads - 1) / kGradThreads;
+        while (xchunk_g > 2 && (int64_t)mblocks * ((s.ex + xchunk_g - 1) / xchunk_g) < 2 * (int64_t)sms) xchunk_g >>= 1;
+    }
+    const Tasks Tg = make_tasks(s.ex, s.ey, s.ez, xchunk_g, kGradThreads);
+    int gridC = min(Tg.total, min(kPartialRows, sms));
     if (gridC > s.n_partial_rows) gridC = s.n_partial_rows;
-    if (stages & NBM_STAGE_GRAD) node_grad_kernel<NET, false><<<gridC, kThreads, 0, st>>>(view_of(s), T);
+    if (stages & NBM_STAGE_GRAD) {
+        cudaError_t e = launch_node_grad<NET, false>(dim3(gridC), view_of(s), Tg, st);
+        if (e != cudaSuccess) return cuda_check(e, "node_grad attribute");
+    }
     if (stages & NBM_STAGE_REDUCE)
         reduce_partials_kernel<<<(NET::NP + 1 + 127) / 128, 128, 0, st>>>(s.partials, gridC, NET::NP + 1, s.loss_grad);
     return cuda_check(cudaGetLastError(), "shared step launch");
@@ -1279,7 +1649,8 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     }
     Tasks T = make_tasks(v.x_end - v.x_begin, s.ny, s.nz, xchunk);
     const int gridF = min(T.total, sms * 2);
-    const int gridG = min(T.total, max(1, sms / 4));         // x 7 replicas: ~2 waves of the 1-CTA/SM backward kernel
+    const Tasks Tg = make_tasks(v.x_end - v.x_begin, s.ny, s.nz, xchunk, kGradThreads);
+    const int gridG = min(Tg.total, max(1, sms / 4));        // x 7 replicas: ~2 waves of the 1-CTA/SM backward kernel
     const int gridR = (int)min((int64_t)sms * 2, (nb + kThreads - 1) / kThreads);
     int gridE = 0;
     if (s.n_crossed > 0) gridE = (int)min((int64_t)sms, (s.n_crossed * 32 + kThreads - 1) / kThreads);
@@ -1294,7 +1665,10 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     fwd_nodes_kernel<NET, true><<<dim3(gridF, 7), kThreads, 0, st>>>(v, T);
     points_rows_kernel<<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, 7 * gridG, np1);
     v.row0 = 0;
-    node_grad_kernel<NET, true><<<dim3(gridG, 7), kThreads, 0, st>>>(v, T);
+    {
+        cudaError_t e = launch_node_grad<NET, true>(dim3(gridG, 7), v, Tg, st);
+        if (e != cudaSuccess) return cuda_check(e, "node_grad attribute");
+    }
     if (gridE > 0) points_extrap_bwd_kernel<NET><<<gridE, kThreads, 0, st>>>(a, 7 * gridG + gridR);
     reduce_partials_kernel<<<(np1 + 127) / 128, 128, 0, st>>>(s.partials, rows_needed, np1, s.loss_grad);
     return cuda_check(cudaGetLastError(), "points step launch");
@@ -1356,7 +1730,17 @@ int nbm_ffma_probe_f32(int iters, float* out, double* flops_host, nbm_stream_t s
 
 int nbm_loss_grad_shared_f32(const nbm_shared_step_t* s, nbm_stream_t stream) {
     NBM_REQUIRE(s, "null plan");
-    NBM_REQUIRE(s->xe && s->ye && s->ze && s->side && s->w && s->rhs, "null tables");
+    NBM_REQUIRE(s->xe && s->ye && s->ze && s->side && s->rhs, "null tables");
+    if (s->faces) {
+        NBM_REQUIRE(s->cface && s->dinv, "null face tables");
+        NBM_REQUIRE(s->n_irr == 0 || (s->irr_wU && s->irr_rhs), "null irregular-row tables (faces mode)");
+        NBM_REQUIRE(((s->ey * s->ez) % 4 == 0) && (s->ez % 2 == 0) &&
+                        ((((uintptr_t)s->cface | (uintptr_t)s->dinv | (uintptr_t)s->rhs | (uintptr_t)s->U |
+                           (uintptr_t)s->R | (uintptr_t)s->G | (uintptr_t)s->nl | (uintptr_t)s->kv) & 15) == 0),
+                    "faces mode needs plane % 4 == 0, even ez and 16-byte aligned arrays");
+    } else {
+        NBM_REQUIRE(s->w, "null tables");
+    }
     NBM_REQUIRE(s->ex >= 3 && s->ey >= 3 && s->ez >= 3, "lattice too small");
     NBM_REQUIRE(s->U && s->R && s->G && s->partials && s->loss_grad, "null work buffers");
     NBM_REQUIRE(s->n_partial_rows >= 1, "n_partial_rows must be >= 1");

@@ -231,7 +231,11 @@ class SharedPlan:
     HX, HY, HZ = 2, 1, 1
 
     def __init__(self, lvl: LevelSet, tr_gstate, xa: int, xb: int, fns, net: NetShape,
-                 nonlinear_m: Nonlinear, nonlinear_p: Nonlinear, n_mean: Optional[int] = None, device=None):
+                 nonlinear_m: Nonlinear, nonlinear_p: Nonlinear, n_mean: Optional[int] = None, device=None,
+                 faces: Optional[bool] = None):
+        """`faces`: store one coefficient per cell FACE + 1/diag (16 B/node) instead of the 7 row weights
+        (28 B/node); irregular rows move into the list.  Default: on whenever the 16-byte stencil kernels
+        apply (even Ny, Nz)."""
         dev = torch.device(device if device is not None else lvl.device)
         self.device, self.net, self.lvl = dev, net, lvl
         L = cabi.lib()
@@ -277,7 +281,15 @@ class SharedPlan:
 
             # ---- K2c row assembly into lattice layout
             use_nl = (nonlinear_m.kind != NL_NONE) or (nonlinear_p.kind != NL_NONE)
-            self.w = torch.zeros(7 * ne, dtype=torch.float32, device=dev)
+            can_faces = (ey % 2 == 0) and (ez % 2 == 0)
+            if faces and not can_faces:
+                raise ValueError("faces=True needs even Ny and Nz (16-byte aligned lattice rows)")
+            self.faces = can_faces if faces is None else bool(faces)
+            self.w = None if self.faces else torch.zeros(7 * ne, dtype=torch.float32, device=dev)
+            self.cface = torch.zeros(3 * ne, dtype=torch.float32, device=dev) if self.faces else None
+            self.dinv = torch.zeros(ne, dtype=torch.float32, device=dev) if self.faces else None
+            use_kv = self.faces and bool(((k_m != 0) | (k_p != 0)).any().item())
+            self.kv = torch.zeros(ne, dtype=torch.float32, device=dev) if use_kv else None
             self.rhs = torch.zeros(ne, dtype=torch.float32, device=dev)
             self.nl = torch.zeros(2 * ne, dtype=torch.float32, device=dev) if use_nl else None
             irr = torch.full((ne,), -1, dtype=torch.int32, device=dev)
@@ -288,6 +300,16 @@ class SharedPlan:
             irr_c = torch.full((cap * 7,), -1, dtype=torch.int32, device=dev)
             irr_nl = torch.zeros(cap, dtype=torch.uint8, device=dev)
             irr_nlw = torch.zeros(cap, dtype=torch.float32, device=dev)
+            if self.faces:
+                # a row is also irregular when a neighbour sits on the other side of the interface
+                cap = min(np_, 7 * cs.n + np_ // 64 + 1024) + 1
+                irr_point = torch.zeros(cap, dtype=torch.int64, device=dev)
+                irr_wE = torch.zeros(cap * 7, dtype=torch.float32, device=dev)
+                irr_c = torch.full((cap * 7,), -1, dtype=torch.int32, device=dev)
+                irr_nl = torch.zeros(cap, dtype=torch.uint8, device=dev)
+                irr_nlw = torch.zeros(cap, dtype=torch.float32, device=dev)
+            irr_wU = torch.zeros(cap * 7, dtype=torch.float32, device=dev) if self.faces else None
+            irr_rhs = torch.zeros(cap, dtype=torch.float32, device=dev) if self.faces else None
             a = cabi.Assemble()
             a.pts = _lattice(pxs, ys, zs)
             a.dx, a.dy, a.dz = dx, dy, dz
@@ -307,11 +329,16 @@ class SharedPlan:
             a.irr_capacity = cap
             a.irr_count, a.irr_point = cabi.ptr(irr_count), cabi.ptr(irr_point)
             a.irr_wE, a.irr_c, a.irr_nl, a.irr_nlw = (cabi.ptr(t) for t in (irr_wE, irr_c, irr_nl, irr_nlw))
+            a.faces = 1 if self.faces else 0
+            a.cface, a.dinv, a.kv = cabi.ptr(self.cface), cabi.ptr(self.dinv), cabi.ptr(self.kv)
+            a.irr_wU, a.irr_rhs = cabi.ptr(irr_wU), cabi.ptr(irr_rhs)
             cabi.check(L.nbm_assemble_f32(C.byref(a), st), "nbm_assemble_f32")
             n_irr = int(irr_count.item())
             if n_irr > cap:
                 raise cabi.NbmError(f"irregular-row capacity exceeded ({n_irr} > {cap})")
             self.n_irr = n_irr
+            self.irr_wU = irr_wU[:max(n_irr, 1) * 7].clone() if self.faces else None
+            self.irr_rhs = irr_rhs[:max(n_irr, 1)].clone() if self.faces else None
             self.irr_point = irr_point[:max(n_irr, 1)].clone()
             self.irr_wE = irr_wE[:max(n_irr, 1) * 7].clone()
             self.irr_c = irr_c[:max(n_irr, 1) * 7].clone()
@@ -345,6 +372,9 @@ class SharedPlan:
             s.inv_n_points = 1.0 / float(n_mean if n_mean is not None else self.n_points)
             s.U, s.R, s.G, s.E, s.gE = (cabi.ptr(t) for t in (self.U, self.R, self.G, self.E, self.gE))
             s.partials, s.n_partial_rows, s.loss_grad = cabi.ptr(self.partials), rows, cabi.ptr(self.loss_grad)
+            s.faces = 1 if self.faces else 0
+            s.cface, s.dinv, s.kv = cabi.ptr(self.cface), cabi.ptr(self.dinv), cabi.ptr(self.kv)
+            s.irr_wU, s.irr_rhs = cabi.ptr(self.irr_wU), cabi.ptr(self.irr_rhs)
             self.step = s
             self.xa, self.xb = xa, xb
             # the regression/cut-cell scratch is not needed by the step
@@ -372,6 +402,14 @@ class SharedPlan:
         return target
 
     # ---- read-backs for tests -----------------------------------------------------------------
+    def rhs_rows(self) -> torch.Tensor:
+        """rhs/diag of every row in lattice layout (in faces mode the irregular rows' entries live in the list)"""
+        if not self.faces or self.n_irr == 0:
+            return self.rhs
+        out = self.rhs.clone()
+        out[self.irr_point[:self.n_irr]] = self.irr_rhs[:self.n_irr]
+        return out
+
     def point_view(self, t: torch.Tensor) -> torch.Tensor:
         """lattice-layout array -> (n_points,) in the reference's point order"""
         ex, ey, ez = self.dims

@@ -149,7 +149,7 @@ def test_cuda_rows_match_reference_golden(path):
             nplan.upload_params(shape, params.to(DEV))
             pl.loss_grad_launch()
             torch.cuda.synchronize()
-        rhs_k = pl.point_view(pl.rhs).cpu()[idx]
+        rhs_k = pl.point_view(pl.rhs_rows()).cpu()[idx]
         lhs_k = pl.point_view(pl.R).cpu()[idx] + rhs_k
         flag_k = pl.point_view(pl.sites.flag).cpu()[idx]
         cidx = pl.point_view(pl.sites.cidx).cpu()[idx]

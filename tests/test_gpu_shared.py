@@ -32,13 +32,13 @@ def fns_of(problem):
                              problem.nonlinear_op_m, problem.nonlinear_op_p)
 
 
-def build(problem, n_train, n_lvl, interp="trilinear", net=None, xa=0, xb=None):
+def build(problem, n_train, n_lvl, interp="trilinear", net=None, xa=0, xb=None, faces=None):
     tr, lv, phi_grid, oprob = util.make_case(problem, n_train, n_lvl, interp, torch.float64, net=net)
     lvl = nplan.LevelSet(lv, phi_grid, interp=interp, perturb_eps=1e-10, device=DEV)
     shape = nplan.NetShape(oprob.shape.Lp, oprob.shape.Hp, oprob.shape.Lm, oprob.shape.Hm)
     pl = nplan.SharedPlan(lvl, tr, xa, xb if xb is not None else tr.shape()[0], fns_of(problem), shape,
                           nplan.Nonlinear.coerce(problem.nonlinear_op_m),
-                          nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=DEV)
+                          nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=DEV, faces=faces)
     return tr, lv, lvl, oprob, pl, shape
 
 
@@ -94,12 +94,15 @@ def test_classification_and_cut_cells(name):
     assert util.rel_inf(got, want) < TOL_FRAC
 
 
-# n = 15 gives an odd (y,z) plane: the scalar stencil kernels; the others take the 16-byte vector path
-@pytest.mark.parametrize("name,n,nl", [("sphere", 16, 32), ("star", 16, 32), ("no_jump", 12, 16), ("sphere", 24, 24),
-                                       ("star", 15, 32)])
-def test_rows_loss_and_gradient(name, n, nl):
+# n = 15 gives an odd (y,z) plane: the scalar stencil kernels; the others take the 16-byte vector path.
+# faces: one coefficient per cell face + 1/diag (the default on even grids) against the 7-weight row table.
+@pytest.mark.parametrize("name,n,nl,faces", [("sphere", 16, 32, True), ("star", 16, 32, True), ("no_jump", 12, 16, True),
+                                             ("sphere", 24, 24, True), ("star", 15, 32, False),
+                                             ("sphere", 16, 32, False), ("star", 16, 32, False)])
+def test_rows_loss_and_gradient(name, n, nl, faces):
     P = problems.PROBLEMS[name]()
-    tr, lv, lvl, oprob, pl, shape = build(P, n, nl)
+    tr, lv, lvl, oprob, pl, shape = build(P, n, nl, faces=faces)
+    assert pl.faces == faces
     dt = torch.float64
     params = O.init_params(oprob.shape, seed=7, dtype=dt)
     d = [tr.dx.to(dt), tr.dy.to(dt), tr.dz.to(dt)]
@@ -110,7 +113,7 @@ def test_rows_loss_and_gradient(name, n, nl):
         nplan.upload_params(shape, p_dev)
         lg = pl.loss_grad_launch()
         torch.cuda.synchronize()
-    rhs_k = pl.point_view(pl.rhs).cpu()
+    rhs_k = pl.point_view(pl.rhs_rows()).cpu()
     lhs_k = pl.point_view(pl.R).cpu() + rhs_k
     e_rhs, e_lhs = util.rel_inf(rhs_k, rhs_o), util.rel_inf(lhs_k, lhs_o)
     assert e_rhs < TOL_ROW and e_lhs < TOL_ROW, (e_lhs, e_rhs)
@@ -144,7 +147,7 @@ def test_anisotropic_grid_and_interface_at_the_box_boundary():
     with torch.cuda.device(DEV):
         nplan.upload_params(shape, params.float().to(DEV))
         lg = pl.loss_grad_launch().cpu()
-    rhs_k = pl.point_view(pl.rhs).cpu()
+    rhs_k = pl.point_view(pl.rhs_rows()).cpu()
     lhs_k = pl.point_view(pl.R).cpu() + rhs_k
     assert util.rel_inf(lhs_k, lhs_o) < TOL_ROW and util.rel_inf(rhs_k, rhs_o) < TOL_ROW
     assert abs(float(lg[-1]) - float(loss_o)) / float(loss_o) < TOL_LOSS
