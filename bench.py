@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
                     help="peer: partial-row reduction fused with the all-reduce over NVLink peer memory; nccl: ncclAllReduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--faces", type=int, default=-1, help="1/0: face-coefficient row table on/off (default: auto)")
+    ap.add_argument("--fused", type=int, default=-1, help="1/0: adjoint stencil fused into the gradient kernel (default: auto)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=12288)
     return ap.parse_args()
@@ -228,7 +230,9 @@ def main():
                                                          "crossed_sites": int(level.sites.n), "irregular_rows": int(level.n_irr)}}))
         return
     pl = nplan.SharedPlan(lvl, tr, xa, xb, fns, net, nplan.Nonlinear.coerce(problem.nonlinear_op_m),
-                          nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=dev)
+                          nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=dev,
+                          faces=None if args.faces < 0 else bool(args.faces),
+                          fused=None if args.fused < 0 else bool(args.fused))
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
 

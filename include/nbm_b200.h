@@ -236,6 +236,14 @@ typedef struct {
     int faces;
     const float* cface; const float* dinv; const float* irr_wU; const float* irr_rhs;
     const float* kv;                 /* may be NULL */
+    /* fused adjoint (faces mode, no nonlinear operator): when S != NULL the residual pass also writes
+     * S = dinv * R of the regular rows, the dense adjoint stencil is NOT run as a kernel but evaluated inside
+     * the gradient kernel from row tables staged plane by plane into shared memory with bulk async copies
+     * (TMA, mbarrier completion).  G then only collects the list contributions (irregular rows, extrapolation):
+     * it must be zero on entry (the gradient kernel re-zeroes what it consumed), nodes that can receive such a
+     * contribution carry bit 2 (value 4) in `side`, and `side` must be readable up to the next multiple of 16
+     * bytes past ex*ey*ez. */
+    float* S;                        /* [ne] or NULL */
 } nbm_shared_step_t;
 
 /* stages of the shared-evaluation step, in launch order */

@@ -67,7 +67,7 @@ class SharedStep(C.Structure):
                 ("U", c_fp), ("R", c_fp), ("G", c_fp), ("E", c_fp), ("gE", c_fp),
                 ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp), ("stages", C.c_int),
                 ("faces", C.c_int), ("cface", c_fp), ("dinv", c_fp), ("irr_wU", c_fp), ("irr_rhs", c_fp),
-                ("kv", c_fp)]
+                ("kv", c_fp), ("S", c_fp)]
 
 
 class PointsStep(C.Structure):

@@ -875,6 +875,12 @@ __global__ void __launch_bounds__(kThreads) adjoint4_kernel(nbm_shared_step_t s)
 struct Faces4 {
     float4 cxp, cxm, cyp, cym, czp, czm;
 };
+// T = dinv * R for regular rows (0 otherwise): d loss / d (un-normalised row)
+__device__ __forceinline__ float4 tval4(float4 di, float4 r) {
+    return make_float4(di.x > 0.f ? di.x * r.x : 0.f, di.y > 0.f ? di.y * r.y : 0.f, di.z > 0.f ? di.z * r.z : 0.f,
+                       di.w > 0.f ? di.w * r.w : 0.f);
+}
+__device__ __forceinline__ float tval(float di, float r) { return di > 0.f ? di * r : 0.f; }
 __device__ __forceinline__ Faces4 load_faces4(const nbm_shared_step_t& s, int64_t e, int m, int ix, int64_t sx,
                                               int64_t sy, int64_t ne, int plane) {
     Faces4 f;
@@ -930,14 +936,8 @@ __global__ void __launch_bounds__(kThreads) residual_faces4_kernel(nbm_shared_st
         r.w += a.w * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.w) + b.w * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.w);
     }
     *reinterpret_cast<float4*>(s.R + e) = r;
+    if (s.S) *reinterpret_cast<float4*>(s.S + e) = tval4(di, r);
 }
-
-// T = dinv * R for regular rows (0 otherwise): d loss / d (un-normalised row)
-__device__ __forceinline__ float4 tval4(float4 di, float4 r) {
-    return make_float4(di.x > 0.f ? di.x * r.x : 0.f, di.y > 0.f ? di.y * r.y : 0.f, di.z > 0.f ? di.z * r.z : 0.f,
-                       di.w > 0.f ? di.w * r.w : 0.f);
-}
-__device__ __forceinline__ float tval(float di, float r) { return di > 0.f ? di * r : 0.f; }
 
 __global__ void __launch_bounds__(kThreads) adjoint_faces4_kernel(nbm_shared_step_t s) {
     const int plane = s.ey * s.ez;
@@ -1066,7 +1066,7 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
     using P = typename NET::P;
     using M = typename NET::M;
     constexpr int H = NET::HPW, HP2 = H / 2, NP = NET::NP;
-    extern __shared__ float dsm[];
+    extern __shared__ __align__(16) float dsm[];
     float* hs = dsm + threadIdx.x;                      // [3H] hoisted sums of this thread, stride kGradThreads
     float* red = dsm + 3 * H * kGradThreads;            // [warps][NP + 1]
 #pragma unroll
@@ -1164,6 +1164,350 @@ static cudaError_t launch_node_grad(dim3 grid, const NodeView& v, const Tasks& T
         configured = true;
     }
     node_grad_kernel<NET, GENERAL><<<grid, kGradThreads, bytes, st>>>(v, T);
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused adjoint + gradient (faces mode, nbm_shared_step_t.S != NULL).  The dense adjoint stencil
+//   G[e] = D_e S[e] - sum_f c_f S[nb_f(e)],   S = dinv * R,
+// is evaluated inside the gradient kernel.  A CTA walks (strip of 384 cells) x (x planes); for every plane
+// one elected thread issues bulk async copies (cp.async.bulk, completion on an mbarrier) of the strip's
+// windows of S (with its y/z halo), the three face-coefficient arrays, dinv, R, kv and side into a
+// shared-memory ring, kRing - 2 planes ahead of the compute, so no register is held by a load in flight.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+
+constexpr unsigned kRing = 8;    // stages of the shared-memory ring
+constexpr unsigned kAhead = 4;   // loads in flight ahead of a warp's position; the other kRing - kAhead - 1 stages let
+                                 // the warps of a CTA drift apart without blocking the issuer
+
+struct FusedView {
+    const float *xe, *ye, *ze;
+    int ex, ey, ez;
+    int64_t ne;
+    const uint8_t* side;
+    const float *S, *cface, *dinv, *kv, *R;
+    float* G;                   // list contributions only; consumed entries are re-zeroed
+    float inv_n;
+    float* partials;
+};
+
+// shared-memory ring stage (offsets in floats, all multiples of 4 -> 16-byte aligned)
+struct StageLayout {
+    int ezu, oS, oCY, oCZ, oCX, oDI, oR, oKV, oSD, floats;
+};
+__host__ __device__ inline StageLayout stage_layout(int ez) {
+    StageLayout L;
+    L.ezu = (ez + 3) & ~3;
+    L.oS = 0;
+    L.oCY = L.oS + kGradThreads + 2 * L.ezu;
+    L.oCZ = L.oCY + kGradThreads + L.ezu;
+    L.oCX = L.oCZ + kGradThreads + 4;
+    L.oDI = L.oCX + kGradThreads;
+    L.oR = L.oDI + kGradThreads;
+    L.oKV = L.oR + kGradThreads;
+    L.oSD = L.oKV + kGradThreads;
+    L.floats = L.oSD + (kGradThreads + 32) / 4;
+    return L;
+}
+template <class NET>
+static int fused_smem_bytes(int ez) {
+    return grad_smem_bytes<NET>() + 16 + kRing * stage_layout(ez).floats * (int)sizeof(float);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+
+// what lane a < 8 of the issuing warp copies for every plane
+struct CopyDesc {
+    const char* base;   // array base
+    int64_t limit;      // elements readable
+    int lo_off, hi_off; // window [e0 + lo_off, e0 + hi_off) in elements
+    int dst_bytes;      // offset of the window inside a stage
+    int esz;            // element size; 1: the window is widened to 16-element boundaries
+};
+
+// raw shared-window addresses (the generic -> shared conversion is done once per kernel)
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+
+// Every task stages the same number of planes, x0-1 .. x0+xchunk (planes outside the lattice or past the chunk are
+// "empty loads": the barrier completes with zero bytes), so load n <-> (task, plane) is closed-form:
+//   n = k * (xchunk + 2) + j,  task = blockIdx.x + k * gridDim.x,  plane = x0 - 1 + j.
+// Load n is issued by warp n % kWarps when that warp reaches position n - kAhead (lanes 0..7 copy one window each).
+template <class NET>
+__global__ void __launch_bounds__(kGradThreads, 1) node_grad_fused_kernel(FusedView v, Tasks T) {
+    using P = typename NET::P;
+    using M = typename NET::M;
+    constexpr int H = NET::HPW, HP2 = H / 2, NP = NET::NP;
+    constexpr int kRed = ((kGradThreads / 32) * (NP + 1) + 3) & ~3;
+    constexpr unsigned kWarps = kGradThreads / 32;
+    extern __shared__ __align__(16) float dsm[];
+    __shared__ __align__(8) uint64_t bars[2 * kRing];   // [0, kRing): full, [kRing, 2 kRing): empty
+    __shared__ CopyDesc desc[8];
+    float* hs = dsm + threadIdx.x;
+    float* red = dsm + 3 * H * kGradThreads;
+    float* ring = red + kRed;
+    const StageLayout SL = stage_layout(v.ez);
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31, warp = tid >> 5;
+    const int plane = T.plane;
+    const int64_t ne = v.ne;
+    const uint32_t full_a = smem_u32(bars), empty_a = full_a + 8u * kRing;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < (int)kRing; ++s) {
+            mbar_init(&bars[s], 8);               // the 8 issuing lanes arrive (each with its own byte count)
+            mbar_init(&bars[kRing + s], kWarps);  // every warp releases a stage after its last read
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int64_t ne16 = (ne + 15) & ~(int64_t)15;
+        const int G = kGradThreads;
+        desc[0] = {(const char*)v.S, ne, -SL.ezu, G + SL.ezu, SL.oS * 4, 4};
+        desc[1] = {(const char*)(v.cface + ne), ne, -SL.ezu, G, SL.oCY * 4, 4};
+        desc[2] = {(const char*)(v.cface + 2 * ne), ne, -4, G, SL.oCZ * 4, 4};
+        desc[3] = {(const char*)v.cface, ne, 0, G, SL.oCX * 4, 4};
+        desc[4] = {(const char*)v.dinv, ne, 0, G, SL.oDI * 4, 4};
+        desc[5] = {(const char*)v.R, ne, 0, G, SL.oR * 4, 4};
+        desc[6] = {(const char*)v.kv, v.kv ? ne : 0, 0, G, SL.oKV * 4, 4};
+        desc[7] = {(const char*)v.side, ne16, 0, G, SL.oSD * 4, 1};
+    }
+#pragma unroll
+    for (int i = 0; i < 3 * H; ++i) hs[i * kGradThreads] = 0.0f;
+    typename P::AccS acc;
+    acc.zero();
+    float accm[M::NP];
+#pragma unroll
+    for (int i = 0; i < M::NP; ++i) accm[i] = 0.0f;
+    float loss = 0.0f;
+    const bool par = (tid & 1) != 0;
+
+    const unsigned per_task = (unsigned)T.xchunk + 2u;
+    const unsigned my_tasks = blockIdx.x < (unsigned)T.total ? ((unsigned)T.total - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
+    const unsigned n_total = my_tasks * per_task;
+    // issue load n (whole warp, converged)
+    auto issue = [&](unsigned n) {
+        const unsigned st = n % kRing;
+        if (n >= kRing) mbar_wait_a(empty_a + 8u * st, ((n / kRing) + 1u) & 1u);   // every warp released its previous use
+        if (lane < 8) {
+            const unsigned k = n / per_task, j = n - k * per_task;
+            const int task = blockIdx.x + k * gridDim.x;
+            const int mb = task % T.mblocks, xc = task / T.mblocks;
+            const int x0 = xc * T.xchunk, x1 = min(v.ex, x0 + T.xchunk);
+            const int q = x0 - 1 + (int)j;
+            uint32_t bytes = 0u;
+            const CopyDesc d = desc[lane];
+            int64_t lo = 0, l = 0;
+            if (q >= 0 && q <= x1 && q < v.ex) {
+                const int64_t e0 = (int64_t)q * plane + mb * kGradThreads;
+                lo = e0 + d.lo_off;
+                int64_t hi = e0 + d.hi_off;
+                if (d.esz == 1) {
+                    lo &= ~(int64_t)15;
+                    hi = (hi + 15) & ~(int64_t)15;
+                }
+                l = max(lo, (int64_t)0);
+                const int64_t h = min(hi, d.limit);
+                bytes = h > l ? (uint32_t)(h - l) * (uint32_t)d.esz : 0u;
+            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_a + 8u * st), "r"(bytes) : "memory");
+            if (bytes)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(ring + st * SL.floats) + (uint32_t)d.dst_bytes + (uint32_t)((l - lo) * d.esz)),
+                             "l"(d.base + l * d.esz), "r"(bytes), "r"(full_a + 8u * st)
+                             : "memory");
+        }
+        __syncwarp();
+    };
+    __syncthreads();   // barriers and descriptors initialised
+    for (unsigned n = 0; n < kAhead && n < n_total; ++n)
+        if (n % kWarps == warp) issue(n);
+
+    unsigned n_cur = 0;
+    for (int task = blockIdx.x; task < T.total; task += gridDim.x) {
+        const int mb = task % T.mblocks, xc = task / T.mblocks;
+        const int m0 = mb * kGradThreads, x0 = xc * T.xchunk, x1 = min(v.ex, x0 + T.xchunk);
+        const int m_raw = m0 + tid;
+        const bool valid = m_raw < plane;
+        const int m = valid ? m_raw : plane - 1;
+        const int t = m - m0;
+        const int iy = m / v.ez, iz = m - iy * v.ez;
+        const float y = __ldg(v.ye + iy), z = __ldg(v.ze + iz);
+        u64 yz[HP2];
+        P::template first_layer_yz<0>(y, z, yz);
+        // neighbours that fall outside the arrays (first rows of plane 0, last rows of plane ex-1) read as zero
+        const bool lo_y = m < v.ez, hi_y = m >= plane - v.ez, lo_z = m == 0, hi_z = m == plane - 1;
+        float S_prev = 0.0f, cxm = 0.0f;
+        // positions j = 0 .. xchunk of the task (j = xchunk + 1, the plane after the chunk, is only read as "next")
+        for (int j = 0; j <= T.xchunk; ++j, ++n_cur) {
+            {
+                const unsigned ni = n_cur + kAhead;
+                if (ni < n_total && ni % kWarps == warp) issue(ni);
+            }
+            const int q = x0 - 1 + j;
+            const unsigned st = n_cur % kRing;
+            const float* cur = ring + st * SL.floats + t;
+            const bool live = q >= 0 && q < x1;     // the plane exists and belongs to the chunk (or precedes it)
+            if (live) mbar_wait_a(full_a + 8u * st, (n_cur / kRing) & 1u);
+            if (j == 0 || !live) {
+                if (live) {      // the plane before the chunk only feeds the x- neighbour
+                    S_prev = cur[SL.oS + SL.ezu];
+                    cxm = cur[SL.oCX];
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    if (!live) mbar_wait_a(full_a + 8u * st, (n_cur / kRing) & 1u);   // (completes with zero bytes)
+                    mbar_arrive_a(empty_a + 8u * st);
+                    if (j == T.xchunk) {   // short last chunk: the task's final stage has no reader either
+                        const unsigned s1 = (n_cur + 1u) % kRing;
+                        mbar_wait_a(full_a + 8u * s1, ((n_cur + 1u) / kRing) & 1u);
+                        mbar_arrive_a(empty_a + 8u * s1);
+                    }
+                }
+                continue;
+            }
+            const float S0 = cur[SL.oS + SL.ezu];
+            const float cxp = cur[SL.oCX];
+            const unsigned nn = n_cur + 1u, sn = nn % kRing;
+            float S_next = 0.0f;
+            if (q + 1 < v.ex && q + 1 <= x1) {
+                mbar_wait_a(full_a + 8u * sn, (nn / kRing) & 1u);
+                S_next = (ring + sn * SL.floats)[SL.oS + SL.ezu + t];
+            }
+            const bool first = q == 0, last = q == v.ex - 1;
+            const bool ym_ok = !(first && lo_y), yp_ok = !(last && hi_y), zm_ok = !(first && lo_z), zp_ok = !(last && hi_z);
+            const float Sym = ym_ok ? cur[SL.oS + SL.ezu - v.ez] : 0.0f;
+            const float Syp = yp_ok ? cur[SL.oS + SL.ezu + v.ez] : 0.0f;
+            const float Szm = zm_ok ? cur[SL.oS + SL.ezu - 1] : 0.0f;
+            const float Szp = zp_ok ? cur[SL.oS + SL.ezu + 1] : 0.0f;
+            const float cyp = cur[SL.oCY + SL.ezu];
+            const float cym = ym_ok ? cur[SL.oCY + SL.ezu - v.ez] : 0.0f;
+            const float czp = cur[SL.oCZ + 4];
+            const float czm = zm_ok ? cur[SL.oCZ + 3] : 0.0f;
+            const float di = cur[SL.oDI];
+            const float r = valid ? cur[SL.oR] : 0.0f;
+            const float kv = v.kv ? cur[SL.oKV] : 0.0f;
+            const int e15 = (int)(((int64_t)q * plane + m0) & 15);
+            const uint8_t sd = reinterpret_cast<const uint8_t*>(cur - t + SL.oSD)[t + e15];
+            __syncwarp();
+            if (lane == 0) {   // this warp is done with the plane's stage (the next plane's stays for one more position)
+                mbar_arrive_a(empty_a + 8u * st);
+                if (j == T.xchunk) {   // last position of the task: nobody reads the following stage as "current"
+                    mbar_wait_a(full_a + 8u * sn, (nn / kRing) & 1u);
+                    mbar_arrive_a(empty_a + 8u * sn);
+                }
+            }
+            float gd = di > 0.0f ? ((((((cxm + cxp) + cym) + cyp) + czm) + czp) + kv) * S0 : (di < 0.0f ? r : 0.0f);
+            gd = fmaf(-cxm, S_prev, gd);
+            gd = fmaf(-cxp, S_next, gd);
+            gd = fmaf(-cym, Sym, gd);
+            gd = fmaf(-cyp, Syp, gd);
+            gd = fmaf(-czm, Szm, gd);
+            gd = fmaf(-czp, Szp, gd);
+            if (valid && (sd & 4)) {
+                const int64_t e = (int64_t)q * plane + m;
+                gd += v.G[e];
+                v.G[e] = 0.0f;
+            }
+            S_prev = S0;
+            cxm = cxp;
+            const float g = valid ? gd * v.inv_n : 0.0f;
+            const float x = __ldg(v.xe + q);
+            const bool plus = (sd & 1) != 0;
+            loss = fmaf(0.5f * r, r, loss);
+            const bool do_p = plus && g != 0.0f;
+            if (__any_sync(0xffffffffu, do_p)) P::grad_split(x, yz, do_p ? g : 0.0f, acc, par);
+            if (!plus && g != 0.0f) {
+                float a[NET::LMD][NET::HMW];
+                M::template forward<P::NP>(x, y, z, a);
+                M::template backward<P::NP, M::NP, P::NP>(x, y, z, a, g, accm);
+            }
+        }
+        {   // the plane after the chunk was only read as "next": its position is skipped, its issue slot is not
+            const unsigned ni = n_cur + kAhead;
+            if (ni < n_total && ni % kWarps == warp) issue(ni);
+            ++n_cur;
+        }
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const float tj = (j & 1) ? hi32(acc.t[j / 2]) : lo32(acc.t[j / 2]);
+            hs[j * kGradThreads] += tj;
+            hs[(H + j) * kGradThreads] = fmaf(y, tj, hs[(H + j) * kGradThreads]);
+            hs[(2 * H + j) * kGradThreads] = fmaf(z, tj, hs[(2 * H + j) * kGradThreads]);
+        }
+#pragma unroll
+        for (int j = 0; j < HP2; ++j) acc.t[j] = 0ull;
+    }
+    loss *= v.inv_n;
+#pragma unroll
+    for (int i = 0; i <= NP; ++i) {
+        float val;
+        if (i < P::NP) val = P::split_get(acc, i, par, hs, kGradThreads);
+        else if (i < NP) val = accm[i < NP ? i - P::NP : 0];
+        else val = loss;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        if (lane == 0) red[warp * (NP + 1) + i] = val;
+    }
+    __syncthreads();
+    for (int i = tid; i < NP + 1; i += kGradThreads) {
+        float val = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kGradThreads / 32; ++w) val += red[w * (NP + 1) + i];
+        v.partials[(size_t)blockIdx.x * (NP + 1) + i] = val;
+    }
+}
+
+template <class NET>
+static cudaError_t launch_node_grad_fused(int grid, const FusedView& v, const Tasks& T, cudaStream_t st) {
+    static int configured = 0;
+    const int bytes = fused_smem_bytes<NET>(v.ez);
+    if (configured < bytes) {
+        cudaError_t e = cudaFuncSetAttribute(node_grad_fused_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        configured = bytes;
+    }
+    node_grad_fused_kernel<NET><<<grid, kGradThreads, bytes, st>>>(v, T);
     return cudaSuccess;
 }
 
@@ -1400,8 +1744,14 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
         }
         if (s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
     }
+    const bool fused = s.faces && s.S && !s.nl;
     if (stages & NBM_STAGE_ADJOINT) {
-        if (s.faces) {
+        if (fused) {
+            // the dense adjoint stencil runs inside the gradient kernel; G only collects the list contributions.
+            // A profiling run that stops before the gradient stage would leave them behind: clear first.
+            if (!(stages & NBM_STAGE_GRAD))
+                cudaMemsetAsync(s.G, 0, sizeof(float) * (size_t)s.ex * s.ey * s.ez, st);
+        } else if (s.faces) {
             dim3 g((s.ey * s.ez / 4 + kThreads - 1) / kThreads, s.ex);
             adjoint_faces4_kernel<<<g, kThreads, 0, st>>>(s);
         } else if (vec4) {
@@ -1423,7 +1773,16 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     const Tasks Tg = make_tasks(s.ex, s.ey, s.ez, xchunk_g, kGradThreads);
     int gridC = min(Tg.total, min(kPartialRows, sms));
     if (gridC > s.n_partial_rows) gridC = s.n_partial_rows;
-    if (stages & NBM_STAGE_GRAD) {
+    if ((stages & NBM_STAGE_GRAD) && fused) {
+        FusedView f;
+        f.xe = s.xe; f.ye = s.ye; f.ze = s.ze;
+        f.ex = s.ex; f.ey = s.ey; f.ez = s.ez;
+        f.ne = (int64_t)s.ex * s.ey * s.ez;
+        f.side = s.side; f.S = s.S; f.cface = s.cface; f.dinv = s.dinv; f.kv = s.kv; f.R = s.R; f.G = s.G;
+        f.inv_n = s.inv_n_points; f.partials = s.partials;
+        cudaError_t e = launch_node_grad_fused<NET>(gridC, f, Tg, st);
+        if (e != cudaSuccess) return cuda_check(e, "node_grad_fused attribute");
+    } else if (stages & NBM_STAGE_GRAD) {
         cudaError_t e = launch_node_grad<NET, false>(dim3(gridC), view_of(s), Tg, st);
         if (e != cudaSuccess) return cuda_check(e, "node_grad attribute");
     }

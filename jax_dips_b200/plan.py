@@ -164,7 +164,8 @@ class CrossedSites:
         st = cabi.stream_ptr()
         dx, dy, dz = d
         self.flag = torch.empty(n_sites, dtype=torch.int8, device=dev)
-        self.side = torch.empty(n_sites, dtype=torch.uint8, device=dev)
+        # (16 bytes of slack: the fused gradient kernel stages `side` with 16-byte bulk copies)
+        self.side = torch.zeros(n_sites + 32, dtype=torch.uint8, device=dev)[:n_sites]
         cabi.check(L.nbm_classify_f32(C.byref(lvl.struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.flag),
                                       cabi.ptr(self.side), st), "nbm_classify_f32")
         # compaction
@@ -232,10 +233,14 @@ class SharedPlan:
 
     def __init__(self, lvl: LevelSet, tr_gstate, xa: int, xb: int, fns, net: NetShape,
                  nonlinear_m: Nonlinear, nonlinear_p: Nonlinear, n_mean: Optional[int] = None, device=None,
-                 faces: Optional[bool] = None):
+                 faces: Optional[bool] = None, fused: Optional[bool] = None):
         """`faces`: store one coefficient per cell FACE + 1/diag (16 B/node) instead of the 7 row weights
         (28 B/node); irregular rows move into the list.  Default: on whenever the 16-byte stencil kernels
-        apply (even Ny, Nz)."""
+        apply (even Ny, Nz).
+        `fused`: evaluate the dense adjoint stencil inside the gradient kernel from TMA-staged row tables
+        instead of a separate pass (needs faces and no nonlinear operator).  Default OFF: measured on B200 at
+        256^3 the fused kernel takes 516-585 us against 370 + 122 us for gradient + adjoint kernels (the
+        shared ring couples the 12 warps of a CTA to the slowest one)."""
         dev = torch.device(device if device is not None else lvl.device)
         self.device, self.net, self.lvl = dev, net, lvl
         L = cabi.lib()
@@ -291,6 +296,11 @@ class SharedPlan:
             use_kv = self.faces and bool(((k_m != 0) | (k_p != 0)).any().item())
             self.kv = torch.zeros(ne, dtype=torch.float32, device=dev) if use_kv else None
             self.rhs = torch.zeros(ne, dtype=torch.float32, device=dev)
+            can_fuse = self.faces and not use_nl
+            if fused and not can_fuse:
+                raise ValueError("fused=True needs the faces table and no nonlinear operator")
+            self.fused = False if fused is None else bool(fused)
+            self.S = torch.zeros(ne, dtype=torch.float32, device=dev) if self.fused else None
             self.nl = torch.zeros(2 * ne, dtype=torch.float32, device=dev) if use_nl else None
             irr = torch.full((ne,), -1, dtype=torch.int32, device=dev)
             cap = min(np_, 7 * cs.n) + 1
@@ -346,6 +356,22 @@ class SharedPlan:
             self.irr_nlw = irr_nlw[:max(n_irr, 1)].clone()
             self.irr = irr
             del mu_m_faces, mu_p_faces, k_m, k_p, f_m, f_p, g_dir
+            if self.fused:
+                # bit 2 of `side`: the node can receive a contribution from the lists (the 27-cube of a crossed
+                # site, the 7 stencil sites of an irregular row); only those read (and re-zero) G in the step
+                sxy, sy = ey * ez, ez
+                tg = []
+                if cs.n > 0:
+                    o27 = torch.tensor([a * sxy + b * sy + c for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)],
+                                       dtype=torch.int64, device=dev)
+                    tg.append((cs.idx[:, None] + o27[None, :]).reshape(-1))
+                if n_irr > 0:
+                    o7 = torch.tensor([0, -sxy, sxy, -sy, sy, -1, 1], dtype=torch.int64, device=dev)
+                    tg.append((self.irr_point[:n_irr, None] + o7[None, :]).reshape(-1))
+                if tg:
+                    nodes = torch.unique(torch.cat(tg))
+                    assert int(nodes.min()) >= 0 and int(nodes.max()) < ne
+                    cs.side[nodes] = cs.side[nodes] | 4
 
             # ---- work buffers + the step descriptor
             P = net.n_params
@@ -375,6 +401,7 @@ class SharedPlan:
             s.faces = 1 if self.faces else 0
             s.cface, s.dinv, s.kv = cabi.ptr(self.cface), cabi.ptr(self.dinv), cabi.ptr(self.kv)
             s.irr_wU, s.irr_rhs = cabi.ptr(self.irr_wU), cabi.ptr(self.irr_rhs)
+            s.S = cabi.ptr(self.S)
             self.step = s
             self.xa, self.xb = xa, xb
             # the regression/cut-cell scratch is not needed by the step

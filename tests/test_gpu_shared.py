@@ -32,13 +32,13 @@ def fns_of(problem):
                              problem.nonlinear_op_m, problem.nonlinear_op_p)
 
 
-def build(problem, n_train, n_lvl, interp="trilinear", net=None, xa=0, xb=None, faces=None):
+def build(problem, n_train, n_lvl, interp="trilinear", net=None, xa=0, xb=None, faces=None, fused=None):
     tr, lv, phi_grid, oprob = util.make_case(problem, n_train, n_lvl, interp, torch.float64, net=net)
     lvl = nplan.LevelSet(lv, phi_grid, interp=interp, perturb_eps=1e-10, device=DEV)
     shape = nplan.NetShape(oprob.shape.Lp, oprob.shape.Hp, oprob.shape.Lm, oprob.shape.Hm)
     pl = nplan.SharedPlan(lvl, tr, xa, xb if xb is not None else tr.shape()[0], fns_of(problem), shape,
                           nplan.Nonlinear.coerce(problem.nonlinear_op_m),
-                          nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=DEV, faces=faces)
+                          nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=DEV, faces=faces, fused=fused)
     return tr, lv, lvl, oprob, pl, shape
 
 
@@ -96,13 +96,17 @@ def test_classification_and_cut_cells(name):
 
 # n = 15 gives an odd (y,z) plane: the scalar stencil kernels; the others take the 16-byte vector path.
 # faces: one coefficient per cell face + 1/diag (the default on even grids) against the 7-weight row table.
-@pytest.mark.parametrize("name,n,nl,faces", [("sphere", 16, 32, True), ("star", 16, 32, True), ("no_jump", 12, 16, True),
-                                             ("sphere", 24, 24, True), ("star", 15, 32, False),
-                                             ("sphere", 16, 32, False), ("star", 16, 32, False)])
-def test_rows_loss_and_gradient(name, n, nl, faces):
+# fused: the dense adjoint stencil evaluated inside the gradient kernel from TMA-staged tables (opt-in)
+# against the separate adjoint pass (default).
+@pytest.mark.parametrize("name,n,nl,faces,fused", [
+    ("sphere", 16, 32, True, True), ("star", 16, 32, True, True), ("no_jump", 12, 16, True, False),
+    ("sphere", 24, 24, True, False), ("star", 32, 32, True, True), ("star", 15, 32, False, False),
+    ("sphere", 16, 32, True, False), ("star", 16, 32, True, False),
+    ("sphere", 16, 32, False, False), ("star", 16, 32, False, False)])
+def test_rows_loss_and_gradient(name, n, nl, faces, fused):
     P = problems.PROBLEMS[name]()
-    tr, lv, lvl, oprob, pl, shape = build(P, n, nl, faces=faces)
-    assert pl.faces == faces
+    tr, lv, lvl, oprob, pl, shape = build(P, n, nl, faces=faces, fused=fused)
+    assert pl.faces == faces and pl.fused == fused
     dt = torch.float64
     params = O.init_params(oprob.shape, seed=7, dtype=dt)
     d = [tr.dx.to(dt), tr.dy.to(dt), tr.dz.to(dt)]
@@ -123,6 +127,12 @@ def test_rows_loss_and_gradient(name, n, nl, faces):
     # per-coordinate check on the large entries too
     big = grad_o.abs() > 1e-2 * grad_o.abs().max()
     assert ((grad_k.double()[big] - grad_o[big]).abs() / grad_o[big].abs()).max() < 10 * TOL_LOSS
+    # a second launch gives the same answer (the fused kernel re-zeroes the list contributions it consumed;
+    # the atomics on the lists are order-dependent in the last bits only)
+    with torch.cuda.device(DEV):
+        lg2 = pl.loss_grad_launch().clone()
+        torch.cuda.synchronize()
+    assert util.rel_inf(lg2[:-1].cpu(), grad_k) < 1e-5
 
 
 def test_anisotropic_grid_and_interface_at_the_box_boundary():
