@@ -192,6 +192,10 @@ typedef struct {
     float* irr_wU;                   /* [cap][7] (faces mode) weight on u(site k) */
     float* irr_rhs;                  /* [cap]    (faces mode) */
     float* kv;                       /* [n_out]  (faces mode) or NULL */
+    /* learned preconditioner input (nn/preconditioner.py; discretization.py:337-339): the 26-vector coeffs_ of
+     * every point, [mu A/d (imh-,imh+,iph-,iph+,jmh-,...,kph+), V-, V+, A (same order)]
+     * (geometric_integrations_per_point.py:873-903, :964-996), SoA [26][n_out]; NULL = not wanted */
+    float* coef26;
 } nbm_assemble_t;
 
 int nbm_assemble_f32(const nbm_assemble_t* a, nbm_stream_t stream);
@@ -244,7 +248,23 @@ typedef struct {
      * contribution carry bit 2 (value 4) in `side`, and `side` must be readable up to the next multiple of 16
      * bytes past ex*ey*ez. */
     float* S;                        /* [ne] or NULL */
+    /* learned preconditioner P = 0.5 + pc_scale * sigmoid(MLP(coeffs_)) (nn/preconditioner.py:10-35), tanh MLP
+     * 26 -> pc_d1 -> pc_d2 -> 1, multiplying lhs/diag and rhs/diag of every row (discretization.py:418-419).
+     * pc_params (device): Dense_0.kernel (26 x d1 row-major), Dense_0.bias, Dense_1.kernel (d1 x d2),
+     * Dense_1.bias, Dense_2.kernel (d2), Dense_2.bias; normally the tail of the flat parameter vector.
+     * With coef26 != NULL the gradient has net + pc entries: every partial row is `row_stride` floats
+     * (>= n_net + n_pc + 1, loss in the last used column n_net + n_pc), rows [0, n_sm) are written by the
+     * network-gradient kernel, the following n_pc_rows by the preconditioner kernel; the buffer must be zero
+     * on first use.  loss_grad has n_net + n_pc + 1 entries.  Compiled: (d1, d2) = (8, 4). */
+    const float* coef26;             /* [26][ne] or NULL */
+    const float* pc_params;
+    int pc_d1, pc_d2;
+    float pc_scale;
+    int n_pc_rows;                   /* partial rows reserved for the preconditioner kernel (>= 1) */
 } nbm_shared_step_t;
+
+/* number of preconditioner parameters for hidden widths (d1, d2) */
+int nbm_precond_num_params(int d1, int d2);
 
 /* stages of the shared-evaluation step, in launch order */
 enum nbm_stage {

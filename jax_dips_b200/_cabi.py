@@ -47,7 +47,7 @@ class Assemble(C.Structure):
                 ("irr_capacity", C.c_int64), ("irr_count", c_fp), ("irr_point", c_fp),
                 ("irr_wE", c_fp), ("irr_c", c_fp), ("irr_nl", c_fp), ("irr_nlw", c_fp),
                 ("faces", C.c_int), ("cface", c_fp), ("dinv", c_fp), ("irr_wU", c_fp), ("irr_rhs", c_fp),
-                ("kv", c_fp)]
+                ("kv", c_fp), ("coef26", c_fp)]
 
 
 class Net(C.Structure):
@@ -67,7 +67,8 @@ class SharedStep(C.Structure):
                 ("U", c_fp), ("R", c_fp), ("G", c_fp), ("E", c_fp), ("gE", c_fp),
                 ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp), ("stages", C.c_int),
                 ("faces", C.c_int), ("cface", c_fp), ("dinv", c_fp), ("irr_wU", c_fp), ("irr_rhs", c_fp),
-                ("kv", c_fp), ("S", c_fp)]
+                ("kv", c_fp), ("S", c_fp), ("coef26", c_fp), ("pc_params", c_fp), ("pc_d1", C.c_int), ("pc_d2", C.c_int),
+                ("pc_scale", c_f), ("n_pc_rows", C.c_int)]
 
 
 class PointsStep(C.Structure):
@@ -108,6 +109,7 @@ SYMBOLS = {
     "nbm_net_num_params": (C.c_int, [_P(Net)]),
     "nbm_upload_params": (C.c_int, [_P(Net), c_fp, c_fp]),
     "nbm_step_partial_rows": (C.c_int, []),
+    "nbm_precond_num_params": (C.c_int, [C.c_int, C.c_int]),
     "nbm_ffma_probe_f32": (C.c_int, [C.c_int, c_fp, _P(C.c_double), c_fp]),
     "nbm_loss_grad_shared_f32": (C.c_int, [_P(SharedStep), c_fp]),
     "nbm_loss_grad_points_f32": (C.c_int, [_P(PointsStep), c_fp]),

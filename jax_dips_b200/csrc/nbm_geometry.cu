@@ -492,14 +492,15 @@ __global__ void assemble_kernel(nbm_assemble_t a) {
     bool bnd = fabsf(x - a.bounds[0]) < 1e-6f * dx || fabsf(x - a.bounds[1]) < 1e-6f * dx ||
                fabsf(y - a.bounds[2]) < 1e-6f * dy || fabsf(y - a.bounds[3]) < 1e-6f * dy ||
                fabsf(z - a.bounds[4]) < 1e-6f * dz || fabsf(z - a.bounds[5]) < 1e-6f * dz;
-    if (bnd && !a.faces) {
+    const bool bnd_early = bnd && !a.faces;   // row is u = g; only the preconditioner input is still needed
+    if (bnd_early) {
         // lhs = u*vol, diag = vol, rhs = g*vol (:389-393, :410-411)
         a.w[out] = 1.0f;
         for (int s = 1; s < 7; ++s) a.w[s * a.n_out + out] = 0.0f;
         a.rhs[out] = a.g_dir[p];
         if (a.nl) { a.nl[out] = 0.0f; a.nl[a.n_out + out] = 0.0f; }
         a.irr[out] = -1;
-        return;
+        if (!a.coef26) return;
     }
     // site ids of the 7 stencil slots
     int64_t sid[7];
@@ -533,6 +534,19 @@ __global__ void assemble_kernel(nbm_assemble_t a) {
     }
     sum_m = cm[0] + cm[1] + cm[2] + cm[3] + cm[4] + cm[5];
     sum_p = cp[0] + cp[1] + cp[2] + cp[3] + cp[4] + cp[5];
+    if (a.coef26) {
+        // coeffs_ of the point, the input of the learned preconditioner (discretization.py:337-339; evaluated
+        // at box-boundary points too)
+        for (int f = 0; f < 6; ++f) {
+            a.coef26[(int64_t)(2 * f) * a.n_out + out] = cm[f];
+            a.coef26[(int64_t)(2 * f + 1) * a.n_out + out] = cp[f];
+            a.coef26[(int64_t)(14 + 2 * f) * a.n_out + out] = am[f];
+            a.coef26[(int64_t)(15 + 2 * f) * a.n_out + out] = ap[f];
+        }
+        a.coef26[(int64_t)12 * a.n_out + out] = Vm;
+        a.coef26[(int64_t)13 * a.n_out + out] = Vp;
+    }
+    if (bnd_early) return;
     float km = a.k_m[p], kp = a.k_p[p];
     float diag = kp * Vp + km * Vm + sum_m + sum_p;
     float rhs = a.f_m[p] * Vm + a.f_p[p] * Vp + bg;

@@ -595,6 +595,7 @@ struct NodeView {
     float inv_n;
     float* partials;
     int row0;
+    int row_stride, loss_col;    // 0: rows are NP + 1 floats with the loss last
 };
 
 static NodeView view_of(const nbm_shared_step_t& s) {
@@ -606,6 +607,7 @@ static NodeView view_of(const nbm_shared_step_t& s) {
     v.rep_nodes = v.hi;
     v.side = s.side; v.U = s.U; v.G = s.G; v.R = s.R;
     v.inv_n = s.inv_n_points; v.partials = s.partials; v.row0 = 0;
+    v.row_stride = 0; v.loss_col = 0;
     return v;
 }
 
@@ -1098,7 +1100,7 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
         // software pipeline: the loads of plane ix+1 are in flight while plane ix is computed
         int64_t e = (int64_t)x0 * T.plane + m;
         bool in_n = valid && (!GENERAL || (e >= v.lo && e < v.hi));
-        float g_n = in_n ? __ldg(G + e) : 0.0f, r_n = (GENERAL || !valid) ? 0.0f : __ldg(R + e), x_n = __ldg(xe + x0);
+        float g_n = in_n ? __ldg(G + e) : 0.0f, r_n = (GENERAL || !valid || !R) ? 0.0f : __ldg(R + e), x_n = __ldg(xe + x0);
         uint8_t sd_n = __ldg(side + e);
         for (int ix = x0; ix < x1; ++ix) {
             const float g = g_n * v.inv_n, r = r_n, x = x_n;
@@ -1107,7 +1109,7 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
                 e += T.plane;
                 in_n = valid && (!GENERAL || (e >= v.lo && e < v.hi));
                 g_n = in_n ? __ldg(G + e) : 0.0f;
-                if (!GENERAL) r_n = valid ? __ldg(R + e) : 0.0f;
+                if (!GENERAL && R) r_n = valid ? __ldg(R + e) : 0.0f;
                 sd_n = __ldg(side + e);
                 x_n = __ldg(xe + ix + 1);
             }
@@ -1145,12 +1147,13 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
         if (lane == 0) red[warp * (NP + 1) + i] = val;
     }
     __syncthreads();
-    float* partials = v.partials + (size_t)(v.row0 + rep * gridDim.x) * (NP + 1);
+    const int stride = v.row_stride ? v.row_stride : NP + 1, loss_col = v.row_stride ? v.loss_col : NP;
+    float* partials = v.partials + (size_t)(v.row0 + rep * gridDim.x) * stride;
     for (int i = threadIdx.x; i < NP + 1; i += kGradThreads) {
         float val = 0.0f;
 #pragma unroll
         for (int w = 0; w < kGradThreads / 32; ++w) val += red[w * (NP + 1) + i];
-        partials[(size_t)blockIdx.x * (NP + 1) + i] = val;
+        partials[(size_t)blockIdx.x * stride + (i < NP ? i : loss_col)] = val;
     }
 }
 
@@ -1511,6 +1514,161 @@ static cudaError_t launch_node_grad_fused(int grid, const FusedView& v, const Ta
     return cudaSuccess;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Learned preconditioner (nn/preconditioner.py:10-35; discretization.py:339, 418-419): every row is scaled by
+// P = 0.5 + scale * sigmoid(MLP(coeffs_)), a tanh MLP 26 -> D1 -> D2 -> 1 on the point's 26 cell coefficients:
+//   loss = mean 0.5 (P r)^2,  d loss/d r = P^2 r / n,  d loss/d theta_P = sum_p (P r^2 / n) dP/d theta_P.
+// One pass over the lattice between the residual and the adjoint stage: it reads the un-preconditioned
+// residual r = R[e], accumulates the loss and the preconditioner gradient, and overwrites R[e] <- P^2 r, which is
+// what the adjoint/gradient stages then propagate.  The 26 x D1 outer product is accumulated co-operatively:
+// a warp stages its 32 points' inputs and first-layer deltas in shared memory and lane k < 26 owns input row k.
+// ---------------------------------------------------------------------------------------------
+template <int D1, int D2>
+struct PrecondNet {
+    static constexpr int NIN = 26;
+    static constexpr int oW1 = 0, ob1 = NIN * D1, oW2 = ob1 + D1, ob2 = oW2 + D1 * D2, oW3 = ob2 + D2, ob3 = oW3 + D2;
+    static constexpr int NP = ob3 + 1;
+};
+
+__device__ __forceinline__ float tanh_acc(float x) { return tanh_nbm(x); }
+
+template <int D1, int D2>
+__global__ void __launch_bounds__(kThreads) precond_kernel(const float* __restrict__ coef26, float* __restrict__ R,
+                                                           int64_t ne, const float* __restrict__ params, float scale,
+                                                           float inv_n, float* __restrict__ partials, int row_stride,
+                                                           int col0, int loss_col) {
+    using PN = PrecondNet<D1, D2>;
+    constexpr int NIN = PN::NIN, NPc = PN::NP, kWarps = kThreads / 32;
+    constexpr int CS = NIN + 1, DS = D1 + 1;   // padded strides: conflict-free column reads
+    __shared__ float sP[NPc];
+    __shared__ float sc[kWarps][32 * CS];
+    __shared__ float sd[kWarps][32 * DS];
+    __shared__ float sred[kWarps][NPc + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < NPc; i += kThreads) sP[i] = params[i];
+    __syncthreads();
+    float aW1[D1];   // lane k < 26: d loss / d W1[k][:]
+    float ab1[D1], aW2[D1][D2], ab2[D2], aW3[D2], ab3 = 0.0f, loss = 0.0f;
+#pragma unroll
+    for (int j = 0; j < D1; ++j) {
+        aW1[j] = 0.0f;
+        ab1[j] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < D2; ++q) aW2[j][q] = 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < D2; ++q) { ab2[q] = 0.0f; aW3[q] = 0.0f; }
+    for (int64_t base = (int64_t)blockIdx.x * kThreads; base < ne; base += (int64_t)gridDim.x * kThreads) {
+        const int64_t e = base + tid;
+        const bool valid = e < ne;
+        const float r = valid ? R[e] : 0.0f;
+        float c[NIN];
+#pragma unroll
+        for (int k = 0; k < NIN; ++k) c[k] = valid ? __ldcs(coef26 + (int64_t)k * ne + e) : 0.0f;
+        // forward
+        float h1[D1], h2[D2];
+#pragma unroll
+        for (int j = 0; j < D1; ++j) {
+            float s = sP[PN::ob1 + j];
+#pragma unroll
+            for (int k = 0; k < NIN; ++k) s = fmaf(c[k], sP[PN::oW1 + k * D1 + j], s);
+            h1[j] = tanh_acc(s);
+        }
+#pragma unroll
+        for (int q = 0; q < D2; ++q) {
+            float s = sP[PN::ob2 + q];
+#pragma unroll
+            for (int j = 0; j < D1; ++j) s = fmaf(h1[j], sP[PN::oW2 + j * D2 + q], s);
+            h2[q] = tanh_acc(s);
+        }
+        float o = sP[PN::ob3];
+#pragma unroll
+        for (int q = 0; q < D2; ++q) o = fmaf(h2[q], sP[PN::oW3 + q], o);
+        const float sg = 1.0f / (1.0f + __expf(-o));
+        const float Pc = fmaf(scale, sg, 0.5f);
+        const float pr = Pc * r;
+        loss = fmaf(0.5f * pr, pr, loss);
+        if (valid) R[e] = Pc * pr;                       // d loss / d r (times n)
+        // backward: d loss/d P (times n) = P r^2
+        const float dO = (pr * r) * inv_n * scale * sg * (1.0f - sg);
+        ab3 += dO;
+        float d2[D2], d1[D1];
+#pragma unroll
+        for (int q = 0; q < D2; ++q) {
+            aW3[q] = fmaf(dO, h2[q], aW3[q]);
+            d2[q] = dO * sP[PN::oW3 + q] * fmaf(-h2[q], h2[q], 1.0f);
+            ab2[q] += d2[q];
+        }
+#pragma unroll
+        for (int j = 0; j < D1; ++j) {
+            float s = 0.0f;
+#pragma unroll
+            for (int q = 0; q < D2; ++q) {
+                aW2[j][q] = fmaf(h1[j], d2[q], aW2[j][q]);
+                s = fmaf(sP[PN::oW2 + j * D2 + q], d2[q], s);
+            }
+            d1[j] = s * fmaf(-h1[j], h1[j], 1.0f);
+            ab1[j] += d1[j];
+        }
+        // co-operative outer product dW1[k][j] += c_p[k] d1_p[j] over the warp's 32 points
+        if (__any_sync(0xffffffffu, r != 0.0f)) {
+#pragma unroll
+            for (int k = 0; k < NIN; ++k) sc[warp][lane * CS + k] = c[k];
+#pragma unroll
+            for (int j = 0; j < D1; ++j) sd[warp][lane * DS + j] = d1[j];
+            __syncwarp();
+            if (lane < NIN) {
+                for (int pnt = 0; pnt < 32; ++pnt) {
+                    const float ck = sc[warp][pnt * CS + lane];
+#pragma unroll
+                    for (int j = 0; j < D1; ++j) aW1[j] = fmaf(ck, sd[warp][pnt * DS + j], aW1[j]);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    // block reduction -> partials[row][col0 + i], loss -> partials[row][loss_col]
+#pragma unroll
+    for (int j = 0; j < D1; ++j)
+        if (lane < NIN) sred[warp][PN::oW1 + lane * D1 + j] = aW1[j];
+    auto wsum = [&](float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+#pragma unroll
+    for (int j = 0; j < D1; ++j) {
+        float v = wsum(ab1[j]);
+        if (lane == 0) sred[warp][PN::ob1 + j] = v;
+#pragma unroll
+        for (int q = 0; q < D2; ++q) {
+            v = wsum(aW2[j][q]);
+            if (lane == 0) sred[warp][PN::oW2 + j * D2 + q] = v;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < D2; ++q) {
+        float v = wsum(ab2[q]);
+        if (lane == 0) sred[warp][PN::ob2 + q] = v;
+        v = wsum(aW3[q]);
+        if (lane == 0) sred[warp][PN::oW3 + q] = v;
+    }
+    {
+        float v = wsum(ab3);
+        if (lane == 0) sred[warp][PN::ob3] = v;
+        v = wsum(loss);
+        if (lane == 0) sred[warp][NPc] = v * inv_n;
+    }
+    __syncthreads();
+    float* row = partials + (size_t)blockIdx.x * row_stride;
+    for (int i = tid; i <= NPc; i += kThreads) {
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) v += sred[w][i];
+        row[i < NPc ? col0 + i : loss_col] = v;
+    }
+}
+
 // K4a: deterministic sum of the per-CTA partial rows
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int rows, int np1, float* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1725,6 +1883,19 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     const bool vec4 = ((s.ey * s.ez) % 4 == 0) && (s.ez % 2 == 0) &&
                       ((((uintptr_t)s.w | (uintptr_t)s.rhs | (uintptr_t)s.U | (uintptr_t)s.R | (uintptr_t)s.G |
                          (uintptr_t)s.nl) & 15) == 0);
+    // the gradient kernel runs one 384-thread CTA per SM: its own strips, x chunks sized for >= 2 tasks per CTA
+    int xchunk_g = 16;
+    {
+        int mblocks = (s.ey * s.ez + kGradThreads - 1) / kGradThreads;
+        while (xchunk_g > 2 && (int64_t)mblocks * ((s.ex + xchunk_g - 1) / xchunk_g) < 2 * (int64_t)sms) xchunk_g >>= 1;
+    }
+    const Tasks Tg = make_tasks(s.ex, s.ey, s.ez, xchunk_g, kGradThreads);
+    const bool pc = s.coef26 != nullptr;
+    const int n_pc = pc ? PrecondNet<8, 4>::NP : 0;
+    const int pc_stride = NET::NP + n_pc + 1;
+    const int gridP = pc ? min(s.n_pc_rows, 2 * sms) : 0;
+    int gridC = min(Tg.total, min(kPartialRows, sms));
+    if (gridC > s.n_partial_rows - gridP) gridC = s.n_partial_rows - gridP;
     if (stages & NBM_STAGE_FWD) {
         int gridA = min(T.total, sms * 8);
         fwd_nodes_kernel<NET, false><<<gridA, kThreads, 0, st>>>(view_of(s), T);
@@ -1743,8 +1914,15 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
             residual_kernel<<<g, kThreads, 0, st>>>(s);
         }
         if (s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
+        if (pc) {
+            // rows [gridC, gridC + gridP) of the partials: preconditioner gradient + the loss
+            precond_kernel<8, 4><<<gridP, kThreads, 0, st>>>(s.coef26, s.R, (int64_t)s.ex * s.ey * s.ez, s.pc_params,
+                                                             s.pc_scale, s.inv_n_points,
+                                                             s.partials + (size_t)gridC * pc_stride, pc_stride, NET::NP,
+                                                             NET::NP + n_pc);
+        }
     }
-    const bool fused = s.faces && s.S && !s.nl;
+    const bool fused = s.faces && s.S && !s.nl && !pc;
     if (stages & NBM_STAGE_ADJOINT) {
         if (fused) {
             // the dense adjoint stencil runs inside the gradient kernel; G only collects the list contributions.
@@ -1764,15 +1942,6 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
         if (s.n_irr > 0) irregular_bwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
         if (s.n_crossed > 0) extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, st>>>(s);
     }
-    // the gradient kernel runs one 384-thread CTA per SM: its own strips, x chunks sized for >= 2 tasks per CTA
-    int xchunk_g = 16;
-    {
-        int mblocks = (s.ey * s.ez + kGradThreads - 1) / kGradThreads;
-        while (xchunk_g > 2 && (int64_t)mblocks * ((s.ex + xchunk_g - 1) / xchunk_g) < 2 * (int64_t)sms) xchunk_g >>= 1;
-    }
-    const Tasks Tg = make_tasks(s.ex, s.ey, s.ez, xchunk_g, kGradThreads);
-    int gridC = min(Tg.total, min(kPartialRows, sms));
-    if (gridC > s.n_partial_rows) gridC = s.n_partial_rows;
     if ((stages & NBM_STAGE_GRAD) && fused) {
         FusedView f;
         f.xe = s.xe; f.ye = s.ye; f.ze = s.ze;
@@ -1783,11 +1952,17 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
         cudaError_t e = launch_node_grad_fused<NET>(gridC, f, Tg, st);
         if (e != cudaSuccess) return cuda_check(e, "node_grad_fused attribute");
     } else if (stages & NBM_STAGE_GRAD) {
-        cudaError_t e = launch_node_grad<NET, false>(dim3(gridC), view_of(s), Tg, st);
+        NodeView nv = view_of(s);
+        if (pc) {   // the loss comes from the preconditioner kernel; rows carry the preconditioner's columns too
+            nv.R = nullptr;
+            nv.row_stride = pc_stride;
+            nv.loss_col = NET::NP + n_pc;
+        }
+        cudaError_t e = launch_node_grad<NET, false>(dim3(gridC), nv, Tg, st);
         if (e != cudaSuccess) return cuda_check(e, "node_grad attribute");
     }
     if (stages & NBM_STAGE_REDUCE)
-        reduce_partials_kernel<<<(NET::NP + 1 + 127) / 128, 128, 0, st>>>(s.partials, gridC, NET::NP + 1, s.loss_grad);
+        reduce_partials_kernel<<<(pc_stride + 127) / 128, 128, 0, st>>>(s.partials, gridC + gridP, pc_stride, s.loss_grad);
     return cuda_check(cudaGetLastError(), "shared step launch");
 }
 
@@ -2023,7 +2198,7 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
                                     kThreads, 0, st>>>(a);
     fwd_nodes_kernel<NET, true><<<dim3(gridF, 7), kThreads, 0, st>>>(v, T);
     points_rows_kernel<<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, 7 * gridG, np1);
-    v.row0 = 0;
+    v.row0 = 0; v.row_stride = 0; v.loss_col = 0;
     {
         cudaError_t e = launch_node_grad<NET, true>(dim3(gridG, 7), v, Tg, st);
         if (e != cudaSuccess) return cuda_check(e, "node_grad attribute");
@@ -2077,6 +2252,7 @@ int nbm_upload_params(const nbm_net_t* net, const float* params, nbm_stream_t st
 }
 
 int nbm_step_partial_rows(void) { return kPartialRows; }
+int nbm_precond_num_params(int d1, int d2) { return 26 * d1 + d1 + d1 * d2 + d2 + d2 + 1; }
 
 int nbm_ffma_probe_f32(int iters, float* out, double* flops_host, nbm_stream_t stream) {
     NBM_REQUIRE(out && iters > 0, "bad arguments");
@@ -2099,6 +2275,15 @@ int nbm_loss_grad_shared_f32(const nbm_shared_step_t* s, nbm_stream_t stream) {
                     "faces mode needs plane % 4 == 0, even ez and 16-byte aligned arrays");
     } else {
         NBM_REQUIRE(s->w, "null tables");
+    }
+    if (s->coef26) {
+        NBM_REQUIRE(s->pc_params, "null preconditioner parameters");
+        NBM_REQUIRE(s->n_pc_rows >= 1 && s->n_partial_rows > s->n_pc_rows, "no partial rows for the preconditioner");
+        NBM_REQUIRE(!s->S, "the fused adjoint path does not take a preconditioner");
+        if (s->pc_d1 != 8 || s->pc_d2 != 4) {
+            set_error("preconditioner widths (%d, %d) are outside the compiled kernel set ((8, 4))", s->pc_d1, s->pc_d2);
+            return NBM_ERR_UNSUPPORTED;
+        }
     }
     NBM_REQUIRE(s->ex >= 3 && s->ey >= 3 && s->ez >= 3, "lattice too small");
     NBM_REQUIRE(s->U && s->R && s->G && s->partials && s->loss_grad, "null work buffers");

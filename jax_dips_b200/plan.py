@@ -90,6 +90,36 @@ class NetShape:
     def n_params(self): return self.n_p + self.n_m
 
 
+class PrecondShape:
+    """model_dict["preconditioner"] (examples/benchmark_LPBE/conf/lpbe.yaml:62-67; nn/preconditioner.py:10-35):
+    tanh MLP 26 -> layer_widths -> 1 on the point's 26 cell coefficients, P = 0.5 + scaling_coeff * sigmoid(.).
+    Flat parameter order (after the network's): Dense_0.kernel (in,out) row-major, Dense_0.bias, Dense_1..."""
+    N_IN = 26
+
+    def __init__(self, layer_widths=(8, 4), scaling_coeff: float = 1.0):
+        self.widths, self.scale = tuple(int(d) for d in layer_widths), float(scaling_coeff)
+        if len(self.widths) != 2:
+            raise NotImplementedError("the preconditioner kernel is compiled for two hidden layers (lpbe.yaml: [8, 4])")
+
+    @staticmethod
+    def from_model_dict(model_dict: dict) -> Optional["PrecondShape"]:
+        pc = model_dict.get("preconditioner") or {}
+        if not pc.get("enable", False):
+            return None
+        return PrecondShape(pc.get("layer_widths", (8, 4)), pc.get("scaling_coeff", 1.0))
+
+    @property
+    def n_params(self) -> int:
+        return int(cabi.lib().nbm_precond_num_params(self.widths[0], self.widths[1]))
+
+    def layer_dims(self):
+        dims, fan_in = [], self.N_IN
+        for d in list(self.widths) + [1]:
+            dims.append((fan_in, d))
+            fan_in = d
+        return dims
+
+
 class LevelSet:
     """phi on `lvl_gstate` + the reference's interpolant, evaluated inside the kernels
     (interpolate.py:906-1021 trilinear, :388-569 non-oscillatory quadratic; level_set.py:34-48)."""
@@ -233,7 +263,7 @@ class SharedPlan:
 
     def __init__(self, lvl: LevelSet, tr_gstate, xa: int, xb: int, fns, net: NetShape,
                  nonlinear_m: Nonlinear, nonlinear_p: Nonlinear, n_mean: Optional[int] = None, device=None,
-                 faces: Optional[bool] = None, fused: Optional[bool] = None):
+                 faces: Optional[bool] = None, fused: Optional[bool] = None, precond: Optional[PrecondShape] = None):
         """`faces`: store one coefficient per cell FACE + 1/diag (16 B/node) instead of the 7 row weights
         (28 B/node); irregular rows move into the list.  Default: on whenever the 16-byte stencil kernels
         apply (even Ny, Nz).
@@ -320,7 +350,10 @@ class SharedPlan:
                 irr_nlw = torch.zeros(cap, dtype=torch.float32, device=dev)
             irr_wU = torch.zeros(cap * 7, dtype=torch.float32, device=dev) if self.faces else None
             irr_rhs = torch.zeros(cap, dtype=torch.float32, device=dev) if self.faces else None
+            self.precond = precond
+            self.coef26 = torch.zeros(26 * ne, dtype=torch.float32, device=dev) if precond is not None else None
             a = cabi.Assemble()
+            a.coef26 = cabi.ptr(self.coef26)
             a.pts = _lattice(pxs, ys, zs)
             a.dx, a.dy, a.dz = dx, dy, dz
             for i, b in enumerate(lvl.bounds):
@@ -356,6 +389,8 @@ class SharedPlan:
             self.irr_nlw = irr_nlw[:max(n_irr, 1)].clone()
             self.irr = irr
             del mu_m_faces, mu_p_faces, k_m, k_p, f_m, f_p, g_dir
+            if self.fused and precond is not None:
+                raise ValueError("the fused adjoint path does not take a preconditioner")
             if self.fused:
                 # bit 2 of `side`: the node can receive a contribution from the lists (the 27-cube of a crossed
                 # site, the 7 stencil sites of an irregular row); only those read (and re-zero) G in the step
@@ -374,14 +409,17 @@ class SharedPlan:
                     cs.side[nodes] = cs.side[nodes] | 4
 
             # ---- work buffers + the step descriptor
-            P = net.n_params
+            P = net.n_params + (precond.n_params if precond is not None else 0)
+            self.n_total = P
             self.U = torch.zeros(ne, dtype=torch.float32, device=dev)
             self.R = torch.zeros(ne, dtype=torch.float32, device=dev)  # halo rows stay 0 for ever
             self.G = torch.zeros(ne, dtype=torch.float32, device=dev)
             self.E = torch.zeros(max(cs.n, 1), dtype=torch.float32, device=dev)
             self.gE = torch.zeros(max(cs.n, 1), dtype=torch.float32, device=dev)
             # the shared path launches at most one gradient CTA per SM: that many partial rows
-            rows = min(L.nbm_step_partial_rows(), torch.cuda.get_device_properties(dev).multi_processor_count)
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            n_pc_rows = sms if precond is not None else 0
+            rows = min(L.nbm_step_partial_rows(), sms) + n_pc_rows
             self.partials = torch.zeros(rows * (P + 1), dtype=torch.float32, device=dev)
             self.loss_grad = torch.zeros(P + 1, dtype=torch.float32, device=dev)
             s = cabi.SharedStep()
@@ -402,6 +440,10 @@ class SharedPlan:
             s.cface, s.dinv, s.kv = cabi.ptr(self.cface), cabi.ptr(self.dinv), cabi.ptr(self.kv)
             s.irr_wU, s.irr_rhs = cabi.ptr(self.irr_wU), cabi.ptr(self.irr_rhs)
             s.S = cabi.ptr(self.S)
+            if precond is not None:
+                s.coef26 = cabi.ptr(self.coef26)
+                s.pc_d1, s.pc_d2, s.pc_scale = precond.widths[0], precond.widths[1], precond.scale
+                s.n_pc_rows = n_pc_rows
             self.step = s
             self.xa, self.xb = xa, xb
             # the regression/cut-cell scratch is not needed by the step
@@ -425,8 +467,17 @@ class SharedPlan:
                        "nbm_loss_grad_shared_f32")
         finally:
             self.step.stages = 0
-        comm.reduce_allreduce(self.partials, self.step.n_partial_rows, self.net.n_params + 1, target)
+        comm.reduce_allreduce(self.partials, self.step.n_partial_rows, self.n_total + 1, target)
         return target
+
+    def bind_params(self, params: torch.Tensor) -> None:
+        """With a preconditioner the step reads its parameters straight from the tail of the flat device vector
+        [network | preconditioner] (the network part travels through `upload_params`)."""
+        if self.precond is not None:
+            if params.numel() != self.n_total:
+                raise ValueError(f"parameter vector has {params.numel()} entries, expected {self.n_total}")
+            self.step.pc_params = params.data_ptr() + 4 * self.net.n_params
+            self._bound = params   # keep the storage alive
 
     # ---- read-backs for tests -----------------------------------------------------------------
     def rhs_rows(self) -> torch.Tensor:

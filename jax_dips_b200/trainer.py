@@ -37,7 +37,7 @@ from . import _cabi as cabi
 from . import data_management
 from . import numpy as jnp
 from .optimizers import OptimizerSpec, get_optimizer
-from .plan import GeneralLevel, LevelSet, NetShape, Nonlinear, PointsPlan, SharedPlan, upload_params
+from .plan import GeneralLevel, LevelSet, NetShape, Nonlinear, PointsPlan, PrecondShape, SharedPlan, upload_params
 from .simulation_states import PoissonSimState, PoissonSimStateFn, replace
 
 logger = logging.getLogger(__name__)
@@ -97,7 +97,18 @@ def haiku_init(net: NetShape, seed: int = 42) -> torch.Tensor:
     return torch.cat(parts).to(torch.float32)
 
 
-def params_to_tree(net: NetShape, flat: torch.Tensor) -> dict:
+def precond_init(pc: PrecondShape, seed: int = 42) -> torch.Tensor:
+    """glorot_uniform kernels, zero biases (nn/preconditioner.py:20; flax nn.Dense defaults), torch generator."""
+    g = torch.Generator().manual_seed(seed + 1000)
+    parts = []
+    for (fan_in, d) in pc.layer_dims():
+        lim = math.sqrt(6.0 / (fan_in + d))
+        parts += [(torch.rand(fan_in * d, generator=g, dtype=torch.float64) * 2 - 1) * lim,
+                  torch.zeros(d, dtype=torch.float64)]
+    return torch.cat(parts).to(torch.float32)
+
+
+def params_to_tree(net: NetShape, flat: torch.Tensor, precond: Optional[PrecondShape] = None) -> dict:
     """haiku-style parameter tree (keys as the reference's checkpoints hold them, cf. trainer.py:323)."""
     flat = flat.detach().cpu().numpy()
     tree, off = {}, 0
@@ -111,16 +122,29 @@ def params_to_tree(net: NetShape, flat: torch.Tensor) -> dict:
             tree[name] = {"w": w, "b": b}
             fan_in = out
     tree["preconditioner"] = {}
+    if precond is not None:
+        # flax parameter tree of nn/preconditioner.py (trainer.py:236-243)
+        dense = {}
+        for l, (fan_in, d) in enumerate(precond.layer_dims()):
+            k = flat[off: off + fan_in * d].reshape(fan_in, d).copy(); off += fan_in * d
+            b = flat[off: off + d].copy(); off += d
+            dense[f"Dense_{l}"] = {"kernel": k, "bias": b}
+        tree["preconditioner"] = {"params": dense}
     return tree
 
 
-def tree_to_params(net: NetShape, tree: dict) -> torch.Tensor:
+def tree_to_params(net: NetShape, tree: dict, precond: Optional[PrecondShape] = None) -> torch.Tensor:
     parts = []
     for head, (L, H) in (("p", (net.layers_p, net.hidden_p)), ("m", (net.layers_m, net.hidden_m))):
         for l in range(L + 1):
             name = f"double_mlp/~mlp_{head}_fn/linear" + ("" if l == 0 else f"_{l}")
             parts += [np.asarray(tree[name]["w"], dtype=np.float32).reshape(-1),
                       np.asarray(tree[name]["b"], dtype=np.float32).reshape(-1)]
+    if precond is not None:
+        dense = tree["preconditioner"]["params"]
+        for l in range(len(precond.layer_dims())):
+            parts += [np.asarray(dense[f"Dense_{l}"]["kernel"], dtype=np.float32).reshape(-1),
+                      np.asarray(dense[f"Dense_{l}"]["bias"], dtype=np.float32).reshape(-1)]
     return torch.from_numpy(np.concatenate(parts))
 
 
@@ -163,8 +187,9 @@ class Trainer:
         self.train_dx, self.train_dy, self.train_dz = (float(tr_gstate.dx), float(tr_gstate.dy), float(tr_gstate.dz))
 
         self.net = NetShape.from_model_dict(model_dict)
-        if model_dict.get("preconditioner", {"enable": False}).get("enable", False):
-            raise NotImplementedError("the learned preconditioner (nn/preconditioner.py) is not on this path yet")
+        # learned preconditioner (nn/preconditioner.py; trainer.py:229-243): parameters ride at the tail of the
+        # flat vector and are trained jointly
+        self.precond = PrecondShape.from_model_dict(model_dict)
         self.nonlinear_m = Nonlinear.coerce(sim_state_fn.nonlinear_op_m)
         self.nonlinear_p = Nonlinear.coerce(sim_state_fn.nonlinear_op_p)
 
@@ -179,14 +204,14 @@ class Trainer:
             # level set on the lvl grid, read by the kernels through the reference's interpolant
             phi_lvl = sim_state_fn.phi_fn(lvl_gstate.R.to(self.device))
             self.lvl = LevelSet(lvl_gstate, phi_lvl, interp=phi_interp, perturb_eps=perturb_eps, device=self.device)
-            P = self.net.n_params
+            P = self.n_params = self.net.n_params + (self.precond.n_params if self.precond is not None else 0)
             self.opt_state = torch.zeros(2 * P, dtype=torch.float32, device=self.device)
             self.opt_count = torch.zeros(1, dtype=torch.int32, device=self.device)
             if restart:
                 state = self.fetch_checkpoint(self.restart_checkpoint_dir)
                 if state is None:
                     raise FileNotFoundError(f"no checkpoint under {self.restart_checkpoint_dir}")
-                self.params = tree_to_params(self.net, state["params"]).to(self.device)
+                self.params = tree_to_params(self.net, state["params"], self.precond).to(self.device)
                 self.opt_state.copy_(torch.as_tensor(state["opt_state"]["moments"]).to(self.device))
                 self.opt_count.fill_(int(state["opt_state"]["count"]))
                 self.batch_size = state["batch_size"]
@@ -194,6 +219,8 @@ class Trainer:
                             f"resolution {state['resolution']}.")
             else:
                 p0 = init_params if init_params is not None else haiku_init(self.net, seed=42)
+                if self.precond is not None and p0.numel() == self.net.n_params:
+                    p0 = torch.cat((p0.detach().cpu().float(), precond_init(self.precond, seed=42)))
                 if p0.numel() != P:
                     raise ValueError(f"init_params has {p0.numel()} entries, the network has {P}")
                 self.params = p0.detach().to(self.device, torch.float32).contiguous().clone()
@@ -235,7 +262,7 @@ class Trainer:
 
     def _checkpoint_state(self, epoch: int) -> dict:
         return {"opt_state": {"moments": self.opt_state.cpu().numpy(), "count": int(self.opt_count.item())},
-                "params": params_to_tree(self.net, self.params), "epoch": epoch, "batch_size": self.batch_size,
+                "params": params_to_tree(self.net, self.params, self.precond), "epoch": epoch, "batch_size": self.batch_size,
                 "resolution": f"{self.train_dx}, {self.train_dy}, {self.train_dz}"}
 
     # ------------------------------------------------------------------------------------------
@@ -250,8 +277,14 @@ class Trainer:
         with torch.cuda.device(self.device):
             if zoom == 0 and p0 % plane == 0 and p1 % plane == 0:
                 pl = SharedPlan(self.lvl, self.tr_gstate, p0 // plane, p1 // plane, self.sim_state_fn, self.net,
-                                self.nonlinear_m, self.nonlinear_p, device=self.device)
+                                self.nonlinear_m, self.nonlinear_p, device=self.device, precond=self.precond)
+                pl.bind_params(self.params)
             else:
+                if self.precond is not None:
+                    raise NotImplementedError(
+                        "the learned preconditioner runs on the shared-evaluation path only (cell size == grid "
+                        "spacing, batches of whole x planes), which is what multi_gpu=True trains on; the single-GPU "
+                        "multi-resolution schedule (data_management.py:320-326) is not covered yet")
                 pl = PointsPlan(self.general_level(zoom), p0, p1)
         self._plans[key] = pl
         return pl
@@ -266,7 +299,7 @@ class Trainer:
     def _optimizer_struct(self) -> cabi.Optimizer:
         if self._opt_struct is None:
             o, s = self.optimizer, self.optimizer.scheduler
-            self._opt_struct = cabi.Optimizer(self.net.n_params, float(o.learning_rate), float(s.decay_rate),
+            self._opt_struct = cabi.Optimizer(self.n_params, float(o.learning_rate), float(s.decay_rate),
                                               float(s.transition_steps), float(o.max_norm), o.b1,
                                               0.9 if o.optimizer_name == "rmsprop" else o.b2, o.eps, o.kind,
                                               0 if s.scheduler_name == "exponential" else 1)

@@ -499,13 +499,61 @@ def init_params(shape: NetShape, seed: int = 42, dtype=torch.float32) -> Tensor:
 
 
 # ----------------------------------------------------------------------------------------
+# learned preconditioner   (nn/preconditioner.py:10-35; trainer.py:229-243, 846-847;
+# discretization.py:339, 418-419)
+# ----------------------------------------------------------------------------------------
+class PrecondShape:
+    """model_dict['preconditioner']: tanh MLP 26 -> layer_widths -> 1, P = 0.5 + scaling_coeff * sigmoid(.)
+    (flax nn.Dense: y = x @ kernel + bias, kernel (in, out))."""
+    N_IN = 26   # length of coeffs_ (geometric_integrations_per_point.py:873-903)
+
+    def __init__(self, layer_widths=(8, 4), scaling_coeff: float = 1.0):
+        self.Ds, self.scale = tuple(int(d) for d in layer_widths), float(scaling_coeff)
+
+    @property
+    def n_params(self):
+        n, fan_in = 0, self.N_IN
+        for d in self.Ds:
+            n += fan_in * d + d
+            fan_in = d
+        return n + fan_in + 1
+
+
+def precond_eval(flat: Tensor, shape: PrecondShape, coeffs: Tensor) -> Tensor:
+    """Preconditioner.__call__ (nn/preconditioner.py:22-35) on (n, 26) inputs; `flat` holds Dense_0.kernel
+    (row-major (in,out)), Dense_0.bias, Dense_1.kernel, ... in that order."""
+    off, fan_in, h = 0, shape.N_IN, coeffs.to(flat.dtype)
+    for d in shape.Ds:
+        W = flat[off: off + fan_in * d].reshape(fan_in, d); off += fan_in * d
+        b = flat[off: off + d]; off += d
+        h = torch.tanh(h @ W + b)
+        fan_in = d
+    W = flat[off: off + fan_in].reshape(fan_in, 1); off += fan_in
+    b = flat[off: off + 1]
+    return 0.5 + shape.scale * torch.sigmoid((h @ W + b).reshape(-1))
+
+
+def init_precond_params(shape: PrecondShape, seed: int = 42, dtype=torch.float32) -> Tensor:
+    """glorot_uniform kernels (nn/preconditioner.py:20), zero biases (flax default).  As for the solution
+    network the reference's PRNGKey(42) stream cannot be reproduced without jax: init is an input."""
+    g = torch.Generator().manual_seed(seed + 1000)
+    parts, fan_in = [], shape.N_IN
+    for d in list(shape.Ds) + [1]:
+        lim = math.sqrt(6.0 / (fan_in + d))
+        parts += [(torch.rand(fan_in * d, generator=g, dtype=torch.float64) * 2 - 1) * lim, torch.zeros(d, dtype=torch.float64)]
+        fan_in = d
+    return torch.cat(parts).to(dtype)
+
+
+# ----------------------------------------------------------------------------------------
 # problem bundle: batched callables (what trainer.setup builds by vmap, trainer.py:995-1005)
 # ----------------------------------------------------------------------------------------
 class OracleProblem:
     """Batched callables (n,3)->(n,), the lvl-grid box bounds, the network shape."""
 
     def __init__(self, phi_fn, mu_m_fn, mu_p_fn, k_m_fn, k_p_fn, f_m_fn, f_p_fn, alpha_fn, beta_fn,
-                 dir_bc_fn, bounds, shape: NetShape = None, nonlinear_op_m=None, nonlinear_op_p=None):
+                 dir_bc_fn, bounds, shape: NetShape = None, nonlinear_op_m=None, nonlinear_op_p=None,
+                 precond: "PrecondShape" = None):
         self.phi_fn = phi_fn
         self.mu_m_fn, self.mu_p_fn = mu_m_fn, mu_p_fn
         self.k_m_fn, self.k_p_fn = k_m_fn, k_p_fn
@@ -516,6 +564,8 @@ class OracleProblem:
         self.shape = shape or NetShape()
         self.nonlinear_op_m = nonlinear_op_m or (lambda u: 0.0 * u)   # trainer.py:1007-1017
         self.nonlinear_op_p = nonlinear_op_p or (lambda u: 0.0 * u)
+        # with a preconditioner the flat parameter vector is [network | preconditioner]
+        self.precond = precond
 
     # evaluate_solution_fn (trainer.py:836-844) / solution_at_point_fn (:849-854) / MLP.py:98
     def solution(self, params: Tensor, R: Tensor, phi: Tensor = None) -> Tensor:
@@ -659,8 +709,9 @@ def is_box_boundary(points: Tensor, dx, dy, dz, bounds) -> Tensor:
 
 def compute_Ax_and_b(params: Tensor, points: Tensor, dx, dy, dz, prob: OracleProblem,
                      return_parts: bool = False):
-    """compute_Ax_and_b_preconditioned_fn with the disabled preconditioner (=1.0, trainer.py:246-253).
-    Returns (lhs/diag, rhs/diag), each (n,)."""
+    """compute_Ax_and_b_preconditioned_fn (discretization.py:299-423).  The preconditioner is 1.0 when
+    disabled (trainer.py:246-253), else P(coeffs_) with the parameters stored after the network's.
+    Returns (lhs/diag * P, rhs/diag * P), each (n,)."""
     dt = params.dtype
     points = points.to(dt)
     n = points.shape[0]
@@ -701,6 +752,9 @@ def compute_Ax_and_b(params: Tensor, points: Tensor, dx, dy, dz, prob: OraclePro
         rhs = torch.where(on_bnd, rhs_b * torch.ones_like(rhs), rhs)
     lhs_n = nan_to_num(lhs / diag)
     rhs_n = nan_to_num(rhs / diag)
+    if prob.precond is not None:   # discretization.py:339, 418-419
+        Pc = precond_eval(params[prob.shape.n_params:], prob.precond, coeffs_)
+        lhs_n, rhs_n = lhs_n * Pc, rhs_n * Pc
     if return_parts:
         return lhs_n, rhs_n, dict(coeffs=coeffs_, diag=diag, rhs=rhs, on_bnd=on_bnd)
     return lhs_n, rhs_n

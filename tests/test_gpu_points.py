@@ -61,7 +61,8 @@ def test_general_and_shared_paths_agree_at_native_spacing():
     assert util.rel_inf(a, b) < 2e-5
 
 
-def _solve(problem, n_tr, n_lvl, n_eval, num_epochs, batch_size, init, multi_gpu=False, optimizer_dict=None):
+def _solve(problem, n_tr, n_lvl, n_eval, num_epochs, batch_size, init, multi_gpu=False, optimizer_dict=None,
+           model_dict=None):
     lo, hi = problem.box
     init_mesh_fn, _ = mesh.construct(3)
     tr = mesh.linspace_grid(lo, hi, [n_tr] * 3)
@@ -72,7 +73,7 @@ def _solve(problem, n_tr, n_lvl, n_eval, num_epochs, batch_size, init, multi_gpu
                             "sched": {"scheduler_name": "exponential", "decay_rate": 0.975}}
     sim_state, solve_fn = init_fn(lvl_gstate=lv, tr_gstate=tr, eval_gstate=ev, num_epochs=num_epochs,
                                   batch_size=batch_size, multi_gpu=multi_gpu, checkpoint_dir=None,
-                                  optimizer_dict=od, init_params=init, device=DEV, print_rate=0)
+                                  optimizer_dict=od, model_dict=model_dict, init_params=init, device=DEV, print_rate=0)
     out = solve_fn(sim_state)
     return out, solve_fn.trainer, (tr, lv, ev)
 
@@ -102,6 +103,39 @@ def test_single_gpu_training_follows_the_oracle_trajectory():
     assert util.rel_inf(state.grad_solution.cpu(), gu_o) < 1e-5
     fin = torch.isfinite(gn_o)
     assert util.rel_inf(state.grad_normal_solution.cpu()[fin], gn_o[fin]) < 1e-4
+
+
+def test_multi_gpu_loop_with_learned_preconditioner_follows_the_oracle():
+    """model_dict["preconditioner"]["enable"] (examples/benchmark_LPBE/conf/lpbe.yaml:62-67) through
+    setup/init_fn/solve_fn on the multi_gpu=True loop (one device here): loss trajectory and final parameters
+    (network + preconditioner, trained jointly) against the oracle's multi_GPU_train."""
+    P = problems.sphere()
+    n_tr, n_lvl = 8, 24
+    tr, lv, phi_grid, oprob = util.make_case(P, n_tr, n_lvl, "trilinear", torch.float64)
+    oprob.precond = O.PrecondShape((8, 4), 1.0)
+    pp = O.init_precond_params(oprob.precond, seed=2, dtype=torch.float64)
+    pp[:26 * 8] *= 10.0
+    p0 = torch.cat((O.init_params(oprob.shape, seed=42, dtype=torch.float64), pp))
+    od = {"optimizer_name": "custom", "learning_rate": 1e-2, "sched": {"scheduler_name": "exponential", "decay_rate": 0.975}}
+    md = {"name": None, "model_type": "mlp",
+          "mlp": {"hidden_layers_m": 1, "hidden_dim_m": 1, "activation_m": "jnp.tanh",
+                  "hidden_layers_p": 2, "hidden_dim_p": 10, "activation_p": "jnp.tanh"},
+          "preconditioner": {"enable": True, "layer_widths": [8, 4], "scaling_coeff": 1.0}}
+    grid_d = [tr.dx.double(), tr.dy.double(), tr.dz.double()]
+    p_o, losses_o = O.multi_gpu_train(p0.clone(), tr.R.double(), grid_d, oprob, num_epochs=6, batch_size=256,
+                                      n_devices=1, optimizer_dict=od)
+    (state, epoch_store, loss_epochs), T, _ = _solve(P, n_tr, n_lvl, 8, 6, 256, p0.float(), optimizer_dict=od,
+                                                     model_dict=md, multi_gpu=True)
+    lk = torch.stack([torch.as_tensor(l).reshape(-1)[0] for l in loss_epochs]).double()
+    lo = torch.tensor(losses_o, dtype=torch.float64)
+    assert ((lk - lo).abs() / lo).max() < 1e-3, (lk, lo)
+    assert util.rel_inf(T.params.cpu(), p_o) < 1e-3
+    tree = ntrainer.params_to_tree(T.net, T.params, T.precond)
+    assert tree["preconditioner"]["params"]["Dense_0"]["kernel"].shape == (26, 8)
+    assert torch.equal(ntrainer.tree_to_params(T.net, tree, T.precond), T.params.cpu())
+    # the single-GPU multi-resolution loop does not take the preconditioner yet: loud, typed failure
+    with pytest.raises(NotImplementedError):
+        _solve(P, n_tr, n_lvl, 8, 8, 256, p0.float(), optimizer_dict=od, model_dict=md)
 
 
 def test_training_reduces_the_error_against_the_exact_solution():

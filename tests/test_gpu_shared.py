@@ -194,3 +194,49 @@ def test_slab_plans_sum_to_the_whole_grid():
             acc += pl.loss_grad_launch() * (pl.n_points / whole.n_points)
         torch.cuda.synchronize()
     assert util.rel_inf(acc, ref) < 1e-5
+
+
+@pytest.mark.parametrize("name,faces", [("sphere", True), ("star", False), ("pb", True)])
+def test_learned_preconditioner(name, faces):
+    """P = 0.5 + s * sigmoid(MLP(coeffs_)) multiplies lhs/diag and rhs/diag of every row (nn/preconditioner.py:10-35,
+    discretization.py:339, 418-419): loss, d loss/d network parameters and d loss/d preconditioner parameters."""
+    if name == "pb":
+        P = problems.poisson_boltzmann(n_atoms=6, seed=3, half_width=1.0)
+        P.nonlinear_op_p = nplan.Nonlinear.sinh(3000.0)
+    else:
+        P = problems.PROBLEMS[name]()
+    dt = torch.float64
+    tr, lv, phi_grid, oprob = util.make_case(P, 16, 32, "trilinear", dt)
+    oprob.precond = O.PrecondShape((8, 4), 1.0)
+    lvl = nplan.LevelSet(lv, phi_grid, device=DEV)
+    shape = nplan.NetShape()
+    pc = nplan.PrecondShape((8, 4), 1.0)
+    assert pc.n_params == oprob.precond.n_params == 257
+    pl = nplan.SharedPlan(lvl, tr, 0, 16, fns_of(P), shape, nplan.Nonlinear.coerce(P.nonlinear_op_m),
+                          nplan.Nonlinear.coerce(P.nonlinear_op_p), device=DEV, faces=faces, precond=pc)
+    # inputs of the preconditioner are O(h): scale its first layer up so that P varies from point to point
+    pp = O.init_precond_params(oprob.precond, seed=5, dtype=dt)
+    pp[:26 * 8] *= 40.0
+    params = torch.cat((O.init_params(oprob.shape, seed=7, dtype=dt), pp))
+    d = [tr.dx.to(dt), tr.dy.to(dt), tr.dz.to(dt)]
+    loss_o, grad_o = O.loss_and_grad(params, tr.R.to(dt), *d, oprob)
+    lhs_o, rhs_o, parts = O.compute_Ax_and_b(params, tr.R.to(dt), *d, oprob, return_parts=True)
+    Pc = O.precond_eval(params[shape.n_params:], oprob.precond, parts["coeffs"])
+    assert float(Pc.max() - Pc.min()) > 1e-2, "the test must exercise a varying preconditioner"
+    # the 26 inputs the kernels hand to the preconditioner
+    c26 = pl.coef26.view(26, *pl.dims)[:, pl.HX:-pl.HX, pl.HY:-pl.HY, pl.HZ:-pl.HZ].reshape(26, -1).T.cpu()
+    assert util.rel_inf(c26, parts["coeffs"]) < TOL_FRAC
+    p_dev = params.float().to(DEV)
+    with torch.cuda.device(DEV):
+        nplan.upload_params(shape, p_dev)
+        pl.bind_params(p_dev)
+        lg = pl.loss_grad_launch().cpu()
+    assert lg.numel() == shape.n_params + 257 + 1
+    assert abs(float(lg[-1]) - float(loss_o)) / float(loss_o) < TOL_LOSS, (float(lg[-1]), float(loss_o))
+    n = shape.n_params
+    assert util.rel_inf(lg[:n], grad_o[:n]) < TOL_LOSS, util.rel_inf(lg[:n], grad_o[:n])
+    assert util.rel_inf(lg[n:-1], grad_o[n:]) < TOL_LOSS, util.rel_inf(lg[n:-1], grad_o[n:])
+    # R now holds d loss/d r (times n) = P^2 r
+    r_o = (lhs_o - rhs_o) / Pc
+    got = pl.point_view(pl.R).cpu()
+    assert util.rel_inf(got, Pc * Pc * r_o) < 10 * TOL_ROW
