@@ -312,6 +312,11 @@ typedef struct {
      * `point[0] - dx`, discretization.py:348-353) and work arrays [7][n_points] */
     const float* xs7; const float* ys7; const float* zs7;
     float* U7; float* G7;
+    /* learned preconditioner (see nbm_shared_step_t): coef26 [26][nx*ny*nz], Pc work array [nx*ny*nz]; `rows`
+     * must then be non-NULL (it carries the un-preconditioned residuals between the kernels); every partial row is
+     * n_net + n_pc + 1 floats and n_pc_rows extra rows are needed after the 7*grid + rows + extrap rows */
+    const float* coef26; const float* pc_params; float* Pc;
+    int pc_d1, pc_d2; float pc_scale; int n_pc_rows;
 } nbm_points_step_t;
 
 /* General path (any cell size, any contiguous batch): 7 network evaluations per point (the reference

@@ -84,7 +84,9 @@ class PointsStep(C.Structure):
                 ("inv_n_points", c_f),
                 ("E", c_fp), ("gE", c_fp),
                 ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp), ("rows", c_fp),
-                ("xs7", c_fp), ("ys7", c_fp), ("zs7", c_fp), ("U7", c_fp), ("G7", c_fp)]
+                ("xs7", c_fp), ("ys7", c_fp), ("zs7", c_fp), ("U7", c_fp), ("G7", c_fp),
+                ("coef26", c_fp), ("pc_params", c_fp), ("Pc", c_fp), ("pc_d1", C.c_int), ("pc_d2", C.c_int),
+                ("pc_scale", c_f), ("n_pc_rows", C.c_int)]
 
 
 class Optimizer(C.Structure):

@@ -1029,7 +1029,8 @@ __global__ void extrap_bwd_kernel(nbm_shared_step_t s) {
 
 // block-level reduction of per-thread accumulators into partials[blockIdx.x][0..NP] (loss last)
 template <class NET>
-__device__ __forceinline__ void block_reduce_store(typename NET::Acc& acc, float loss, float* __restrict__ partials) {
+__device__ __forceinline__ void block_reduce_store(typename NET::Acc& acc, float loss, float* __restrict__ partials,
+                                                   int stride = NET::NP + 1) {
     constexpr int NP = NET::NP;
     __shared__ float sm[kThreads / 32][NP + 1];
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1045,7 +1046,7 @@ __device__ __forceinline__ void block_reduce_store(typename NET::Acc& acc, float
         float v = 0.0f;
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w) v += sm[w][i];
-        partials[(size_t)blockIdx.x * (NP + 1) + i] = v;
+        partials[(size_t)blockIdx.x * stride + (i < NP ? i : stride - 1)] = v;
     }
 }
 
@@ -1533,7 +1534,8 @@ struct PrecondNet {
 __device__ __forceinline__ float tanh_acc(float x) { return tanh_nbm(x); }
 
 template <int D1, int D2>
-__global__ void __launch_bounds__(kThreads) precond_kernel(const float* __restrict__ coef26, float* __restrict__ R,
+__global__ void __launch_bounds__(kThreads) precond_kernel(const float* __restrict__ coef26, int64_t cstride,
+                                                           float* __restrict__ R,
                                                            int64_t ne, const float* __restrict__ params, float scale,
                                                            float inv_n, float* __restrict__ partials, int row_stride,
                                                            int col0, int loss_col) {
@@ -1564,7 +1566,7 @@ __global__ void __launch_bounds__(kThreads) precond_kernel(const float* __restri
         const float r = valid ? R[e] : 0.0f;
         float c[NIN];
 #pragma unroll
-        for (int k = 0; k < NIN; ++k) c[k] = valid ? __ldcs(coef26 + (int64_t)k * ne + e) : 0.0f;
+        for (int k = 0; k < NIN; ++k) c[k] = valid ? __ldcs(coef26 + (int64_t)k * cstride + e) : 0.0f;
         // forward
         float h1[D1], h2[D2];
 #pragma unroll
@@ -1666,6 +1668,39 @@ __global__ void __launch_bounds__(kThreads) precond_kernel(const float* __restri
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) v += sred[w][i];
         row[i < NPc ? col0 + i : loss_col] = v;
+    }
+}
+
+// forward only: Pc[i] = P(coeffs_ of point i)   (general path: the seeds of the backward pass need P first)
+template <int D1, int D2>
+__global__ void __launch_bounds__(kThreads) precond_fwd_kernel(const float* __restrict__ coef26, int64_t cstride,
+                                                               int64_t n, const float* __restrict__ params, float scale,
+                                                               float* __restrict__ Pc) {
+    using PN = PrecondNet<D1, D2>;
+    constexpr int NIN = PN::NIN, NPc = PN::NP;
+    __shared__ float sP[NPc];
+    for (int i = threadIdx.x; i < NPc; i += kThreads) sP[i] = params[i];
+    __syncthreads();
+    for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < n; e += (int64_t)gridDim.x * kThreads) {
+        float c[NIN], h1[D1];
+#pragma unroll
+        for (int k = 0; k < NIN; ++k) c[k] = __ldg(coef26 + (int64_t)k * cstride + e);
+#pragma unroll
+        for (int j = 0; j < D1; ++j) {
+            float s = sP[PN::ob1 + j];
+#pragma unroll
+            for (int k = 0; k < NIN; ++k) s = fmaf(c[k], sP[PN::oW1 + k * D1 + j], s);
+            h1[j] = tanh_acc(s);
+        }
+        float o = sP[PN::ob3];
+#pragma unroll
+        for (int q = 0; q < D2; ++q) {
+            float s = sP[PN::ob2 + q];
+#pragma unroll
+            for (int j = 0; j < D1; ++j) s = fmaf(h1[j], sP[PN::oW2 + j * D2 + q], s);
+            o = fmaf(tanh_acc(s), sP[PN::oW3 + q], o);
+        }
+        Pc[e] = fmaf(scale, 1.0f / (1.0f + __expf(-o)), 0.5f);
     }
 }
 
@@ -1916,7 +1951,8 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
         if (s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
         if (pc) {
             // rows [gridC, gridC + gridP) of the partials: preconditioner gradient + the loss
-            precond_kernel<8, 4><<<gridP, kThreads, 0, st>>>(s.coef26, s.R, (int64_t)s.ex * s.ey * s.ez, s.pc_params,
+            precond_kernel<8, 4><<<gridP, kThreads, 0, st>>>(s.coef26, (int64_t)s.ex * s.ey * s.ez, s.R,
+                                                             (int64_t)s.ex * s.ey * s.ez, s.pc_params,
                                                              s.pc_scale, s.inv_n_points,
                                                              s.partials + (size_t)gridC * pc_stride, pc_stride, NET::NP,
                                                              NET::NP + n_pc);
@@ -2081,8 +2117,14 @@ __global__ void __launch_bounds__(kThreads) points_rows_kernel(PointsArgs a, con
                                                     : nl_apply(s.nonlinear_p, s.nl_coef_p, Ec), r);
             }
         }
-        loss = fmaf(0.5f * r, r, loss);
         if (s.rows) s.rows[p] = r;
+        if (s.Pc) {
+            // preconditioned row P r: d loss/d r (times n) = P^2 r; loss and d/d theta_P come from precond_kernel
+            const float Pp = s.Pc[p];
+            r *= Pp * Pp;
+        } else {
+            loss = fmaf(0.5f * r, r, loss);
+        }
         if (q_irr >= 0) {
             // each crossed site belongs to exactly one (point, slot): plain stores (gE carries the un-normalised
             // residual weight; the 1/n of the mean is applied by the backward kernels)
@@ -2130,7 +2172,7 @@ __global__ void __launch_bounds__(kThreads) points_rows_kernel(PointsArgs a, con
 
 // Z2: backward through the extrapolation of the crossed sites of the batch
 template <class NET>
-__global__ void __launch_bounds__(kThreads, 1) points_extrap_bwd_kernel(PointsArgs a, int row0) {
+__global__ void __launch_bounds__(kThreads, 1) points_extrap_bwd_kernel(PointsArgs a, int row0, int stride) {
     const nbm_points_step_t& s = a.s;
     typename NET::Acc acc;
     acc.zero();
@@ -2150,7 +2192,7 @@ __global__ void __launch_bounds__(kThreads, 1) points_extrap_bwd_kernel(PointsAr
                 NET::grad(plus, s.c_pos[3 * c] + X0, s.c_pos[3 * c + 1] + X1, s.c_pos[3 * c + 2] + X2, gq, acc);
         }
     }
-    block_reduce_store<NET>(acc, 0.0f, s.partials + (size_t)row0 * (NET::NP + 1));
+    block_reduce_store<NET>(acc, 0.0f, s.partials + (size_t)row0 * stride, stride);
 }
 
 template <class NET>
@@ -2188,23 +2230,38 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     const int gridR = (int)min((int64_t)sms * 2, (nb + kThreads - 1) / kThreads);
     int gridE = 0;
     if (s.n_crossed > 0) gridE = (int)min((int64_t)sms, (s.n_crossed * 32 + kThreads - 1) / kThreads);
-    const int rows_needed = 7 * gridG + gridR + gridE;
+    const bool pc = s.coef26 != nullptr;
+    const int n_pc = pc ? PrecondNet<8, 4>::NP : 0;
+    const int stride = NET::NP + n_pc + 1;
+    const int gridP = pc ? min(s.n_pc_rows, 2 * sms) : 0;
+    const int rows_needed = 7 * gridG + gridR + gridE + gridP;
     if (rows_needed > s.n_partial_rows) {
         set_error("partials buffer has %d rows, %d needed", s.n_partial_rows, rows_needed);
         return NBM_ERR_WORKSPACE;
     }
+    // plans of one level share the partials buffer and their row roles differ with the batch size: with the wider
+    // preconditioner rows every kernel writes only its own columns, so start from zero
+    if (pc) cudaMemsetAsync(s.partials, 0, sizeof(float) * (size_t)rows_needed * stride, st);
     if (s.n_crossed > 0)
         points_extrap_kernel<NET><<<(unsigned)min((int64_t)sms * 4, (s.n_crossed * 32 + kThreads - 1) / kThreads),
                                     kThreads, 0, st>>>(a);
     fwd_nodes_kernel<NET, true><<<dim3(gridF, 7), kThreads, 0, st>>>(v, T);
-    points_rows_kernel<<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, 7 * gridG, np1);
-    v.row0 = 0; v.row_stride = 0; v.loss_col = 0;
+    if (pc)
+        precond_fwd_kernel<8, 4><<<(unsigned)min((int64_t)sms * 8, (nb + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+            s.coef26 + s.p0, a.n_points, nb, s.pc_params, s.pc_scale, s.Pc + s.p0);
+    points_rows_kernel<<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, 7 * gridG, stride);
+    if (pc)   // loss + d loss/d theta_P from the raw residuals kept in `rows`
+        precond_kernel<8, 4><<<gridP, kThreads, 0, st>>>(s.coef26 + s.p0, a.n_points, s.rows + s.p0, nb, s.pc_params,
+                                                         s.pc_scale, s.inv_n_points,
+                                                         s.partials + (size_t)(7 * gridG + gridR + gridE) * stride, stride,
+                                                         NET::NP, NET::NP + n_pc);
+    v.row0 = 0; v.row_stride = pc ? stride : 0; v.loss_col = NET::NP + n_pc;
     {
         cudaError_t e = launch_node_grad<NET, true>(dim3(gridG, 7), v, Tg, st);
         if (e != cudaSuccess) return cuda_check(e, "node_grad attribute");
     }
-    if (gridE > 0) points_extrap_bwd_kernel<NET><<<gridE, kThreads, 0, st>>>(a, 7 * gridG + gridR);
-    reduce_partials_kernel<<<(np1 + 127) / 128, 128, 0, st>>>(s.partials, rows_needed, np1, s.loss_grad);
+    if (gridE > 0) points_extrap_bwd_kernel<NET><<<gridE, kThreads, 0, st>>>(a, 7 * gridG + gridR, stride);
+    reduce_partials_kernel<<<(stride + 127) / 128, 128, 0, st>>>(s.partials, rows_needed, stride, s.loss_grad);
     return cuda_check(cudaGetLastError(), "points step launch");
 }
 
@@ -2309,6 +2366,14 @@ int nbm_loss_grad_points_f32(const nbm_points_step_t* s, nbm_stream_t stream) {
     NBM_REQUIRE(s->n_irr == 0 || (s->irr_wE && s->irr_c && s->irr_nl && s->irr_nlw), "null irregular-row tables");
     NBM_REQUIRE((s->nonlinear_m == NBM_NL_NONE && s->nonlinear_p == NBM_NL_NONE) || s->nl,
                 "nonlinear operator needs the nl table");
+    if (s->coef26) {
+        NBM_REQUIRE(s->pc_params && s->Pc && s->rows, "the preconditioner needs pc_params, Pc and rows");
+        NBM_REQUIRE(s->n_pc_rows >= 1, "no partial rows for the preconditioner");
+        if (s->pc_d1 != 8 || s->pc_d2 != 4) {
+            set_error("preconditioner widths (%d, %d) are outside the compiled kernel set ((8, 4))", s->pc_d1, s->pc_d2);
+            return NBM_ERR_UNSUPPORTED;
+        }
+    }
     return dispatch_points(*s, as_stream(stream));
 }
 

@@ -527,7 +527,7 @@ class GeneralLevel:
     (the grid displaced by 0, -+dx, -+dy, -+dz), nothing shared between points."""
 
     def __init__(self, lvl: LevelSet, tr_gstate, d, fns, net: NetShape, nonlinear_m: Nonlinear,
-                 nonlinear_p: Nonlinear, device=None):
+                 nonlinear_p: Nonlinear, device=None, precond: Optional[PrecondShape] = None):
         dev = torch.device(device if device is not None else lvl.device)
         self.device, self.net, self.lvl, self.d = dev, net, lvl, tuple(float(v) for v in d)
         self.nonlinear_m, self.nonlinear_p = nonlinear_m, nonlinear_p
@@ -558,7 +558,11 @@ class GeneralLevel:
             irr_c = torch.full((cap * 7,), -1, dtype=torch.int32, device=dev)
             irr_nl = torch.zeros(cap, dtype=torch.uint8, device=dev)
             irr_nlw = torch.zeros(cap, dtype=torch.float32, device=dev)
+            self.precond = precond
+            self.coef26 = torch.zeros(26 * N, dtype=torch.float32, device=dev) if precond is not None else None
+            self.Pc = torch.zeros(N, dtype=torch.float32, device=dev) if precond is not None else None
             a = cabi.Assemble()
+            a.coef26 = cabi.ptr(self.coef26)
             a.pts = _lattice(self.xs, self.ys, self.zs)
             a.dx, a.dy, a.dz = dx, dy, dz
             for i, b in enumerate(lvl.bounds):
@@ -592,9 +596,12 @@ class GeneralLevel:
             self.zs7 = (self.zs[None, :] + sh[:, 2:3]).contiguous()
             self.U7 = torch.zeros(7 * N, dtype=torch.float32, device=dev)
             self.G7 = torch.zeros(7 * N, dtype=torch.float32, device=dev)
-            rows = L.nbm_step_partial_rows()
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            self.n_pc_rows = sms if precond is not None else 0
+            rows = L.nbm_step_partial_rows() + self.n_pc_rows
             self.rows = rows
-            self.partials = torch.zeros(rows * (net.n_params + 1), dtype=torch.float32, device=dev)
+            self.n_total = net.n_params + (precond.n_params if precond is not None else 0)
+            self.partials = torch.zeros(rows * (self.n_total + 1), dtype=torch.float32, device=dev)
 
 
 class PointsPlan:
@@ -603,11 +610,13 @@ class PointsPlan:
 
     def __init__(self, level: GeneralLevel, p0: int, p1: int, n_mean: Optional[int] = None, keep_rows: bool = False):
         self.level, self.p0, self.p1 = level, int(p0), int(p1)
+        keep_rows = keep_rows or level.precond is not None   # the preconditioner kernels exchange the raw residuals
         self.rows = torch.zeros(level.n_points, dtype=torch.float32, device=level.device) if keep_rows else None
         self.device = level.device
         self.n_points = self.p1 - self.p0
         net, cs = level.net, level.sites
-        self.loss_grad = torch.zeros(net.n_params + 1, dtype=torch.float32, device=level.device)
+        self.loss_grad = torch.zeros(level.n_total + 1, dtype=torch.float32, device=level.device)
+        self.n_total, self.precond, self.net = level.n_total, level.precond, net
         s = cabi.PointsStep()
         s.net = net.struct()
         s.nonlinear_m, s.nonlinear_p = level.nonlinear_m.kind, level.nonlinear_p.kind
@@ -628,7 +637,19 @@ class PointsPlan:
         s.rows = cabi.ptr(self.rows)
         s.xs7, s.ys7, s.zs7 = cabi.ptr(level.xs7), cabi.ptr(level.ys7), cabi.ptr(level.zs7)
         s.U7, s.G7 = cabi.ptr(level.U7), cabi.ptr(level.G7)
+        if level.precond is not None:
+            s.coef26, s.Pc = cabi.ptr(level.coef26), cabi.ptr(level.Pc)
+            s.pc_d1, s.pc_d2, s.pc_scale = level.precond.widths[0], level.precond.widths[1], level.precond.scale
+            s.n_pc_rows = level.n_pc_rows
         self.step = s
+
+    def bind_params(self, params: torch.Tensor) -> None:
+        """see SharedPlan.bind_params"""
+        if self.precond is not None:
+            if params.numel() != self.n_total:
+                raise ValueError(f"parameter vector has {params.numel()} entries, expected {self.n_total}")
+            self.step.pc_params = params.data_ptr() + 4 * self.net.n_params
+            self._bound = params
 
     def loss_grad_launch(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if out is not None:

@@ -194,11 +194,16 @@ class Trainer:
         self.nonlinear_p = Nonlinear.coerce(sim_state_fn.nonlinear_op_p)
 
         name = optimizer_dict["optimizer_name"]
+        self.optimizer_name = name
         if name == "lbfgs":
-            raise NotImplementedError("the jaxopt L-BFGS driver (trainer.py:354-427) is outside this path")
-        self.optimizer: OptimizerSpec = get_optimizer(
-            optimizer_name=name, scheduler_name=optimizer_dict["sched"]["scheduler_name"],
-            learning_rate=optimizer_dict["learning_rate"], decay_rate=optimizer_dict["sched"]["decay_rate"])
+            # trainer.py:197-208: no optax chain; solve = solve_jaxopt (scipy L-BFGS-B on the first batch)
+            self.optimizer = None
+            self.solve = self.solve_jaxopt
+        else:
+            self.optimizer: OptimizerSpec = get_optimizer(
+                optimizer_name=name, scheduler_name=optimizer_dict["sched"]["scheduler_name"],
+                learning_rate=optimizer_dict["learning_rate"], decay_rate=optimizer_dict["sched"]["decay_rate"])
+            self.solve = self.solve_optax
 
         with torch.cuda.device(self.device):
             # level set on the lvl grid, read by the kernels through the reference's interpolant
@@ -280,12 +285,8 @@ class Trainer:
                                 self.nonlinear_m, self.nonlinear_p, device=self.device, precond=self.precond)
                 pl.bind_params(self.params)
             else:
-                if self.precond is not None:
-                    raise NotImplementedError(
-                        "the learned preconditioner runs on the shared-evaluation path only (cell size == grid "
-                        "spacing, batches of whole x planes), which is what multi_gpu=True trains on; the single-GPU "
-                        "multi-resolution schedule (data_management.py:320-326) is not covered yet")
                 pl = PointsPlan(self.general_level(zoom), p0, p1)
+                pl.bind_params(self.params)
         self._plans[key] = pl
         return pl
 
@@ -293,7 +294,8 @@ class Trainer:
         if zoom not in self._levels:
             with torch.cuda.device(self.device):
                 self._levels[zoom] = GeneralLevel(self.lvl, self.tr_gstate, self.TD.zoom_cell(zoom), self.sim_state_fn,
-                                                  self.net, self.nonlinear_m, self.nonlinear_p, device=self.device)
+                                                  self.net, self.nonlinear_m, self.nonlinear_p, device=self.device,
+                                                  precond=self.precond)
         return self._levels[zoom]
 
     def _optimizer_struct(self) -> cabi.Optimizer:
@@ -384,7 +386,44 @@ class Trainer:
         final_solution, grad_u, grad_u_normal = self.evaluate_solution_and_gradients(self.params, self.eval_gstate)
         return final_solution, grad_u, grad_u_normal, self.epoch_store, self.loss_epochs
 
-    solve = solve_optax
+    def solve_jaxopt(self):
+        """trainer.py:354-427: `jaxopt.ScipyMinimize(method="l-bfgs-b", fun=self.loss, tol=1e-15,
+        maxiter=num_epochs)` on the FIRST batch at the native cell size.  jaxopt hands scipy a float64 copy of the
+        flattened parameters and a value_and_grad callback; here the callback is the CUDA loss/gradient step
+        (one launch sequence + a 168-float read-back per evaluation), scipy's L-BFGS-B does the rest on the host."""
+        from scipy.optimize import minimize
+        DD = data_management.DatasetDict(num_points=self.tr_gstate.num_points(), batch_size=self.batch_size)
+        p0, p1 = DD.ranges(0)[0]
+        plan = self.plan_for(0, p0, p1)
+        n = self.n_params
+        history = []
+
+        def fun(x):
+            with torch.cuda.device(self.device):
+                self.params.copy_(torch.from_numpy(np.asarray(x, dtype=np.float32)))
+                lg = self.loss_and_grad(self.params, plan).cpu().double().numpy()
+            history.append(float(lg[n]))
+            return float(lg[n]), lg[:n]
+
+        start_time = time.time()
+        with torch.cuda.device(self.device):
+            x0 = self.params.detach().cpu().double().numpy()
+        sol = minimize(fun, x0, jac=True, method="L-BFGS-B", tol=1e-15, options={"maxiter": int(self.num_epochs)})
+        logger.info(f"solve took {time.time() - start_time} (sec)")
+        with torch.cuda.device(self.device):
+            self.params.copy_(torch.from_numpy(sol.x.astype(np.float32)))
+        self.scipy_result = sol
+        self.loss_history = history
+        d = _dist()
+        if d is None or d.get_rank() == 0:
+            self.save_checkpoint(self.checkpoint_dir, {
+                "opt_state": {"fun_val": float(sol.fun), "iter_num": int(sol.nit), "success": bool(sol.success),
+                              "status": int(sol.status)},
+                "params": params_to_tree(self.net, self.params, self.precond), "epoch": int(self.epoch_store[-1]) + 1,
+                "batch_size": self.batch_size, "resolution": f"{self.train_dx}, {self.train_dy}, {self.train_dz}"})
+        final_solution, grad_u, grad_u_normal = self.evaluate_solution_and_gradients(self.params, self.eval_gstate)
+        # like the reference, epoch_store / loss_epochs are returned as initialised (trainer.py:260-263, 421-427)
+        return final_solution, grad_u, grad_u_normal, self.epoch_store, self.loss_epochs
 
     def single_GPU_train(self):
         """trainer.py:501-591: epochs x batches, cell size halves every num_epochs//4 epochs

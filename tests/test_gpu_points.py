@@ -10,7 +10,7 @@ from test_gpu_shared import DEV, TOL_LOSS, TOL_ROW, build, fns_of
 pytestmark = pytest.mark.gpu
 
 
-def general(problem, n_train, n_lvl, zoom, interp="trilinear"):
+def general(problem, n_train, n_lvl, zoom, interp="trilinear", precond=None):
     tr, lv, phi_grid, oprob = util.make_case(problem, n_train, n_lvl, interp, torch.float64)
     lvl = nplan.LevelSet(lv, phi_grid, interp=interp, perturb_eps=1e-10, device=DEV)
     shape = nplan.NetShape()
@@ -19,7 +19,7 @@ def general(problem, n_train, n_lvl, zoom, interp="trilinear"):
     d32 = [float(torch.tensor(float(v), dtype=torch.float32) * torch.tensor(0.5 ** zoom, dtype=torch.float32))
            for v in (tr.dx, tr.dy, tr.dz)]
     level = nplan.GeneralLevel(lvl, tr, d32, fns_of(problem), shape, nplan.Nonlinear.coerce(problem.nonlinear_op_m),
-                               nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=DEV)
+                               nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=DEV, precond=precond)
     return tr, oprob, level, shape, d32
 
 
@@ -133,9 +133,68 @@ def test_multi_gpu_loop_with_learned_preconditioner_follows_the_oracle():
     tree = ntrainer.params_to_tree(T.net, T.params, T.precond)
     assert tree["preconditioner"]["params"]["Dense_0"]["kernel"].shape == (26, 8)
     assert torch.equal(ntrainer.tree_to_params(T.net, tree, T.precond), T.params.cpu())
-    # the single-GPU multi-resolution loop does not take the preconditioner yet: loud, typed failure
-    with pytest.raises(NotImplementedError):
-        _solve(P, n_tr, n_lvl, 8, 8, 256, p0.float(), optimizer_dict=od, model_dict=md)
+    # the single-GPU loop (4 zoom levels x 2 epochs, 2 batches: shared path at zoom 0, general path above)
+    p_s, losses_s = O.single_gpu_train(p0.clone(), tr.R.double(), grid_d, oprob, num_epochs=8, batch_size=256,
+                                       optimizer_dict=od)
+    (state, _, loss_epochs), T, _ = _solve(P, n_tr, n_lvl, 8, 8, 256, p0.float(), optimizer_dict=od, model_dict=md)
+    lk = torch.as_tensor(loss_epochs).double()
+    lo = torch.tensor(losses_s, dtype=torch.float64)
+    assert ((lk - lo).abs() / lo).max() < 1e-3, (lk, lo)
+    assert util.rel_inf(T.params.cpu(), p_s) < 1e-3
+
+
+@pytest.mark.parametrize("name,zoom", [("sphere", 1), ("star", 2)])
+def test_general_path_with_learned_preconditioner(name, zoom):
+    """loss, network gradient and preconditioner gradient of the per-point path (cell size = spacing / 2^zoom)"""
+    P = problems.PROBLEMS[name]()
+    dt = torch.float64
+    tr, oprob, level, shape, d32 = general(P, 12, 32, zoom, precond=nplan.PrecondShape((8, 4), 1.0))
+    oprob.precond = O.PrecondShape((8, 4), 1.0)
+    n = tr.num_points()
+    pp = O.init_precond_params(oprob.precond, seed=5, dtype=dt)
+    pp[:26 * 8] *= 60.0
+    params = torch.cat((O.init_params(oprob.shape, seed=11, dtype=dt), pp))
+    dd = [torch.tensor(v, dtype=dt) for v in d32]
+    for (a, b) in ((0, n), (n // 3, n // 3 + 700)):
+        pl = nplan.PointsPlan(level, a, b)
+        loss_o, grad_o = O.loss_and_grad(params, tr.R.to(dt)[a:b], *dd, oprob)
+        p_dev = params.float().to(DEV)
+        with torch.cuda.device(DEV):
+            nplan.upload_params(shape, p_dev)
+            pl.bind_params(p_dev)
+            lg = pl.loss_grad_launch().cpu()
+        assert lg.numel() == params.numel() + 1
+        assert abs(float(lg[-1]) - float(loss_o)) / float(loss_o) < TOL_LOSS
+        k = shape.n_params
+        assert util.rel_inf(lg[:k], grad_o[:k]) < TOL_LOSS
+        assert util.rel_inf(lg[k:-1], grad_o[k:]) < TOL_LOSS
+
+
+def test_lbfgs_driver_minimises_the_first_batch():
+    """optimizer_name "lbfgs" (trainer.py:197-208, 354-427): scipy L-BFGS-B, maxiter = num_epochs, on the first batch
+    at the native cell size, driven by the CUDA loss/gradient.  The same scipy call on the oracle's float64
+    loss/gradient gives the reference trajectory."""
+    from scipy.optimize import minimize
+    P = problems.no_jump()
+    n_tr, n_lvl = 8, 12
+    tr, lv, phi_grid, oprob = util.make_case(P, n_tr, n_lvl, "trilinear", torch.float64)
+    p0 = O.init_params(oprob.shape, seed=42, dtype=torch.float64)
+    od = {"optimizer_name": "lbfgs", "learning_rate": 1e-2, "sched": {"scheduler_name": "exponential", "decay_rate": 0.975}}
+    (state, epoch_store, loss_epochs), T, _ = _solve(P, n_tr, n_lvl, 8, 15, 512, p0.float(), optimizer_dict=od)
+    assert T.scipy_result.nit <= 15 and len(T.loss_history) >= 2
+    assert T.loss_history[-1] < 0.2 * T.loss_history[0]
+    d = [tr.dx.double(), tr.dy.double(), tr.dz.double()]
+
+    def fun(x):
+        l, g = O.loss_and_grad(torch.from_numpy(x), tr.R.double(), *d, oprob)
+        return float(l), g.numpy()
+
+    l0, _ = fun(p0.numpy())
+    assert abs(T.loss_history[0] - l0) / l0 < 1e-4
+    sol = minimize(fun, p0.numpy(), jac=True, method="L-BFGS-B", tol=1e-15, options={"maxiter": 15})
+    # the fp32 and fp64 line searches take the same path for the first iterations: same order of magnitude at the end
+    assert 0.2 < float(T.scipy_result.fun) / float(sol.fun) < 5.0
+    assert state.solution.shape[0] == 8 ** 3
 
 
 def test_training_reduces_the_error_against_the_exact_solution():

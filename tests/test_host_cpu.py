@@ -183,3 +183,25 @@ def test_two_rank_partition_and_psum_over_gloo():
     # and it is NOT the global mean: psum of means = world_size x the single-device mean gradient
     l1, g1 = O.loss_and_grad(params, tr.R.double(), *d, op)
     assert np.allclose(buf[:-1], 2 * g1.numpy(), rtol=1e-9, atol=1e-14)
+
+
+def test_vtk_writer_roundtrip(tmp_path):
+    """write_vtk_manual (jax_dips/utils/io.py:80-89): VTK XML StructuredGrid with appended raw data, x fastest,
+    fields given flat in the grid's z-fastest order."""
+    from jax_dips_b200 import io as nio
+    g = mesh.linspace_grid((-1.0, 0.0, 2.0), (1.0, 3.0, 4.0), [4, 5, 6])
+    R = g.R
+    sol = (R[:, 0] + 10.0 * R[:, 1] + 100.0 * R[:, 2]).float()
+    phi = (R ** 2).sum(1).double()
+    path = nio.write_vtk_manual(g, {"sol": sol, "phi": phi}, filename=str(tmp_path / "out" / "dump"))
+    assert path.endswith("dump.vts") and os.path.exists(path)
+    pts, fields = nio.read_vts(path)
+    assert pts.shape == (4 * 5 * 6, 3) and set(fields) == {"sol", "phi"}
+    # VTK point order is x fastest; point data must follow it
+    P = pts.reshape(6, 5, 4, 3)                     # (k, j, i, xyz)
+    assert np.allclose(P[0, 0, :, 0], g.x.numpy()) and np.allclose(P[0, :, 0, 1], g.y.numpy())
+    want = (pts[:, 0] + 10.0 * pts[:, 1] + 100.0 * pts[:, 2]).reshape(6, 5, 4).transpose(2, 1, 0)
+    assert np.allclose(fields["sol"], want, rtol=1e-6)
+    assert fields["phi"].dtype == np.float64
+    head = open(path, "rb").read(200).decode("ascii", "replace")
+    assert 'type="StructuredGrid"' in head and 'header_type="UInt64"' in head
