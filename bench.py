@@ -30,7 +30,13 @@ UNIT = "points/s"
 # default net p(3-10-10-1) | m(3-1-1), shared evaluation at native spacing
 F_STEP = 1.0e3        # FLOP per point for the whole step (fwd 0.38k + bwd 0.55k + stencil 0.06k)
 F_GRAD = 0.93e3       # FLOP per lattice node for the dominant kernel (forward recompute 0.38k + backward 0.55k)
-B_STEP = 64.0         # bytes per point streamed by the step (row table 7 w + rhs = 32 B read twice)
+# bytes per lattice node streamed by the two stencil passes: with the face table the residual
+# pass moves cface 12 + dinv 4 + rhs 4 + U 4 + R 4 = 28 B and the adjoint pass cface 12 + dinv 4 + R 4 + G 4 = 24 B;
+# with the 7-weight row table 40 B + 36 B (SURVEY section 8(d) quotes 64 B/point for a streamed K2 table)
+B_STEP_FACES = 52.0
+B_STEP_ROWS = 76.0
+# DRAM bytes (read + write) of one node_grad launch at 256^3, `ncu --set full` (profiles/r1_ncu_summary.md)
+NODE_GRAD_TRAFFIC_256 = 161860608   # 155.8 MB read + 6.0 MB written (profiles/r1b_ncu_summary.md)
 
 
 def parse():
@@ -297,7 +303,8 @@ def main():
             step = eager_step
             torch.cuda.synchronize()
 
-    launches_per_step = 5 + (1 if pl.sites.n > 0 else 0) * 2 + (1 if pl.n_irr > 0 else 0) * 2 + 1  # + update kernel
+    # prep_params, fwd_nodes, residual, adjoint, node_grad, reduce, apply_update (+ 2 list kernels each for crossed sites / irregular rows)
+    launches_per_step = 7 + (1 if pl.sites.n > 0 else 0) * 2 + (1 if pl.n_irr > 0 else 0) * 2
 
     # ---------------- value: device-resident inputs -------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -396,22 +403,26 @@ def main():
         ne = pl.ne
         ach = F_GRAD * ne / (stage_ms["node_grad"] * 1e-3) / 1e12
         step_ach = F_STEP * (pl.n_points) / ((ms / args.steps) * 1e-3) / 1e12
+        b_step = B_STEP_FACES if pl.faces else B_STEP_ROWS
+        traffic = NODE_GRAD_TRAFFIC_256 if (args.workload == "sphere" and args.grid == 256 and world == 1) else None
         roof = {"bound": "fp32", "kernel": "node_grad_kernel", "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s",
-                "frac": ach / ffma_peak if ffma_peak else None, "traffic": None,
+                "frac": ach / ffma_peak if ffma_peak else None, "traffic": traffic,
                 "peak_source": "FFMA probe kernel run in this process (MEASURED_PEAKS.json has no FP32 figure; "
                                "nominal 148 SM x 128 x 2 x 1.965 GHz = 74.5)",
                 "algorithmic_flop_per_node": F_GRAD, "nodes_per_launch": ne,
                 "stage_ms": stage_ms,
                 "step": {"achieved": step_ach, "frac": step_ach / ffma_peak if ffma_peak else None,
                          "algorithmic_flop_per_point": F_STEP},
-                "hbm": {"achieved": B_STEP * pl.n_points / ((stage_ms["residual"] + stage_ms["adjoint"]) * 1e-3) / 1e9,
+                "hbm": {"achieved": b_step * ne / ((stage_ms["residual"] + stage_ms["adjoint"]) * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s", "kernels": "residual + adjoint",
+                        "algorithmic_bytes_per_node": b_step,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"}}
         roof["hbm"]["frac"] = roof["hbm"]["achieved"] / hbm_peak
         if not args.no_cpu_baseline and world == 1:
             r = cpu_baseline(problem, args, args.cpu_sample, steps=1, warmup=1)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    table_mb = pl.ne * ((16 if pl.faces else 28) + 4 + 1 + 12) / 1e6
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -420,7 +431,9 @@ def main():
                                        f"x-slabs of {per} planes per GPU), level set on {args.lvl}^3 lvl grid "
                                        f"({args.interp}), MLP p 3-10-10-1 | m 3-1-1 tanh, optimizer custom(adam), "
                                        "one batch per GPU",
-                           "l2": "row tables (553 MB at 256^3) exceed the 126 MB L2; no flush needed",
+                           "l2": f"row tables + work arrays ({table_mb:.0f} MB per GPU) exceed the 126 MB L2; no flush needed",
+                           "row_table": "faces (3 face coefficients + 1/diag per node)" if pl.faces else "7 row weights per node",
+                           "adjoint": "fused into the gradient kernel (TMA ring)" if pl.fused else "separate stencil pass",
                            "cuda_graph": used_graph,
                            "allreduce": ("peer-memory kernel fused with the partial reduction" if comm is not None
                                          else ("nccl" if world > 1 else "none")),

@@ -1704,13 +1704,17 @@ __global__ void __launch_bounds__(kThreads) precond_fwd_kernel(const float* __re
     }
 }
 
-// K4a: deterministic sum of the per-CTA partial rows
+// K4a: deterministic sum of the per-CTA partial rows: one warp per column, lane l adds rows l, l + 32, ... in order,
+// then a fixed shuffle tree (the row count and therefore the summation order depend only on the launch geometry)
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int rows, int np1, float* __restrict__ out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (i >= np1) return;
     float v = 0.0f;
-    for (int r = 0; r < rows; ++r) v += partials[(size_t)r * np1 + i];
-    out[i] = v;
+    for (int r = lane; r < rows; r += 32) v += partials[(size_t)r * np1 + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) out[i] = v;
 }
 
 // K4b: optax chain (solvers/optimizers.py:33-54, optax 0.1.5 semantics), one CTA
@@ -1998,7 +2002,7 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
         if (e != cudaSuccess) return cuda_check(e, "node_grad attribute");
     }
     if (stages & NBM_STAGE_REDUCE)
-        reduce_partials_kernel<<<(pc_stride + 127) / 128, 128, 0, st>>>(s.partials, gridC + gridP, pc_stride, s.loss_grad);
+        reduce_partials_kernel<<<(pc_stride * 32 + 127) / 128, 128, 0, st>>>(s.partials, gridC + gridP, pc_stride, s.loss_grad);
     return cuda_check(cudaGetLastError(), "shared step launch");
 }
 
@@ -2261,7 +2265,7 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
         if (e != cudaSuccess) return cuda_check(e, "node_grad attribute");
     }
     if (gridE > 0) points_extrap_bwd_kernel<NET><<<gridE, kThreads, 0, st>>>(a, 7 * gridG + gridR, stride);
-    reduce_partials_kernel<<<(stride + 127) / 128, 128, 0, st>>>(s.partials, rows_needed, stride, s.loss_grad);
+    reduce_partials_kernel<<<(stride * 32 + 127) / 128, 128, 0, st>>>(s.partials, rows_needed, stride, s.loss_grad);
     return cuda_check(cudaGetLastError(), "points step launch");
 }
 
