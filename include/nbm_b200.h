@@ -344,9 +344,10 @@ int nbm_apply_update_f32(const nbm_optimizer_t* opt, const float* loss_grad, flo
  *
  * Every rank owns one small communication block (allocated by the library with cudaMalloc because it
  * must be exportable through CUDA IPC); the blocks of all ranks of the node are mapped into every
- * process.  One single-CTA kernel per rank: sum the per-CTA partial rows -> store [grad, loss] into the
- * own block (slot = step parity) -> release a step flag -> acquire the flags of all peers -> read all
- * slots over NVLink and add them in rank order (bitwise identical result on every rank) -> out.
+ * process.  One single-CTA kernel per rank: sum the per-CTA partial rows -> PUSH [grad, loss] into this rank's
+ * slot of EVERY rank's block over NVLink (slot = step parity; remote stores do not wait) -> fence -> raise this
+ * rank's step flag in every block -> poll the LOCAL flags of all peers -> add the local slots in rank order
+ * (bitwise identical result on every rank) -> out.
  * A spin that lasts longer than ~2 s sets comm error state instead of hanging (nbm_comm_error()).
  * ---------------------------------------------------------------------------------------- */
 #define NBM_IPC_HANDLE_BYTES 64
@@ -359,7 +360,7 @@ int nbm_comm_close_peer(void* peer_block);
 int nbm_comm_free(void* local_block);
 /* blocks_host[world]: device pointers of all ranks' blocks as seen from THIS process (own block at [rank]).
  * partials[rows][np1]; step_dev: device int32 step counter of this rank (starts at 0, incremented here);
- * out[np1] receives the sum over ranks.  np1 <= 1025. */
+ * out[np1] receives the sum over ranks.  np1 <= 1024. */
 int nbm_reduce_allreduce_f32(const float* partials, int rows, int np1, int rank, int world,
                              void* const* blocks_host, int32_t* step_dev, float* out, nbm_stream_t stream);
 /* nonzero once a peer wait timed out on this device's block (host read of the block's error word) */

@@ -1827,10 +1827,10 @@ __global__ void prep_params_kernel(nbm_net_t net, const float* __restrict__ para
 // fused partial-row reduction + all-reduce over NVLink peer memory (one process per GPU, CUDA IPC)
 // ---------------------------------------------------------------------------------------------
 struct CommBlock {
-    unsigned int flag[2];   // step+1 of the last slot written, per parity
-    unsigned int error;     // set when a peer wait timed out
-    unsigned int pad;
-    float data[2][NBM_MAXP + 8];
+    unsigned int flag[2][NBM_COMM_MAX_RANKS];   // [parity][source rank]: step + 1 of the last slot that rank pushed here
+    unsigned int error;                         // set when a peer wait timed out
+    unsigned int pad[3];
+    float data[2][NBM_COMM_MAX_RANKS][NBM_MAXP + 8];   // [parity][source rank][entry], written by the source rank
 };
 
 struct CommPeers {
@@ -1851,28 +1851,42 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
     return v;
 }
 
+// One CTA.  (1) deterministic sum of the partial rows (row groups in parallel, fixed order);  (2) PUSH: every rank stores
+// its [grad, loss] vector into its slot of EVERY rank's block (remote stores over NVLink are fire-and-forget), fences,
+// then raises its flag in every block;  (3) each rank polls only its LOCAL flags and adds the slots in rank order, so the
+// result is bitwise identical on all ranks.  Slots are double-buffered by step parity: a peer can be at most one step
+// ahead (it cannot finish step k+1 before this rank has raised its k+1 flags, which happens after step k's reads).
 __global__ void __launch_bounds__(1024) reduce_allreduce_kernel(const float* __restrict__ partials, int rows, int np1,
                                                                 int rank, int world, CommPeers peers,
                                                                 int32_t* __restrict__ step_dev, float* __restrict__ out) {
-    const int i = threadIdx.x;
+    extern __shared__ float sred[];   // [ngrp][np1]
+    const int t = threadIdx.x;
     const unsigned int step = (unsigned int)*step_dev;
     const int par = step & 1;
     CommBlock* mine = peers.b[rank];
-    if (i < np1) {
+    const int ngrp = max(1, (int)blockDim.x / np1);
+    {
+        const int grp = t / np1, col = t - grp * np1;
+        if (grp < ngrp) {
+            float v = 0.0f;
+            for (int r = grp; r < rows; r += ngrp) v += partials[(size_t)r * np1 + col];
+            sred[grp * np1 + col] = v;
+        }
+    }
+    __syncthreads();
+    if (t < np1) {
         float v = 0.0f;
-        for (int r = 0; r < rows; ++r) v += partials[(size_t)r * np1 + i];
-        mine->data[par][i] = v;
+        for (int g = 0; g < ngrp; ++g) v += sred[g * np1 + t];
+        for (int r = 0; r < world; ++r) peers.b[r]->data[par][rank][t] = v;
     }
     __threadfence_system();
     __syncthreads();
     __shared__ int s_fail;
-    if (i == 0) {
-        s_fail = 0;
-        st_release_sys(&mine->flag[par], step + 1);
-    }
-    // one waiting thread per peer
-    if (i > 0 && i <= world && (i - 1) != rank) {
-        const unsigned int* f = &peers.b[i - 1]->flag[par];
+    if (t == 0) s_fail = 0;
+    if (t < world) st_release_sys(&peers.b[t]->flag[par][rank], step + 1);
+    __syncthreads();
+    if (t < world && t != rank) {
+        const unsigned int* f = &mine->flag[par][t];
         long long t0 = clock64();
         while ((int)(ld_acquire_sys(f) - (step + 1)) < 0) {
             if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz: report instead of hanging the device
@@ -1883,14 +1897,13 @@ __global__ void __launch_bounds__(1024) reduce_allreduce_kernel(const float* __r
         }
     }
     __syncthreads();
-    __threadfence_system();
-    if (i < np1) {
+    if (t < np1) {
         float v = 0.0f;
-        for (int r = 0; r < world; ++r) v += (r == rank) ? mine->data[par][i] : ld_relaxed_sys(&peers.b[r]->data[par][i]);
-        out[i] = s_fail ? __int_as_float(0x7fc00000) : v;
+        for (int r = 0; r < world; ++r) v += ld_relaxed_sys(&mine->data[par][r][t]);
+        out[t] = s_fail ? __int_as_float(0x7fc00000) : v;
     }
     __syncthreads();
-    if (i == 0) *step_dev = (int32_t)(step + 1);
+    if (t == 0) *step_dev = (int32_t)(step + 1);
 }
 
 static int g_sm_count = 0;
@@ -2424,8 +2437,11 @@ int nbm_reduce_allreduce_f32(const float* partials, int rows, int np1, int rank,
     CommPeers peers;
     for (int r = 0; r < NBM_COMM_MAX_RANKS; ++r) peers.b[r] = r < world ? reinterpret_cast<CommBlock*>(blocks_host[r]) : nullptr;
     for (int r = 0; r < world; ++r) NBM_REQUIRE(peers.b[r], "null peer block");
-    int threads = ((max(np1, world + 1) + 31) / 32) * 32;
-    reduce_allreduce_kernel<<<1, threads, 0, as_stream(stream)>>>(partials, rows, np1, rank, world, peers, step_dev, out);
+    const int threads = 1024;   // np1 <= 1025 columns... one column per thread in the last phase needs np1 <= 1024
+    NBM_REQUIRE(np1 <= 1024, "np1 must be <= 1024");
+    const int ngrp = threads / np1 > 0 ? threads / np1 : 1;
+    reduce_allreduce_kernel<<<1, threads, sizeof(float) * (size_t)ngrp * np1, as_stream(stream)>>>(partials, rows, np1, rank,
+                                                                                                 world, peers, step_dev, out);
     NBM_LAUNCH_CHECK("reduce_allreduce");
     return NBM_OK;
 }
