@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--faces", type=int, default=-1, help="1/0: face-coefficient row table on/off (default: auto)")
     ap.add_argument("--fused", type=int, default=-1, help="1/0: adjoint stencil fused into the gradient kernel (default: auto)")
+    ap.add_argument("--emulate", default="", help="R/W: on ONE GPU, time the slab rank R would own in a W-GPU weak-scaling "
+                                                  "run (load-balance diagnosis; not a bench line)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=12288)
     return ap.parse_args()
@@ -201,11 +203,12 @@ def main():
     L = cabi.lib()
 
     problem = make_problem(args.workload)
-    tr, lv = grids(problem, args, world)
+    emu = tuple(int(v) for v in args.emulate.split("/")) if args.emulate else None
+    tr, lv = grids(problem, args, emu[1] if emu else world)
     fns = sim_fns(problem)
     Nx, Ny, Nz = tr.shape()
-    per = Nx // world
-    xa, xb = rank * per, (rank + 1) * per
+    per = Nx // (emu[1] if emu else world)
+    xa, xb = (emu[0] if emu else rank) * per, ((emu[0] if emu else rank) + 1) * per
     net = nplan.NetShape()
     P = net.n_params
     phi_lvl = fns.phi_fn(lv.R.to(dev))
