@@ -380,13 +380,23 @@ class SharedPlan:
             if n_irr > cap:
                 raise cabi.NbmError(f"irregular-row capacity exceeded ({n_irr} > {cap})")
             self.n_irr = n_irr
-            self.irr_wU = irr_wU[:max(n_irr, 1) * 7].clone() if self.faces else None
-            self.irr_rhs = irr_rhs[:max(n_irr, 1)].clone() if self.faces else None
-            self.irr_point = irr_point[:max(n_irr, 1)].clone()
-            self.irr_wE = irr_wE[:max(n_irr, 1) * 7].clone()
-            self.irr_c = irr_c[:max(n_irr, 1) * 7].clone()
-            self.irr_nl = irr_nl[:max(n_irr, 1)].clone()
-            self.irr_nlw = irr_nlw[:max(n_irr, 1)].clone()
+            # the assembly kernel appends irregular rows in atomic order: sort them by lattice node so that the list
+            # kernels touch U / R / G with locality (and the order, hence the fp32 atomics' operands, is reproducible)
+            m = max(n_irr, 1)
+            perm = torch.argsort(irr_point[:n_irr]) if n_irr > 1 else torch.arange(m, device=dev)
+            take = lambda t, w=1: (t[:m * w].view(m, w)[perm].reshape(-1).contiguous() if n_irr > 1 else t[:m * w].clone())
+            self.irr_wU = take(irr_wU, 7) if self.faces else None
+            self.irr_rhs = take(irr_rhs) if self.faces else None
+            self.irr_point = take(irr_point)
+            self.irr_wE = take(irr_wE, 7)
+            self.irr_c = take(irr_c, 7)
+            self.irr_nl = take(irr_nl)
+            self.irr_nlw = take(irr_nlw)
+            if n_irr > 1:   # lattice node -> slot map follows the permutation
+                inv = torch.empty_like(perm)
+                inv[perm] = torch.arange(n_irr, device=dev)
+                has = irr >= 0
+                irr[has] = inv[irr[has].long()].to(torch.int32)
             self.irr = irr
             del mu_m_faces, mu_p_faces, k_m, k_p, f_m, f_p, g_dir
             if self.fused and precond is not None:
