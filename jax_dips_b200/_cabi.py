@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnbm_b200.so")
+# NBM_B200_LIB: load another build of the same ABI (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("NBM_B200_LIB") or os.path.join(_HERE, "libnbm_b200.so")
 
 c_f = C.c_float
 c_fp = C.c_void_p  # all device pointers travel as void*

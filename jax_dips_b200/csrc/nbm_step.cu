@@ -186,13 +186,13 @@ __device__ __forceinline__ u64 cpair(int idx) { return *reinterpret_cast<const u
 // (tanh is 1 to the last bit far below that).
 __device__ __forceinline__ u64 tanh2_prescaled(u64 sp) {
     float s0 = fminf(lo32(sp), 63.0f), s1 = fminf(hi32(sp), 63.0f);
-    float e0, e1, r;
+    float e0, e1, m;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
-    u64 a = fadd2(pk(e0, e1), pk(1.0f, 1.0f));
-    float a0 = lo32(a), a1 = hi32(a);
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a0 * a1));
-    return ffma2(pk(-2.0f, -2.0f), pk(r * a1, r * a0), pk(1.0f, 1.0f));
+    // A = (a1, -a0/2) with a = e + 1;  m = 1 / (lo hi) = -2 / (a0 a1);  t = 1 + (m, -2m) A = (1 - 2/a0, 1 - 2/a1)
+    const u64 A = ffma2(pk(e1, e0), pk(1.0f, -0.5f), pk(1.0f, -0.5f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(lo32(A) * hi32(A)));
+    return ffma2(pk(m, -2.0f * m), A, pk(1.0f, 1.0f));
 }
 
 // Packed head: H even, OFF even.  Accumulators are pairs: accp[k] = (grad[2k], grad[2k+1]).
@@ -300,14 +300,14 @@ struct MlpP {
                                                     u64 (&acc)[NPAIR]) {
         static_assert(OFF == 0, "packed accumulators are indexed from the head's own origin");
         const int oo = 4 * H + (L - 1) * (H * H + H);
-        const u64 one = pk(1.0f, 1.0f);
-        const u64 g2 = pk(g, g);
+        const u64 mone = pk(-1.0f, -1.0f);
+        const u64 g2 = pk(g, g), g2n = pk(-g, -g);
         u64 d[HP];
 #pragma unroll
         for (int j = 0; j < HP; ++j) {
             acc[(oo + 2 * j) / 2] = ffma2(a[L - 1][j], g2, acc[(oo + 2 * j) / 2]);
-            u64 om = ffma2(neg2(a[L - 1][j]), a[L - 1][j], one);
-            d[j] = fmul2(fmul2(cpair(oo + 2 * j), g2), om);
+            u64 omn = ffma2(a[L - 1][j], a[L - 1][j], mone);          // a^2 - 1
+            d[j] = fmul2(fmul2(cpair(oo + 2 * j), g2n), omn);         // W g (1 - a^2)
         }
         acc[(oo + H) / 2] = fadd2(acc[(oo + H) / 2], pk(g, 0.0f));
 #pragma unroll
@@ -336,9 +336,9 @@ struct MlpP {
                 for (int ip = 0; ip < HP; ++ip) dn[ip] = ffma2(cpair(2 * NBM_MAXP + o + j * H + 2 * ip), dj2, dn[ip]);
             }
 #pragma unroll
-            for (int ip = 0; ip < HP; ++ip) {
-                u64 om = ffma2(neg2(a[l - 1][ip]), a[l - 1][ip], one);
-                dn[ip] = fmul2(dn[ip], om);
+            for (int ip = 0; ip < HP; ++ip) {   // dn = -(W delta) from the negated transposed copy
+                u64 omn = ffma2(a[l - 1][ip], a[l - 1][ip], mone);
+                dn[ip] = fmul2(dn[ip], omn);
             }
 #pragma unroll
             for (int j = 0; j < HP; ++j) d[j] = dn[j];
@@ -414,14 +414,14 @@ struct MlpP {
             for (int j = 0; j < HP; ++j) a[l][j] = tanh2_prescaled(acc[j]);
         }
         const int oo = 4 * H + (L - 1) * (H * H + H);
-        const u64 one = pk(1.0f, 1.0f);
-        const u64 g2 = pk(g, g);
+        const u64 mone = pk(-1.0f, -1.0f);
+        const u64 g2 = pk(g, g), g2n = pk(-g, -g);
         u64 d[HP];
 #pragma unroll
         for (int j = 0; j < HP; ++j) {
             A.w3[j] = ffma2(a[L - 1][j], g2, A.w3[j]);
-            u64 om = ffma2(neg2(a[L - 1][j]), a[L - 1][j], one);
-            d[j] = fmul2(fmul2(cpair(oo + 2 * j), g2), om);
+            u64 omn = ffma2(a[L - 1][j], a[L - 1][j], mone);          // a^2 - 1
+            d[j] = fmul2(fmul2(cpair(oo + 2 * j), g2n), omn);         // W g (1 - a^2)
         }
         A.b3 += g;
 #pragma unroll
@@ -455,9 +455,9 @@ struct MlpP {
                 for (int ip = 0; ip < HP; ++ip) dn[ip] = ffma2(cpair(2 * NBM_MAXP + o + j * H + 2 * ip), dj2, dn[ip]);
             }
 #pragma unroll
-            for (int ip = 0; ip < HP; ++ip) {
-                u64 om = ffma2(neg2(a[l - 1][ip]), a[l - 1][ip], one);
-                d[ip] = fmul2(dn[ip], om);
+            for (int ip = 0; ip < HP; ++ip) {   // dn = -(W delta) from the negated transposed copy
+                u64 omn = ffma2(a[l - 1][ip], a[l - 1][ip], mone);
+                d[ip] = fmul2(dn[ip], omn);
             }
         }
 #pragma unroll
@@ -1823,13 +1823,18 @@ __global__ void prep_params_kernel(nbm_net_t net, const float* __restrict__ para
     int hidden_len = 4 * H + (Lh - 1) * (H * H + H);  // everything before the output layer
     stage[i] = v;
     stage[NBM_MAXP + i] = k < hidden_len ? v * kTwoLog2e : v;
-    // third copy: hidden HxH matrices transposed in place
+    // third copy: hidden HxH matrices transposed in place AND negated: the backward pass forms (a^2 - 1) = -(1 - a^2)
+    // with one FFMA2 (no sign flips) and gets the sign back from -W^T
     int dst = i;
+    float v3 = v;
     if (k >= 4 * H && k < hidden_len) {
         int q = (k - 4 * H) % (H * H + H);
-        if (q < H * H) dst = i - q + (q % H) * H + q / H;
+        if (q < H * H) {
+            dst = i - q + (q % H) * H + q / H;
+            v3 = -v;
+        }
     }
-    stage[2 * NBM_MAXP + dst] = v;
+    stage[2 * NBM_MAXP + dst] = v3;
 }
 
 
