@@ -195,6 +195,18 @@ __device__ __forceinline__ u64 tanh2_prescaled(u64 sp) {
     return ffma2(pk(m, -2.0f * m), A, pk(1.0f, 1.0f));
 }
 
+// Variant for kernels with MUFU head-room (node_grad: XU pipe ~30 % busy): one reciprocal per element instead of a
+// shared one.  4 MUFU per pair instead of 3, but 6 instructions instead of 9 and no clamp: rcp(inf) = 0 gives t = 1.
+__device__ __forceinline__ u64 tanh2_prescaled_4mufu(u64 sp) {
+    float e0, e1, r0, r1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(lo32(sp)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(hi32(sp)));
+    const u64 a = fadd2(pk(e0, e1), pk(1.0f, 1.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(lo32(a)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(hi32(a)));
+    return ffma2(pk(r0, r1), pk(-2.0f, -2.0f), pk(1.0f, 1.0f));
+}
+
 // Packed head: H even, OFF even.  Accumulators are pairs: accp[k] = (grad[2k], grad[2k+1]).
 template <int L, int H>
 struct MlpP {
@@ -396,7 +408,7 @@ struct MlpP {
         u64 a[L][HP];
         const u64 x2 = pk(x, x);
 #pragma unroll
-        for (int j = 0; j < HP; ++j) a[0][j] = tanh2_prescaled(ffma2(x2, cpair(S + 2 * j), yz[j]));
+        for (int j = 0; j < HP; ++j) a[0][j] = tanh2_prescaled_4mufu(ffma2(x2, cpair(S + 2 * j), yz[j]));
 #pragma unroll
         for (int l = 1; l < L; ++l) {
             const int o = S + 4 * H + (l - 1) * (H * H + H);
@@ -411,7 +423,7 @@ struct MlpP {
                 for (int j = 0; j < HP; ++j) acc[j] = ffma2(ai2, cpair(o + i * H + 2 * j), acc[j]);
             }
 #pragma unroll
-            for (int j = 0; j < HP; ++j) a[l][j] = tanh2_prescaled(acc[j]);
+            for (int j = 0; j < HP; ++j) a[l][j] = tanh2_prescaled_4mufu(acc[j]);
         }
         const int oo = 4 * H + (L - 1) * (H * H + H);
         const u64 mone = pk(-1.0f, -1.0f);
