@@ -440,18 +440,19 @@ struct MlpP {
         for (int l = L - 1; l >= 1; --l) {
             const int o = 4 * H + (l - 1) * (H * H + H);
             u64 dP[HP];
-            float aown[HP], apart[HP];
 #pragma unroll
             for (int j = 0; j < HP; ++j) {
                 A.b2[l - 1][j] = fadd2(A.b2[l - 1][j], d[j]);
                 dP[j] = shfl1(d[j]);
-                const float lo = lo32(a[l - 1][j]), hi = hi32(a[l - 1][j]);
-                aown[j] = par ? hi : lo;
-                apart[j] = __shfl_xor_sync(0xffffffffu, par ? lo : hi, 1);
             }
 #pragma unroll
             for (int k = 0; k < HP; ++k) {
-                const u64 ao = pk(aown[k], aown[k]), ap = pk(apart[k], apart[k]);
+                // my row 2k + par of this layer's outer product: my activation and the partner's (selected and
+                // exchanged right where they are used: no staging arrays)
+                const float lo = lo32(a[l - 1][k]), hi = hi32(a[l - 1][k]);
+                const float aown = par ? hi : lo;
+                const float apart = __shfl_xor_sync(0xffffffffu, par ? lo : hi, 1);
+                const u64 ao = pk(aown, aown), ap = pk(apart, apart);
 #pragma unroll
                 for (int j = 0; j < HP; ++j)
                     A.w2[l - 1][k][j] = ffma2(ap, dP[j], ffma2(ao, d[j], A.w2[l - 1][k][j]));
@@ -1120,21 +1121,34 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
         u64 yz[HP2];
         P::template first_layer_yz<0>(y, z, yz);
         const int x0 = v.x_begin + xc * T.xchunk, x1 = min(v.x_end, x0 + T.xchunk);
-        // software pipeline: the loads of plane ix+1 are in flight while plane ix is computed
+        // software pipeline: the loads of plane ix+1 are in flight while plane ix is computed; running pointers, one
+        // add per array and plane
         int64_t e = (int64_t)x0 * T.plane + m;
+        const float* gp = G + e;
+        const float* rp = (GENERAL || !R) ? nullptr : R + e;
+        const uint8_t* sp = side + e;
+        const float* xp = xe + x0;
         bool in_n = valid && (!GENERAL || (e >= v.lo && e < v.hi));
-        float g_n = in_n ? __ldg(G + e) : 0.0f, r_n = (GENERAL || !valid || !R) ? 0.0f : __ldg(R + e), x_n = __ldg(xe + x0);
-        uint8_t sd_n = __ldg(side + e);
+        float g_n = in_n ? __ldg(gp) : 0.0f, r_n = (rp && valid) ? __ldg(rp) : 0.0f, x_n = __ldg(xp);
+        uint8_t sd_n = __ldg(sp);
         for (int ix = x0; ix < x1; ++ix) {
             const float g = g_n * v.inv_n, r = r_n, x = x_n;
             const bool plus = (sd_n & 1) != 0;
             if (ix + 1 < x1) {
-                e += T.plane;
-                in_n = valid && (!GENERAL || (e >= v.lo && e < v.hi));
-                g_n = in_n ? __ldg(G + e) : 0.0f;
-                if (!GENERAL && R) r_n = valid ? __ldg(R + e) : 0.0f;
-                sd_n = __ldg(side + e);
-                x_n = __ldg(xe + ix + 1);
+                gp += T.plane;
+                sp += T.plane;
+                ++xp;
+                if (GENERAL) {
+                    e += T.plane;
+                    in_n = valid && e >= v.lo && e < v.hi;
+                }
+                g_n = in_n ? __ldg(gp) : 0.0f;
+                if (!GENERAL && rp) {
+                    rp += T.plane;
+                    r_n = valid ? __ldg(rp) : 0.0f;
+                }
+                sd_n = __ldg(sp);
+                x_n = __ldg(xp);
             }
             loss = fmaf(0.5f * r, r, loss);
             const bool do_p = plus && g != 0.0f;
