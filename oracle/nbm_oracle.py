@@ -18,9 +18,12 @@ Pinning status
 * geometry / regression / residual rows: pinned against the reference's OWN source files
   executed in the build container through a minimal numpy stand-in for the jax API
   (oracle/jax_shim + oracle/make_golden.py -> tests/golden/*.npz).
-* loss / gradient / optimizer chain: the reference holds no golden vector; the gradient is
-  torch autograd of the pinned rows, the optax chain follows optax 0.1.5's published
-  semantics.  "parity unpinned" beyond the rows for those two items.
+* loss / gradient: the reference holds no golden vector and `jax.value_and_grad` cannot run without jax, but the
+  loss itself and its central differences along 11 parameter directions ARE computed by the reference's own source
+  files in x64 mode (oracle/make_golden_grad.py -> tests/golden/grad_*.npz); the oracle's loss agrees to 8e-8 and
+  its autograd gradient (projected on those directions) to 4e-7.  Pinned.
+* optimizer chain: follows optax 0.1.5's published semantics; learned preconditioner: restated flax
+  `nn.Dense`/tanh/sigmoid.  "parity unpinned" for those two items (neither optax nor flax is installed).
 
 dtype: every function works in the dtype of its inputs.  float32 mirrors what the reference
 prints (`jax_enable_x64 = False`); float64 gives the exact-arithmetic value of the same
