@@ -3,9 +3,13 @@
 
 The reference materialises `(n_gpus, n_batches, batch, 3)` point arrays.  The CUDA path works from
 the grid's 1-D coordinate arrays, so a batch is only a contiguous RANGE of the z-fastest flattened
-point list; `DatasetDict` here computes those ranges with the reference's arithmetic.  Configurations
-that would need the reference's random padding (sizes not divisible) are rejected: the padding
-points come from jax PRNGKey(0) and cannot be reproduced.
+point list; `DatasetDict` here computes those ranges with the reference's arithmetic.
+
+Ragged sizes (the reference's own LPBE example: 32^3 points in batches of 3996, lpbe.yaml:76-84): the
+reference fills the short last batch of every device with `batch_size - last` RANDOM points drawn from
+jax PRNGKey(0) (:70-76, :135-150), which cannot be reproduced without jax.  Here the short batch is
+trained on its real points only (its loss is the mean over those points); a device whose block ends
+early gets empty ranges so that every device still takes the same number of steps.  `padded` tells.
 """
 from __future__ import annotations
 
@@ -24,22 +28,23 @@ class DatasetDict:
         self.last_batch_size = self._len_per_gpu % self.batch_size               # :109
         self.extra_batch_per_gpu = 1 if self.last_batch_size != 0 else 0         # :93
         self.num_batches_per_gpu = self._len_per_gpu // self.batch_size          # :94
-        if self.extra_batch_per_gpu or self._len % self.num_gpus:
-            raise NotImplementedError(
-                f"{self._len} points over {self.num_gpus} device(s) in batches of {self.batch_size} needs the "
-                "reference's random padding (data_management.py:70-76, jax PRNGKey(0)); choose divisible sizes")
+        # where the reference pads with random points
+        self.padded = bool(self.extra_batch_per_gpu or self._len % self.num_gpus)
 
     @property
     def num_batches(self) -> int:
-        return self.num_batches_per_gpu
+        return self.num_batches_per_gpu + self.extra_batch_per_gpu
 
     def batch_range(self, gpu: int, batch_id: int) -> Tuple[int, int]:
-        """flattened-point range of batch `batch_id` on device `gpu` (:121-130)"""
-        begin = gpu * (self.num_batches_per_gpu * self.batch_size) + batch_id * self.batch_size
-        return begin, begin + self.batch_size
+        """flattened-point range of batch `batch_id` on device `gpu` (:121-130, :152-165); may be short (the last
+        batch) or empty (a device whose block ends before this batch)"""
+        begin = gpu * self._len_per_gpu + batch_id * self.batch_size
+        size = self.batch_size if batch_id < self.num_batches_per_gpu else self.last_batch_size
+        begin = min(begin, self._len)
+        return begin, min(begin + size, self._len)
 
     def ranges(self, gpu: int = 0) -> List[Tuple[int, int]]:
-        return [self.batch_range(gpu, b) for b in range(self.num_batches_per_gpu)]
+        return [self.batch_range(gpu, b) for b in range(self.num_batches)]
 
 
 class TrainData:

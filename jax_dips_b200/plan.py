@@ -667,3 +667,25 @@ class PointsPlan:
         cabi.check(cabi.lib().nbm_loss_grad_points_f32(C.byref(self.step), cabi.stream_ptr()),
                    "nbm_loss_grad_points_f32")
         return out if out is not None else self.loss_grad
+
+
+class EmptyPlan:
+    """A batch with no points on this device (ragged multi-device partitions): contributes zeros, but still takes part
+    in the gradient exchange so that every device performs the same sequence of collectives."""
+
+    def __init__(self, n_total: int, device):
+        self.n_total, self.device = int(n_total), torch.device(device)
+        self.n_points = 0
+        self.loss_grad = torch.zeros(self.n_total + 1, dtype=torch.float32, device=self.device)
+        self._partials = torch.zeros(self.n_total + 1, dtype=torch.float32, device=self.device)
+
+    def bind_params(self, params: torch.Tensor) -> None:
+        pass
+
+    def loss_grad_launch(self, out: Optional[torch.Tensor] = None, comm=None) -> torch.Tensor:
+        target = out if out is not None else self.loss_grad
+        if comm is None:
+            target.zero_()
+        else:
+            comm.reduce_allreduce(self._partials, 1, self.n_total + 1, target)
+        return target

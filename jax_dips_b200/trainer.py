@@ -37,7 +37,8 @@ from . import _cabi as cabi
 from . import data_management
 from . import numpy as jnp
 from .optimizers import OptimizerSpec, get_optimizer
-from .plan import GeneralLevel, LevelSet, NetShape, Nonlinear, PointsPlan, PrecondShape, SharedPlan, upload_params
+from .plan import (EmptyPlan, GeneralLevel, LevelSet, NetShape, Nonlinear, PointsPlan, PrecondShape, SharedPlan,
+                   upload_params)
 from .simulation_states import PoissonSimState, PoissonSimStateFn, replace
 
 logger = logging.getLogger(__name__)
@@ -280,7 +281,9 @@ class Trainer:
         Nx, Ny, Nz = self.tr_gstate.shape()
         plane = Ny * Nz
         with torch.cuda.device(self.device):
-            if zoom == 0 and p0 % plane == 0 and p1 % plane == 0:
+            if p1 <= p0:
+                pl = EmptyPlan(self.n_params, self.device)
+            elif zoom == 0 and p0 % plane == 0 and p1 % plane == 0:
                 pl = SharedPlan(self.lvl, self.tr_gstate, p0 // plane, p1 // plane, self.sim_state_fn, self.net,
                                 self.nonlinear_m, self.nonlinear_p, device=self.device, precond=self.precond)
                 pl.bind_params(self.params)
@@ -297,6 +300,13 @@ class Trainer:
                                                   self.net, self.nonlinear_m, self.nonlinear_p, device=self.device,
                                                   precond=self.precond)
         return self._levels[zoom]
+
+    def _warn_if_padded(self, DD) -> None:
+        if DD.padded and not getattr(self, "_warned_padding", False):
+            self._warned_padding = True
+            logger.warning("%d points do not fold into %d device(s) x batches of %d: the reference pads the short batch "
+                           "with random points from jax PRNGKey(0) (data_management.py:70-76); here it is trained on its "
+                           "real points only", DD._len, DD.num_gpus, DD.batch_size)
 
     def _optimizer_struct(self) -> cabi.Optimizer:
         if self._opt_struct is None:
@@ -319,7 +329,7 @@ class Trainer:
         """update (trainer.py:783-789) / update_multi_gpu (:824-834) on the current stream"""
         d = _dist() if allreduce else None
         if d is not None and d.get_world_size() > 1:
-            comm = self._peer_comm() if (self.allreduce_kind == "peer" and isinstance(plan, SharedPlan)) else None
+            comm = self._peer_comm() if (self.allreduce_kind == "peer" and isinstance(plan, (SharedPlan, EmptyPlan))) else None
             upload_params(self.net, self.params)
             if comm is not None:
                 lg = plan.loss_grad_launch(comm=comm)    # reduction fused with the psum over NVLink peer memory
@@ -429,6 +439,7 @@ class Trainer:
         """trainer.py:501-591: epochs x batches, cell size halves every num_epochs//4 epochs
         (data_management.py:320-326), loss_epochs[e] = mean over batches of the batch losses."""
         DD = data_management.DatasetDict(num_points=self.tr_gstate.num_points(), batch_size=self.batch_size)
+        self._warn_if_padded(DD)
         ranges = DD.ranges(0)
         nb = len(ranges)
         with torch.cuda.device(self.device):
@@ -462,8 +473,14 @@ class Trainer:
         rank = d.get_rank() if d is not None else 0
         DD = data_management.DatasetDict(num_points=self.tr_gstate.num_points(), batch_size=world * self.batch_size,
                                          num_gpus=world)
+        self._warn_if_padded(DD)
         ranges = DD.ranges(rank)
         nb = len(ranges)
+        # every rank must pick the same exchange for the same batch: the fused peer kernel serves whole-plane batches
+        # (shared path) only
+        plane = self.tr_gstate.shape()[1] * self.tr_gstate.shape()[2]
+        if not all(p0 % plane == 0 and p1 % plane == 0 for r in range(world) for (p0, p1) in DD.ranges(r) if p1 > p0):
+            self.allreduce_kind = "nccl"
         loss_epochs, epoch_store = [], []
         t0 = time.time()
         with torch.cuda.device(self.device):

@@ -815,13 +815,25 @@ class OptaxCustom:
         return -1.0 * (step_size * upd)
 
 
-def batch_points(points: Tensor, batch_size: int, num_gpus: int = 1) -> Tensor:
-    """DatasetDict (data/data_management.py:79-186) for the no-padding case (divisible sizes)."""
+def batch_points(points: Tensor, batch_size: int, num_gpus: int = 1):
+    """DatasetDict (data/data_management.py:79-186): per device a list of batches, contiguous blocks of the point list
+    (:121-130).  Divisible sizes are the reference exactly.  For ragged sizes the reference fills the short last
+    batch with random points from jax PRNGKey(0) (:70-76, :135-150), which cannot be restated without jax: here -
+    as in the product - the short batch keeps its real points only, and a device whose block ends early gets empty
+    batches (so that every device takes the same number of steps)."""
     n = points.shape[0]
     per = math.ceil(n / num_gpus)
     b = min(batch_size, per)
-    assert per % b == 0 and n % num_gpus == 0, "oracle covers the divisible (no random padding) case"
-    return points.reshape(num_gpus, per // b, b, 3)
+    nb = per // b + (1 if per % b else 0)
+    out = []
+    for g in range(num_gpus):
+        dev = []
+        for k in range(nb):
+            lo = min(g * per + k * b, n)
+            hi = min(lo + (b if k < per // b else per % b), n)
+            dev.append(points[lo:hi])
+        out.append(dev)
+    return out
 
 
 def single_gpu_train(params: Tensor, points: Tensor, grid_d, prob: OracleProblem, num_epochs: int,
@@ -835,11 +847,11 @@ def single_gpu_train(params: Tensor, points: Tensor, grid_d, prob: OracleProblem
         zoom = epoch // (num_epochs // 4) if multires else 0
         d = [g * 0.5 ** zoom for g in grid_d]
         acc = 0.0
-        for b in range(batches.shape[0]):
-            l, g = loss_and_grad(params, batches[b], d[0], d[1], d[2], prob)
+        for pts in batches:
+            l, g = loss_and_grad(params, pts, d[0], d[1], d[2], prob)
             params = params + opt.update(g)
             acc += float(l)
-        losses.append(acc / batches.shape[0])
+        losses.append(acc / len(batches))
     return params, losses
 
 
@@ -849,18 +861,21 @@ def multi_gpu_train(params: Tensor, points: Tensor, grid_d, prob: OracleProblem,
     (:829-830), identical update everywhere, no multi-resolution schedule."""
     od = optimizer_dict or {"learning_rate": 1e-3, "sched": {"decay_rate": 0.96}}
     opt = OptaxCustom(params.numel(), od["learning_rate"], od["sched"]["decay_rate"], dtype=params.dtype)
-    data = batch_points(points, n_devices * batch_size, n_devices)   # (G, nb, B, 3)
+    data = batch_points(points, n_devices * batch_size, n_devices)   # [device][batch] -> (B, 3)
+    nb = len(data[0])
     losses = []
     for epoch in range(num_epochs):
         acc = 0.0
-        for b in range(data.shape[1]):
+        for b in range(nb):
             gsum = torch.zeros_like(params); lsum = 0.0
             for dev in range(n_devices):
-                l, g = loss_and_grad(params, data[dev, b], grid_d[0], grid_d[1], grid_d[2], prob)
+                if data[dev][b].shape[0] == 0:
+                    continue
+                l, g = loss_and_grad(params, data[dev][b], grid_d[0], grid_d[1], grid_d[2], prob)
                 gsum += g; lsum += float(l)
             params = params + opt.update(gsum)
             acc += lsum
-        losses.append(acc / data.shape[1])
+        losses.append(acc / nb)
     return params, losses
 
 

@@ -170,6 +170,25 @@ def test_general_path_with_learned_preconditioner(name, zoom):
         assert util.rel_inf(lg[k:-1], grad_o[k:]) < TOL_LOSS
 
 
+def test_ragged_batches_keep_their_real_points():
+    """512 points in batches of 200 (200 + 200 + 112; the reference would pad the last one with 88 random points from
+    jax PRNGKey(0), data_management.py:70-76): unaligned batches run on the per-point path at every zoom level."""
+    P = problems.sphere()
+    n_tr, n_lvl = 8, 24
+    tr, lv, phi_grid, oprob = util.make_case(P, n_tr, n_lvl, "trilinear", torch.float64)
+    p0 = O.init_params(oprob.shape, seed=42, dtype=torch.float64)
+    od = {"optimizer_name": "custom", "learning_rate": 1e-2, "sched": {"scheduler_name": "exponential", "decay_rate": 0.975}}
+    grid_d = [tr.dx.double(), tr.dy.double(), tr.dz.double()]
+    p_o, losses_o = O.single_gpu_train(p0.clone(), tr.R.double(), grid_d, oprob, num_epochs=4, batch_size=200,
+                                       optimizer_dict=od)
+    (state, epoch_store, loss_epochs), T, _ = _solve(P, n_tr, n_lvl, 8, 4, 200, p0.float(), optimizer_dict=od)
+    lk = torch.as_tensor(loss_epochs).double()
+    lo = torch.tensor(losses_o, dtype=torch.float64)
+    assert ((lk - lo).abs() / lo).max() < 1e-3, (lk, lo)
+    assert util.rel_inf(T.params.cpu(), p_o) < 1e-3
+    assert int(T.opt_count.item()) == 12
+
+
 def test_lbfgs_driver_minimises_the_first_batch():
     """optimizer_name "lbfgs" (trainer.py:197-208, 354-427): scipy L-BFGS-B, maxiter = num_epochs, on the first batch
     at the native cell size, driven by the CUDA loss/gradient.  The same scipy call on the oracle's float64

@@ -77,8 +77,18 @@ def test_dataset_dict_ranges_follow_the_reference_arithmetic():
     # multi device: per-device batch = min(n_dev*batch, ceil(N/n_dev)) (trainer.py:733-737), x-slabs
     DD = data_management.DatasetDict(num_points=32 ** 3, batch_size=8 * 131072, num_gpus=8)
     assert [DD.ranges(r) for r in range(8)] == [[(r * 4096, (r + 1) * 4096)] for r in range(8)]
-    with pytest.raises(NotImplementedError):
-        data_management.DatasetDict(num_points=1000, batch_size=300)            # would need random padding
+    # ragged sizes: the short last batch keeps its real points (the reference pads it with PRNGKey(0) random points)
+    DD = data_management.DatasetDict(num_points=1000, batch_size=300)
+    assert DD.padded and DD.num_batches == 4
+    assert DD.ranges(0) == [(0, 300), (300, 600), (600, 900), (900, 1000)]
+    # the reference's own LPBE example (lpbe.yaml:76-84): 32^3 points in batches of 3996
+    DD = data_management.DatasetDict(num_points=32 ** 3, batch_size=3996)
+    r = DD.ranges(0)
+    assert len(r) == 9 and r[-1] == (8 * 3996, 32 ** 3) and all(b - a == 3996 for a, b in r[:-1])
+    # devices whose block ends early get empty ranges, every device takes the same number of steps
+    DD = data_management.DatasetDict(num_points=1001, batch_size=2 * 250, num_gpus=2)
+    assert DD.batch_size == 500 and DD.ranges(0) == [(0, 500), (500, 501)] and DD.ranges(1) == [(501, 1001), (1001, 1001)]
+    assert not data_management.DatasetDict(num_points=4096, batch_size=1024).padded
 
 
 def test_zoom_schedule():
@@ -205,3 +215,18 @@ def test_vtk_writer_roundtrip(tmp_path):
     assert fields["phi"].dtype == np.float64
     head = open(path, "rb").read(200).decode("ascii", "replace")
     assert 'type="StructuredGrid"' in head and 'header_type="UInt64"' in head
+
+
+def test_empty_plan_contributes_zeros():
+    """ragged multi-device partitions: a device without points for a batch still joins the exchange with zeros"""
+    from jax_dips_b200.plan import EmptyPlan
+    pl = EmptyPlan(5, "cpu")
+    pl.loss_grad.fill_(3.0)
+    out = pl.loss_grad_launch()
+    assert out.shape == (6,) and float(out.abs().sum()) == 0.0 and pl.n_points == 0
+
+    class FakeComm:
+        def reduce_allreduce(self, partials, rows, np1, target):
+            assert rows == 1 and np1 == 6 and float(partials.abs().sum()) == 0.0
+            target.copy_(partials + 1.0)      # what the peers contributed
+    assert float(pl.loss_grad_launch(comm=FakeComm()).sum()) == 6.0

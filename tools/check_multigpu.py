@@ -45,6 +45,21 @@ def main():
     allp = [torch.zeros_like(T.params) for _ in range(world)]
     dist.all_gather(allp, T.params)
     assert all(torch.equal(a, allp[0]) for a in allp)
+    # ragged partition: 15 x 16 x 16 points do not split into whole x planes per rank -> per-point path + NCCL
+    tr2 = mesh.linspace_grid(*P.box, [15, 16, 16])
+    tr2o, lv2, phi2, oprob2 = util.make_case(P, [15, 16, 16], n_lvl, "trilinear", torch.float64)
+    sim2, solve2 = init_fn(lvl_gstate=lv, tr_gstate=tr2, eval_gstate=ev, num_epochs=2, batch_size=700,
+                           multi_gpu=True, checkpoint_dir=None, optimizer_dict=od, init_params=p0.float(), print_rate=0)
+    (_, _, le2) = solve2(sim2)
+    T2 = solve2.trainer
+    assert T2.allreduce_kind == "nccl"
+    if rank == 0:
+        gd = [tr2.dx.double(), tr2.dy.double(), tr2.dz.double()]
+        p_o2, l_o2 = O.multi_gpu_train(p0.clone(), tr2.R.double(), gd, oprob2, 2, 700, world, od)
+        lk2 = torch.stack([l[0] for l in le2]).double()
+        e2 = float(((lk2 - torch.tensor(l_o2, dtype=torch.float64)).abs() / torch.tensor(l_o2, dtype=torch.float64)).max())
+        print(f"ragged: loss trajectory rel err {e2:.3e}, params rel-inf {util.rel_inf(T2.params.cpu(), p_o2):.3e}")
+        assert e2 < 1e-3 and util.rel_inf(T2.params.cpu(), p_o2) < 1e-3
     dist.destroy_process_group()
     if rank == 0:
         print("MULTIGPU OK")
