@@ -3,6 +3,7 @@ import pytest
 import torch
 
 import util
+from jax_dips_b200 import numpy as jnp
 from jax_dips_b200 import mesh, plan as nplan, problems, trainer as ntrainer
 from oracle import nbm_oracle as O
 from test_gpu_shared import DEV, TOL_LOSS, TOL_ROW, build, fns_of
@@ -168,6 +169,40 @@ def test_general_path_with_learned_preconditioner(name, zoom):
         k = shape.n_params
         assert util.rel_inf(lg[:k], grad_o[:k]) < TOL_LOSS
         assert util.rel_inf(lg[k:-1], grad_o[k:]) < TOL_LOSS
+
+
+def test_config0_sphere_32_error_metrics_track_the_oracle(tmp_path):
+    """BASELINE.json configs[0] (tests/test_poisson.py, sphere of experiment_configs.py:21, 32^3 training grid, default
+    MLP, optimizer "custom"): after the same epochs from the same initial vector the accuracy figures the reference's
+    test logs (L_inf, RMSD, relative L_2 against the exact solution, test_poisson.py:276-283) must agree with the
+    oracle's within 2 % (north star), and the fields go to a VTK file like test_poisson.py:249-253."""
+    from jax_dips_b200 import io as nio
+    P = problems.sphere()
+    n_tr, n_lvl, n_ev, epochs, bs = 32, 64, 32, 4, 16384
+    tr, lv, phi_grid, oprob = util.make_case(P, n_tr, n_lvl, "trilinear", torch.float64)
+    p0 = O.init_params(oprob.shape, seed=42, dtype=torch.float64)
+    od = {"optimizer_name": "custom", "learning_rate": 1e-2, "sched": {"scheduler_name": "exponential", "decay_rate": 0.975}}
+    grid_d = [tr.dx.double(), tr.dy.double(), tr.dz.double()]
+    p_o, losses_o = O.single_gpu_train(p0.clone(), tr.R.double(), grid_d, oprob, num_epochs=epochs, batch_size=bs,
+                                       optimizer_dict=od)
+    (state, _, loss_epochs), T, (trk, lvk, ev) = _solve(P, n_tr, n_lvl, n_ev, epochs, bs, p0.float(), optimizer_dict=od)
+    phi_ev = jnp.vmap(P.phi_fn)(ev.R)
+    exact = torch.where(phi_ev >= 0, jnp.vmap(P.exact_sol_p_fn)(ev.R), jnp.vmap(P.exact_sol_m_fn)(ev.R)).double()
+    u_o = oprob.solution(p_o, ev.R.double())
+    u_k = state.solution.cpu().double()
+
+    def metrics(u):
+        e = u - exact
+        return (float(e.abs().max()), float((e ** 2).mean().sqrt()), float(((e ** 2).sum() / (exact ** 2).sum()).sqrt()))
+
+    mk, mo = metrics(u_k), metrics(u_o)
+    for a, b in zip(mk, mo):
+        assert abs(a - b) / b < 0.02, (mk, mo)
+    assert ((torch.as_tensor(loss_epochs).double() - torch.tensor(losses_o)).abs() / torch.tensor(losses_o)).max() < 1e-3
+    path = nio.write_vtk_manual(ev, {"phi": phi_ev, "U": state.solution, "U_exact": exact, "U-U_exact": u_k - exact},
+                                filename=str(tmp_path / "sphere"))
+    pts, fields = nio.read_vts(path)
+    assert set(fields) == {"phi", "U", "U_exact", "U-U_exact"} and pts.shape[0] == n_ev ** 3
 
 
 def test_ragged_batches_keep_their_real_points():
