@@ -261,6 +261,16 @@ typedef struct {
     int pc_d1, pc_d2;
     float pc_scale;
     int n_pc_rows;                   /* partial rows reserved for the preconditioner kernel (>= 1) */
+    /* Deterministic adjoint of the lists (optional; all NULL = the atomic kernels).  The adjoint of the irregular rows
+     * and of the extrapolation scatters into gE and G; given the transposed incidence in CSR form it is GATHERED
+     * instead - no atomics, fixed summation order, bitwise reproducible step:
+     *   ge_ptr[nc+1], ge_ent[]: per crossed site c the (row q, slot k) pairs with irr_c[q][k] == c, packed q*8+k
+     *   list_nodes[n_list]    : the lattice nodes that receive a list contribution, ascending
+     *   g_ptr[n_list+1], g_ent[]: per such node its contributions: >= 0: q*8+k -> irr_wU[q][k] * R[irr_point[q]]
+     *                            (faces table only);  < 0: -(c*32+v)-1 -> B[c][v] * gE[c] */
+    const int32_t* ge_ptr; const int32_t* ge_ent;
+    const int64_t* list_nodes; int64_t n_list;
+    const int32_t* g_ptr; const int32_t* g_ent;
 } nbm_shared_step_t;
 
 /* number of preconditioner parameters for hidden widths (d1, d2) */

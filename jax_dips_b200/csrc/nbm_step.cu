@@ -998,6 +998,51 @@ __global__ void __launch_bounds__(kThreads) adjoint_faces4_kernel(nbm_shared_ste
     *reinterpret_cast<float4*>(s.G + e) = g;
 }
 
+// C0 (deterministic form): the adjoint of the lists GATHERED through the transposed incidence (CSR built once per
+// level on the host): no atomics, fixed summation order.
+//   gE[c] = sum over (row q, slot k) with irr_c[q][k] == c of  wE[q][k] R[q]  (+ the nonlinear term of slot 0)
+__global__ void gather_gE_kernel(nbm_shared_step_t s) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= s.n_crossed) return;
+    float acc = 0.0f;
+    const int b = s.ge_ptr[c], e = s.ge_ptr[c + 1];
+    for (int i = b; i < e; ++i) {
+        const int ent = s.ge_ent[i];
+        const int q = ent >> 3, k = ent & 7;
+        const float r = s.R[s.irr_point[q]];
+        acc = fmaf(s.irr_wE[(int64_t)q * 7 + k], r, acc);
+        if (k == 0) {
+            const uint8_t nlr = s.irr_nl[q];
+            if (nlr) {
+                const float Ec = s.E[c];
+                const float d = nlr == 1 ? nl_deriv(s.nonlinear_m, s.nl_coef_m, Ec) : nl_deriv(s.nonlinear_p, s.nl_coef_p, Ec);
+                acc = fmaf(s.irr_nlw[q] * d, r, acc);
+            }
+        }
+    }
+    s.gE[c] = acc;
+}
+//   G[n] += sum of irr_wU[q][k] R[q] over the irregular rows that use node n (faces table)
+//         + sum of B[c][v] gE[c] over the crossed sites whose 27-cube holds node n
+__global__ void gather_G_kernel(nbm_shared_step_t s) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n_list) return;
+    float acc = 0.0f;
+    const int b = s.g_ptr[i], e = s.g_ptr[i + 1];
+    for (int j = b; j < e; ++j) {
+        const int ent = s.g_ent[j];
+        if (ent >= 0) {
+            const int q = ent >> 3, k = ent & 7;
+            acc = fmaf(s.irr_wU[(int64_t)q * 7 + k], s.R[s.irr_point[q]], acc);
+        } else {
+            const int m = -(ent + 1);
+            const int c = m >> 5, v = m & 31;
+            acc = fmaf(s.B[(int64_t)c * 28 + v], s.gE[c], acc);
+        }
+    }
+    s.G[s.list_nodes[i]] += acc;
+}
+
 // C0: adjoint of the irregular rows: gE[c] += wE * R[p]
 __global__ void irregular_bwd_kernel(nbm_shared_step_t s) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2024,8 +2069,13 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
             dim3 g((s.ey * s.ez + kThreads - 1) / kThreads, s.ex);
             adjoint_kernel<<<g, kThreads, 0, st>>>(s);
         }
-        if (s.n_irr > 0) irregular_bwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
-        if (s.n_crossed > 0) extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, st>>>(s);
+        if (s.g_ptr) {   // deterministic gathers through the transposed incidence
+            if (s.n_crossed > 0) gather_gE_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
+            if (s.n_list > 0) gather_G_kernel<<<(unsigned)((s.n_list + 127) / 128), 128, 0, st>>>(s);
+        } else {
+            if (s.n_irr > 0) irregular_bwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
+            if (s.n_crossed > 0) extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, st>>>(s);
+        }
     }
     if ((stages & NBM_STAGE_GRAD) && fused) {
         FusedView f;
@@ -2381,6 +2431,11 @@ int nbm_loss_grad_shared_f32(const nbm_shared_step_t* s, nbm_stream_t stream) {
                     "faces mode needs plane % 4 == 0, even ez and 16-byte aligned arrays");
     } else {
         NBM_REQUIRE(s->w, "null tables");
+    }
+    if (s->g_ptr) {
+        NBM_REQUIRE(s->g_ent && s->list_nodes && s->n_list >= 0, "null list-node tables");
+        NBM_REQUIRE(s->n_crossed == 0 || (s->ge_ptr && s->ge_ent), "null crossed-site incidence");
+        NBM_REQUIRE(!s->S, "the gathered list adjoint and the fused adjoint (S) are alternatives");
     }
     if (s->coef26) {
         NBM_REQUIRE(s->pc_params, "null preconditioner parameters");

@@ -127,12 +127,35 @@ def test_rows_loss_and_gradient(name, n, nl, faces, fused):
     # per-coordinate check on the large entries too
     big = grad_o.abs() > 1e-2 * grad_o.abs().max()
     assert ((grad_k.double()[big] - grad_o[big]).abs() / grad_o[big].abs()).max() < 10 * TOL_LOSS
-    # a second launch gives the same answer (the fused kernel re-zeroes the list contributions it consumed;
-    # the atomics on the lists are order-dependent in the last bits only)
+    # a second launch gives the same answer (the fused kernel re-zeroes the list contributions it consumed; the adjoint
+    # of the lists uses fp32 atomics: order-dependent in the last bits only)
     with torch.cuda.device(DEV):
         lg2 = pl.loss_grad_launch().clone()
         torch.cuda.synchronize()
     assert util.rel_inf(lg2[:-1].cpu(), grad_k) < 1e-5
+
+
+@pytest.mark.parametrize("name,faces", [("star", True), ("sphere", False)])
+def test_deterministic_list_adjoint_is_bitwise_reproducible(name, faces):
+    """deterministic=True: the adjoint of the irregular rows and of the extrapolation is gathered through the transposed
+    incidence (no atomics): same gradient as the scattered form within fp32 rounding, and bitwise identical from launch to
+    launch."""
+    P = problems.PROBLEMS[name]()
+    tr, lv, phi_grid, oprob = util.make_case(P, 16, 32, "trilinear", torch.float64)
+    lvl = nplan.LevelSet(lv, phi_grid, device=DEV)
+    shape = nplan.NetShape()
+    mk = lambda det: nplan.SharedPlan(lvl, tr, 0, 16, fns_of(P), shape, nplan.Nonlinear(), nplan.Nonlinear(), device=DEV,
+                                      faces=faces, deterministic=det)
+    a, b = mk(True), mk(False)
+    assert a.g_ptr is not None and b.g_ptr is None and a.n_list > 0
+    params = O.init_params(oprob.shape, seed=7).to(DEV)
+    with torch.cuda.device(DEV):
+        nplan.upload_params(shape, params)
+        runs = [a.loss_grad_launch().clone() for _ in range(4)]
+        ref = b.loss_grad_launch().clone()
+        torch.cuda.synchronize()
+    assert all(torch.equal(r, runs[0]) for r in runs[1:])
+    assert util.rel_inf(runs[0], ref) < 1e-6
 
 
 def test_anisotropic_grid_and_interface_at_the_box_boundary():
