@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--faces", type=int, default=-1, help="1/0: face-coefficient row table on/off (default: auto)")
     ap.add_argument("--fused", type=int, default=-1, help="1/0: adjoint stencil fused into the gradient kernel (default: auto)")
+    ap.add_argument("--precond", action="store_true",
+                    help="train the learned preconditioner too (model_dict['preconditioner'], lpbe.yaml:62-67): 257 more "
+                         "parameters, one more kernel per step")
     ap.add_argument("--emulate", default="", help="R/W: on ONE GPU, time the slab rank R would own in a W-GPU weak-scaling "
                                                   "run (load-balance diagnosis; not a bench line)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -210,7 +213,8 @@ def main():
     per = Nx // (emu[1] if emu else world)
     xa, xb = (emu[0] if emu else rank) * per, ((emu[0] if emu else rank) + 1) * per
     net = nplan.NetShape()
-    P = net.n_params
+    precond = nplan.PrecondShape((8, 4), 1.0) if args.precond else None
+    P = net.n_params + (precond.n_params if precond is not None else 0)
     phi_lvl = fns.phi_fn(lv.R.to(dev))
     lvl = nplan.LevelSet(lv, phi_lvl, interp=args.interp, perturb_eps=1e-10, device=dev)
     t_setup = time.time()
@@ -241,11 +245,16 @@ def main():
     pl = nplan.SharedPlan(lvl, tr, xa, xb, fns, net, nplan.Nonlinear.coerce(problem.nonlinear_op_m),
                           nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=dev,
                           faces=None if args.faces < 0 else bool(args.faces),
-                          fused=None if args.fused < 0 else bool(args.fused))
+                          fused=None if args.fused < 0 else bool(args.fused), precond=precond)
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
 
-    params = haiku_init(net, 42).to(dev)
+    params = haiku_init(net, 42)
+    if precond is not None:
+        from jax_dips_b200.trainer import precond_init
+        params = torch.cat((params, precond_init(precond, 42)))
+    params = params.to(dev)
+    pl.bind_params(params)
     opt_state = torch.zeros(2 * P, device=dev)
     opt_count = torch.zeros(1, dtype=torch.int32, device=dev)
     spec = get_optimizer("custom", "exponential", 1e-3, 0.975)

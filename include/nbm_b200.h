@@ -261,6 +261,11 @@ typedef struct {
     int pc_d1, pc_d2;
     float pc_scale;
     int n_pc_rows;                   /* partial rows reserved for the preconditioner kernel (>= 1) */
+    /* optional fast path: pc_nodes_m / pc_nodes_p = the lattice nodes that hold a row and whose cell is NOT crossed, per
+     * side (ascending), pc_d = the cell size.  They take per-side kernels whose first layer sees only the 6 face
+     * coefficients of the node's side (the other 20 inputs are zero or grid constants); crossed cells (c_node) take
+     * the generic kernel.  Needs n_pc_rows >= 3 (one third of the rows per kernel; 3 x #SM is a good value). */
+    const int32_t* pc_nodes_m; int64_t n_pc_m; const int32_t* pc_nodes_p; int64_t n_pc_p; float pc_d[3];
     /* Deterministic adjoint of the lists (optional; all NULL = the atomic kernels).  The adjoint of the irregular rows
      * and of the extrapolation scatters into gE and G; given the transposed incidence in CSR form it is GATHERED
      * instead - no atomics, fixed summation order, bitwise reproducible step:

@@ -69,7 +69,8 @@ class SharedStep(C.Structure):
                 ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp), ("stages", C.c_int),
                 ("faces", C.c_int), ("cface", c_fp), ("dinv", c_fp), ("irr_wU", c_fp), ("irr_rhs", c_fp),
                 ("kv", c_fp), ("S", c_fp), ("coef26", c_fp), ("pc_params", c_fp), ("pc_d1", C.c_int), ("pc_d2", C.c_int),
-                ("pc_scale", c_f), ("n_pc_rows", C.c_int),
+                ("pc_scale", c_f), ("n_pc_rows", C.c_int), ("pc_nodes_m", c_fp), ("n_pc_m", C.c_int64), ("pc_nodes_p", c_fp), ("n_pc_p", C.c_int64),
+                ("pc_d", c_f * 3),
                 ("ge_ptr", c_fp), ("ge_ent", c_fp), ("list_nodes", c_fp), ("n_list", C.c_int64), ("g_ptr", c_fp),
                 ("g_ent", c_fp)]
 

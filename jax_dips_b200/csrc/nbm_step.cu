@@ -20,6 +20,8 @@ namespace nbm {
 // product W delta also runs as 5 independent fp32x2 chains with adjacent constant-bank pairs.
 __constant__ __align__(16) float c_P[3 * NBM_MAXP];
 __device__ __align__(16) float g_stage[3 * NBM_MAXP];
+// the learned preconditioner's parameters (nn/preconditioner.py), uploaded before its kernels run
+__constant__ __align__(16) float c_PC[512];
 constexpr float kTwoLog2e = 2.8853900817779268f;
 
 constexpr int kThreads = 256;
@@ -1607,7 +1609,7 @@ __device__ __forceinline__ float tanh_acc(float x) { return tanh_nbm(x); }
 
 template <int D1, int D2>
 __global__ void __launch_bounds__(kThreads) precond_kernel(const float* __restrict__ coef26, int64_t cstride,
-                                                           float* __restrict__ R,
+                                                           float* __restrict__ R, const int64_t* __restrict__ nodes,
                                                            int64_t ne, const float* __restrict__ params, float scale,
                                                            float inv_n, float* __restrict__ partials, int row_stride,
                                                            int col0, int loss_col) {
@@ -1633,8 +1635,9 @@ __global__ void __launch_bounds__(kThreads) precond_kernel(const float* __restri
 #pragma unroll
     for (int q = 0; q < D2; ++q) { ab2[q] = 0.0f; aW3[q] = 0.0f; }
     for (int64_t base = (int64_t)blockIdx.x * kThreads; base < ne; base += (int64_t)gridDim.x * kThreads) {
-        const int64_t e = base + tid;
-        const bool valid = e < ne;
+        // `nodes` != null: the kernel walks a list of nodes (the crossed cells of the shared path) instead of a range
+        const bool valid = base + tid < ne;
+        const int64_t e = !valid ? 0 : (nodes ? nodes[base + tid] : base + tid);
         const float r = valid ? R[e] : 0.0f;
         float c[NIN];
 #pragma unroll
@@ -1714,6 +1717,168 @@ __global__ void __launch_bounds__(kThreads) precond_kernel(const float* __restri
     for (int j = 0; j < D1; ++j) {
         float v = wsum(ab1[j]);
         if (lane == 0) sred[warp][PN::ob1 + j] = v;
+#pragma unroll
+        for (int q = 0; q < D2; ++q) {
+            v = wsum(aW2[j][q]);
+            if (lane == 0) sred[warp][PN::oW2 + j * D2 + q] = v;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < D2; ++q) {
+        float v = wsum(ab2[q]);
+        if (lane == 0) sred[warp][PN::ob2 + q] = v;
+        v = wsum(aW3[q]);
+        if (lane == 0) sred[warp][PN::oW3 + q] = v;
+    }
+    {
+        float v = wsum(ab3);
+        if (lane == 0) sred[warp][PN::ob3] = v;
+        v = wsum(loss);
+        if (lane == 0) sred[warp][NPc] = v * inv_n;
+    }
+    __syncthreads();
+    float* row = partials + (size_t)blockIdx.x * row_stride;
+    for (int i = tid; i <= NPc; i += kThreads) {
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) v += sred[w][i];
+        row[i < NPc ? col0 + i : loss_col] = v;
+    }
+}
+
+// Uncrossed cells (all but ~0.5 %): the 26 inputs of a cell on side S are 6 face coefficients mu A / d of that side,
+// the cell volume and the 6 face areas (grid constants), zeros for the other side (geometric_integrations_per_point.py:
+// 906-996).  One launch per side with S a compile-time constant: the first layer is 6 x D1 FMAs on top of a per-side
+// constant K, its gradient needs 6 x D1 accumulators plus sum(delta1) (the volume / area rows follow by scaling at the
+// end), and every weight is a constant-bank operand.  Crossed cells take the generic kernel over their node list.
+template <int D1, int D2, int S>
+__global__ void __launch_bounds__(kThreads) precond_bulk_kernel(const float* __restrict__ coef26, int64_t ne,
+                                                                const int32_t* __restrict__ nodes, int64_t n_nodes,
+                                                                float* __restrict__ R,
+                                                                float vol, float ax, float ay, float az, float scale,
+                                                                float inv_n, float* __restrict__ partials, int row_stride,
+                                                                int col0, int loss_col) {
+    using PN = PrecondNet<D1, D2>;
+    constexpr int NPc = PN::NP, kWarps = kThreads / 32;
+    __shared__ float sred[kWarps][NPc + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float area[6] = {ax, ax, ay, ay, az, az};
+    // K[j] = b1[j] + vol W1[12+S][j] + sum_f A_f W1[14+2f+S][j]
+    float K[D1];
+#pragma unroll
+    for (int j = 0; j < D1; ++j) {
+        float k = fmaf(vol, c_PC[PN::oW1 + (12 + S) * D1 + j], c_PC[PN::ob1 + j]);
+#pragma unroll
+        for (int f = 0; f < 6; ++f) k = fmaf(area[f], c_PC[PN::oW1 + (14 + 2 * f + S) * D1 + j], k);
+        K[j] = k;
+    }
+    float aW1[6][D1], aD[D1], aW2[D1][D2], ab2[D2], aW3[D2], ab3 = 0.0f, loss = 0.0f;
+#pragma unroll
+    for (int j = 0; j < D1; ++j) {
+        aD[j] = 0.0f;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) aW1[f][j] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < D2; ++q) aW2[j][q] = 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < D2; ++q) { ab2[q] = 0.0f; aW3[q] = 0.0f; }
+    // the uncrossed row nodes of side S come as a list (built once per level); software pipeline (8 warps per SM cannot
+    // hide dependent global loads): node index two entries ahead, its residual and 6 coefficients one entry ahead
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    int64_t i = (int64_t)blockIdx.x * kThreads + tid;
+    int e_0 = i < n_nodes ? __ldg(nodes + i) : -1;
+    int e_1 = i + stride < n_nodes ? __ldg(nodes + i + stride) : -1;
+    float r_n = 0.0f, c_n[6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) c_n[f] = 0.0f;
+    if (e_0 >= 0) {
+        r_n = R[e_0];
+#pragma unroll
+        for (int f = 0; f < 6; ++f) c_n[f] = __ldcs(coef26 + (int64_t)(2 * f + S) * ne + e_0);
+    }
+    for (; i < n_nodes; i += stride) {
+        const int e = e_0;
+        const float r = r_n;
+        float c[6];
+#pragma unroll
+        for (int f = 0; f < 6; ++f) c[f] = c_n[f];
+        e_0 = e_1;
+        e_1 = i + 2 * stride < n_nodes ? __ldg(nodes + i + 2 * stride) : -1;
+        if (e_0 >= 0) {
+            r_n = R[e_0];
+#pragma unroll
+            for (int f = 0; f < 6; ++f) c_n[f] = __ldcs(coef26 + (int64_t)(2 * f + S) * ne + e_0);
+        }
+        if (r == 0.0f) continue;   // an exactly satisfied row contributes nothing
+        float h1[D1], h2[D2];
+#pragma unroll
+        for (int j = 0; j < D1; ++j) {
+            float z = K[j];
+#pragma unroll
+            for (int f = 0; f < 6; ++f) z = fmaf(c[f], c_PC[PN::oW1 + (2 * f + S) * D1 + j], z);
+            h1[j] = tanh_acc(z);
+        }
+#pragma unroll
+        for (int q = 0; q < D2; ++q) {
+            float z = c_PC[PN::ob2 + q];
+#pragma unroll
+            for (int j = 0; j < D1; ++j) z = fmaf(h1[j], c_PC[PN::oW2 + j * D2 + q], z);
+            h2[q] = tanh_acc(z);
+        }
+        float o = c_PC[PN::ob3];
+#pragma unroll
+        for (int q = 0; q < D2; ++q) o = fmaf(h2[q], c_PC[PN::oW3 + q], o);
+        const float sg = 1.0f / (1.0f + __expf(-o));
+        const float Pc = fmaf(scale, sg, 0.5f);
+        const float pr = Pc * r;
+        loss = fmaf(0.5f * pr, pr, loss);
+        R[e] = Pc * pr;
+        const float dO = (pr * r) * inv_n * scale * sg * (1.0f - sg);
+        ab3 += dO;
+        float d2[D2];
+#pragma unroll
+        for (int q = 0; q < D2; ++q) {
+            aW3[q] = fmaf(dO, h2[q], aW3[q]);
+            d2[q] = dO * c_PC[PN::oW3 + q] * fmaf(-h2[q], h2[q], 1.0f);
+            ab2[q] += d2[q];
+        }
+#pragma unroll
+        for (int j = 0; j < D1; ++j) {
+            float t = 0.0f;
+#pragma unroll
+            for (int q = 0; q < D2; ++q) {
+                aW2[j][q] = fmaf(h1[j], d2[q], aW2[j][q]);
+                t = fmaf(c_PC[PN::oW2 + j * D2 + q], d2[q], t);
+            }
+            const float d1 = t * fmaf(-h1[j], h1[j], 1.0f);
+            aD[j] += d1;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) aW1[f][j] = fmaf(c[f], d1, aW1[f][j]);
+        }
+    }
+    // block reduction into this CTA's partial row; rows of W1 that belong to the other side stay zero
+    auto wsum = [&](float v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+    for (int i = tid; i < kWarps * (NPc + 1); i += kThreads) (&sred[0][0])[i] = 0.0f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < D1; ++j) {
+        float v = wsum(aD[j]);
+        if (lane == 0) {
+            sred[warp][PN::ob1 + j] = v;
+            sred[warp][PN::oW1 + (12 + S) * D1 + j] = vol * v;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) sred[warp][PN::oW1 + (14 + 2 * f + S) * D1 + j] = area[f] * v;
+        }
+#pragma unroll
+        for (int f = 0; f < 6; ++f) {
+            v = wsum(aW1[f][j]);
+            if (lane == 0) sred[warp][PN::oW1 + (2 * f + S) * D1 + j] = v;
+        }
 #pragma unroll
         for (int q = 0; q < D2; ++q) {
             v = wsum(aW2[j][q]);
@@ -2022,7 +2187,7 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     const bool pc = s.coef26 != nullptr;
     const int n_pc = pc ? PrecondNet<8, 4>::NP : 0;
     const int pc_stride = NET::NP + n_pc + 1;
-    const int gridP = pc ? min(s.n_pc_rows, 2 * sms) : 0;
+    const int gridP = pc ? min(s.n_pc_rows, 3 * sms) : 0;
     int gridC = min(Tg.total, min(kPartialRows, sms));
     if (gridC > s.n_partial_rows - gridP) gridC = s.n_partial_rows - gridP;
     if (stages & NBM_STAGE_FWD) {
@@ -2044,12 +2209,29 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
         }
         if (s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
         if (pc) {
-            // rows [gridC, gridC + gridP) of the partials: preconditioner gradient + the loss
-            precond_kernel<8, 4><<<gridP, kThreads, 0, st>>>(s.coef26, (int64_t)s.ex * s.ey * s.ez, s.R,
-                                                             (int64_t)s.ex * s.ey * s.ez, s.pc_params,
-                                                             s.pc_scale, s.inv_n_points,
-                                                             s.partials + (size_t)gridC * pc_stride, pc_stride, NET::NP,
-                                                             NET::NP + n_pc);
+            // rows [gridC, gridC + gridP) of the partials: preconditioner gradient + the loss.  Uncrossed cells: one
+            // launch per side (inputs reduce to 6 face coefficients); crossed cells: the generic kernel on their list
+            const int64_t ne = (int64_t)s.ex * s.ey * s.ez;
+            cudaMemcpyToSymbolAsync(c_PC, s.pc_params, sizeof(float) * n_pc, 0, cudaMemcpyDeviceToDevice, st);
+            float* rows = s.partials + (size_t)gridC * pc_stride;
+            if (s.pc_nodes_m || s.pc_nodes_p) {
+                const float vol = s.pc_d[0] * s.pc_d[1] * s.pc_d[2];
+                const float ax = s.pc_d[1] * s.pc_d[2], ay = s.pc_d[0] * s.pc_d[2], az = s.pc_d[0] * s.pc_d[1];
+                const int gb = gridP / 3, gx = gridP - 2 * gb;
+                // (all three always launched: each also zero-fills its partial rows)
+                precond_bulk_kernel<8, 4, 0><<<gb, kThreads, 0, st>>>(s.coef26, ne, s.pc_nodes_m, s.n_pc_m, s.R, vol, ax, ay, az,
+                                                                     s.pc_scale, s.inv_n_points, rows, pc_stride, NET::NP,
+                                                                     NET::NP + n_pc);
+                precond_bulk_kernel<8, 4, 1><<<gb, kThreads, 0, st>>>(s.coef26, ne, s.pc_nodes_p, s.n_pc_p, s.R, vol, ax, ay, az,
+                                                                     s.pc_scale, s.inv_n_points, rows + (size_t)gb * pc_stride,
+                                                                     pc_stride, NET::NP, NET::NP + n_pc);
+                precond_kernel<8, 4><<<gx, kThreads, 0, st>>>(s.coef26, ne, s.R, s.c_node, s.n_crossed, s.pc_params, s.pc_scale,
+                                                              s.inv_n_points, rows + (size_t)2 * gb * pc_stride, pc_stride,
+                                                              NET::NP, NET::NP + n_pc);
+            } else {
+                precond_kernel<8, 4><<<gridP, kThreads, 0, st>>>(s.coef26, ne, s.R, nullptr, ne, s.pc_params, s.pc_scale,
+                                                                 s.inv_n_points, rows, pc_stride, NET::NP, NET::NP + n_pc);
+            }
         }
     }
     const bool fused = s.faces && s.S && !s.nl && !pc;
@@ -2332,7 +2514,7 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     const bool pc = s.coef26 != nullptr;
     const int n_pc = pc ? PrecondNet<8, 4>::NP : 0;
     const int stride = NET::NP + n_pc + 1;
-    const int gridP = pc ? min(s.n_pc_rows, 2 * sms) : 0;
+    const int gridP = pc ? min(s.n_pc_rows, 3 * sms) : 0;
     const int rows_needed = 7 * gridG + gridR + gridE + gridP;
     if (rows_needed > s.n_partial_rows) {
         set_error("partials buffer has %d rows, %d needed", s.n_partial_rows, rows_needed);
@@ -2350,7 +2532,7 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
             s.coef26 + s.p0, a.n_points, nb, s.pc_params, s.pc_scale, s.Pc + s.p0);
     points_rows_kernel<<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, 7 * gridG, stride);
     if (pc)   // loss + d loss/d theta_P from the raw residuals kept in `rows`
-        precond_kernel<8, 4><<<gridP, kThreads, 0, st>>>(s.coef26 + s.p0, a.n_points, s.rows + s.p0, nb, s.pc_params,
+        precond_kernel<8, 4><<<gridP, kThreads, 0, st>>>(s.coef26 + s.p0, a.n_points, s.rows + s.p0, nullptr, nb, s.pc_params,
                                                          s.pc_scale, s.inv_n_points,
                                                          s.partials + (size_t)(7 * gridG + gridR + gridE) * stride, stride,
                                                          NET::NP, NET::NP + n_pc);
@@ -2440,6 +2622,8 @@ int nbm_loss_grad_shared_f32(const nbm_shared_step_t* s, nbm_stream_t stream) {
     if (s->coef26) {
         NBM_REQUIRE(s->pc_params, "null preconditioner parameters");
         NBM_REQUIRE(s->n_pc_rows >= 1 && s->n_partial_rows > s->n_pc_rows, "no partial rows for the preconditioner");
+        NBM_REQUIRE(!(s->pc_nodes_m || s->pc_nodes_p) || s->n_pc_rows >= 3, "the per-side preconditioner kernels need n_pc_rows >= 3");
+        NBM_REQUIRE((s->n_pc_m == 0 || s->pc_nodes_m) && (s->n_pc_p == 0 || s->pc_nodes_p), "null preconditioner node lists");
         NBM_REQUIRE(!s->S, "the fused adjoint path does not take a preconditioner");
         if (s->pc_d1 != 8 || s->pc_d2 != 4) {
             set_error("preconditioner widths (%d, %d) are outside the compiled kernel set ((8, 4))", s->pc_d1, s->pc_d2);

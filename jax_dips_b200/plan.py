@@ -474,7 +474,7 @@ class SharedPlan:
             self.gE = torch.zeros(max(cs.n, 1), dtype=torch.float32, device=dev)
             # the shared path launches at most one gradient CTA per SM: that many partial rows
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            n_pc_rows = sms if precond is not None else 0
+            n_pc_rows = 3 * sms if precond is not None else 0
             rows = min(L.nbm_step_partial_rows(), sms) + n_pc_rows
             self.partials = torch.zeros(rows * (P + 1), dtype=torch.float32, device=dev)
             self.loss_grad = torch.zeros(P + 1, dtype=torch.float32, device=dev)
@@ -504,6 +504,18 @@ class SharedPlan:
                 s.coef26 = cabi.ptr(self.coef26)
                 s.pc_d1, s.pc_d2, s.pc_scale = precond.widths[0], precond.widths[1], precond.scale
                 s.n_pc_rows = n_pc_rows
+                # uncrossed row nodes per side: they take the per-side preconditioner kernels (6 inputs instead of 26)
+                assert ne < 2 ** 31
+                fl = torch.zeros((ex, ey, ez), dtype=torch.int8, device=dev)
+                pv = (slice(self.HX, ex - self.HX), slice(self.HY, ey - self.HY), slice(self.HZ, ez - self.HZ))
+                fl[pv] = cs.flag.view(ex, ey, ez)[pv]
+                fl = fl.reshape(-1)
+                self.pc_nodes_m = torch.nonzero(fl < 0).reshape(-1).to(torch.int32).contiguous()
+                self.pc_nodes_p = torch.nonzero(fl > 0).reshape(-1).to(torch.int32).contiguous()
+                del fl
+                s.pc_nodes_m, s.n_pc_m = cabi.ptr(self.pc_nodes_m), self.pc_nodes_m.numel()
+                s.pc_nodes_p, s.n_pc_p = cabi.ptr(self.pc_nodes_p), self.pc_nodes_p.numel()
+                s.pc_d[0], s.pc_d[1], s.pc_d[2] = dx, dy, dz
             self.step = s
             self.xa, self.xb = xa, xb
             # the regression/cut-cell scratch is not needed by the step
