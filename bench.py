@@ -355,8 +355,8 @@ def main():
         d_coords.copy_(h_coords, non_blocking=True)
         step()
         h_out.copy_(lg, non_blocking=True)
+        h_params.copy_(params, non_blocking=True)   # the host keeps the parameters: next step's input
         torch.cuda.current_stream().synchronize()
-        h_params.copy_(params)  # the host keeps the parameters: next step's input
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
