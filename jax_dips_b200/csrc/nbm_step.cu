@@ -1751,15 +1751,17 @@ __global__ void __launch_bounds__(kThreads) precond_kernel(const float* __restri
 // 906-996).  One launch per side with S a compile-time constant: the first layer is 6 x D1 FMAs on top of a per-side
 // constant K, its gradient needs 6 x D1 accumulators plus sum(delta1) (the volume / area rows follow by scaling at the
 // end), and every weight is a constant-bank operand.  Crossed cells take the generic kernel over their node list.
+constexpr int kPcThreads = 384;   // 12 warps per SM at <= 168 registers
+
 template <int D1, int D2, int S>
-__global__ void __launch_bounds__(kThreads) precond_bulk_kernel(const float* __restrict__ coef26, int64_t ne,
+__global__ void __launch_bounds__(kPcThreads, 1) precond_bulk_kernel(const float* __restrict__ coef26, int64_t ne,
                                                                 const int32_t* __restrict__ nodes, int64_t n_nodes,
                                                                 float* __restrict__ R,
                                                                 float vol, float ax, float ay, float az, float scale,
                                                                 float inv_n, float* __restrict__ partials, int row_stride,
                                                                 int col0, int loss_col) {
     using PN = PrecondNet<D1, D2>;
-    constexpr int NPc = PN::NP, kWarps = kThreads / 32;
+    constexpr int NPc = PN::NP, kWarps = kPcThreads / 32;
     __shared__ float sred[kWarps][NPc + 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float area[6] = {ax, ax, ay, ay, az, az};
@@ -1772,21 +1774,33 @@ __global__ void __launch_bounds__(kThreads) precond_bulk_kernel(const float* __r
         for (int f = 0; f < 6; ++f) k = fmaf(area[f], c_PC[PN::oW1 + (14 + 2 * f + S) * D1 + j], k);
         K[j] = k;
     }
-    float aW1[6][D1], aD[D1], aW2[D1][D2], ab2[D2], aW3[D2], ab3 = 0.0f, loss = 0.0f;
+    // packed fp32x2 arithmetic, pairs along the output index (adjacent in the (in,out) row-major kernels)
+    static_assert(D1 % 2 == 0 && D2 % 2 == 0, "packed preconditioner kernel needs even widths");
+    constexpr int P1 = D1 / 2, P2 = D2 / 2;
+    auto cp = [](int idx) { return *reinterpret_cast<const u64*>(&c_PC[idx]); };
+    auto half = [](u64 v, int odd) { return odd ? hi32(v) : lo32(v); };
+    const u64 k2l = pk(kTwoLog2e, kTwoLog2e), mone = pk(-1.0f, -1.0f);
+    u64 K2[P1];
 #pragma unroll
-    for (int j = 0; j < D1; ++j) {
-        aD[j] = 0.0f;
+    for (int jp = 0; jp < P1; ++jp) K2[jp] = pk(K[2 * jp], K[2 * jp + 1]);
+    u64 aW1[6][P1], aD[P1], aW2[D1][P2], ab2[P2], aW3[P2];
+    float ab3 = 0.0f, loss = 0.0f;
 #pragma unroll
-        for (int f = 0; f < 6; ++f) aW1[f][j] = 0.0f;
+    for (int jp = 0; jp < P1; ++jp) {
+        aD[jp] = 0ull;
 #pragma unroll
-        for (int q = 0; q < D2; ++q) aW2[j][q] = 0.0f;
+        for (int f = 0; f < 6; ++f) aW1[f][jp] = 0ull;
     }
 #pragma unroll
-    for (int q = 0; q < D2; ++q) { ab2[q] = 0.0f; aW3[q] = 0.0f; }
+    for (int j = 0; j < D1; ++j)
+#pragma unroll
+        for (int qp = 0; qp < P2; ++qp) aW2[j][qp] = 0ull;
+#pragma unroll
+    for (int qp = 0; qp < P2; ++qp) { ab2[qp] = 0ull; aW3[qp] = 0ull; }
     // the uncrossed row nodes of side S come as a list (built once per level); software pipeline (8 warps per SM cannot
     // hide dependent global loads): node index two entries ahead, its residual and 6 coefficients one entry ahead
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    int64_t i = (int64_t)blockIdx.x * kThreads + tid;
+    const int64_t stride = (int64_t)gridDim.x * kPcThreads;
+    int64_t i = (int64_t)blockIdx.x * kPcThreads + tid;
     int e_0 = i < n_nodes ? __ldg(nodes + i) : -1;
     int e_1 = i + stride < n_nodes ? __ldg(nodes + i + stride) : -1;
     float r_n = 0.0f, c_n[6];
@@ -1811,24 +1825,30 @@ __global__ void __launch_bounds__(kThreads) precond_bulk_kernel(const float* __r
             for (int f = 0; f < 6; ++f) c_n[f] = __ldcs(coef26 + (int64_t)(2 * f + S) * ne + e_0);
         }
         if (r == 0.0f) continue;   // an exactly satisfied row contributes nothing
-        float h1[D1], h2[D2];
+        u64 c2[6], h1[P1], h2[P2];
 #pragma unroll
-        for (int j = 0; j < D1; ++j) {
-            float z = K[j];
+        for (int f = 0; f < 6; ++f) c2[f] = pk(c[f], c[f]);
 #pragma unroll
-            for (int f = 0; f < 6; ++f) z = fmaf(c[f], c_PC[PN::oW1 + (2 * f + S) * D1 + j], z);
-            h1[j] = tanh_acc(z);
+        for (int jp = 0; jp < P1; ++jp) {
+            u64 z = K2[jp];
+#pragma unroll
+            for (int f = 0; f < 6; ++f) z = ffma2(c2[f], cp(PN::oW1 + (2 * f + S) * D1 + 2 * jp), z);
+            h1[jp] = tanh2_prescaled_4mufu(fmul2(z, k2l));
         }
 #pragma unroll
-        for (int q = 0; q < D2; ++q) {
-            float z = c_PC[PN::ob2 + q];
+        for (int qp = 0; qp < P2; ++qp) {
+            u64 z = cp(PN::ob2 + 2 * qp);
 #pragma unroll
-            for (int j = 0; j < D1; ++j) z = fmaf(h1[j], c_PC[PN::oW2 + j * D2 + q], z);
-            h2[q] = tanh_acc(z);
+            for (int j = 0; j < D1; ++j) {
+                const float hj = half(h1[j / 2], j & 1);
+                z = ffma2(pk(hj, hj), cp(PN::oW2 + j * D2 + 2 * qp), z);
+            }
+            h2[qp] = tanh2_prescaled_4mufu(fmul2(z, k2l));
         }
-        float o = c_PC[PN::ob3];
+        u64 o2 = pk(c_PC[PN::ob3], 0.0f);
 #pragma unroll
-        for (int q = 0; q < D2; ++q) o = fmaf(h2[q], c_PC[PN::oW3 + q], o);
+        for (int qp = 0; qp < P2; ++qp) o2 = ffma2(h2[qp], cp(PN::oW3 + 2 * qp), o2);
+        const float o = lo32(o2) + hi32(o2);
         const float sg = 1.0f / (1.0f + __expf(-o));
         const float Pc = fmaf(scale, sg, 0.5f);
         const float pr = Pc * r;
@@ -1836,25 +1856,35 @@ __global__ void __launch_bounds__(kThreads) precond_bulk_kernel(const float* __r
         R[e] = Pc * pr;
         const float dO = (pr * r) * inv_n * scale * sg * (1.0f - sg);
         ab3 += dO;
-        float d2[D2];
+        const u64 dO2 = pk(dO, dO), dO2n = pk(-dO, -dO);
+        u64 d2[P2];
 #pragma unroll
-        for (int q = 0; q < D2; ++q) {
-            aW3[q] = fmaf(dO, h2[q], aW3[q]);
-            d2[q] = dO * c_PC[PN::oW3 + q] * fmaf(-h2[q], h2[q], 1.0f);
-            ab2[q] += d2[q];
+        for (int qp = 0; qp < P2; ++qp) {
+            aW3[qp] = ffma2(dO2, h2[qp], aW3[qp]);
+            const u64 omn = ffma2(h2[qp], h2[qp], mone);                       // h^2 - 1
+            d2[qp] = fmul2(fmul2(cp(PN::oW3 + 2 * qp), dO2n), omn);            // dO W3 (1 - h^2)
+            ab2[qp] = fadd2(ab2[qp], d2[qp]);
         }
+        float tn[D1];   // -(W2 delta2)_j
 #pragma unroll
         for (int j = 0; j < D1; ++j) {
-            float t = 0.0f;
+            const float hj = half(h1[j / 2], j & 1);
+            const u64 hj2 = pk(hj, hj);
+            u64 t2 = 0ull;
 #pragma unroll
-            for (int q = 0; q < D2; ++q) {
-                aW2[j][q] = fmaf(h1[j], d2[q], aW2[j][q]);
-                t = fmaf(c_PC[PN::oW2 + j * D2 + q], d2[q], t);
+            for (int qp = 0; qp < P2; ++qp) {
+                aW2[j][qp] = ffma2(hj2, d2[qp], aW2[j][qp]);
+                t2 = ffma2(cp(PN::oW2 + j * D2 + 2 * qp), d2[qp], t2);
             }
-            const float d1 = t * fmaf(-h1[j], h1[j], 1.0f);
-            aD[j] += d1;
+            tn[j] = -lo32(t2) - hi32(t2);
+        }
 #pragma unroll
-            for (int f = 0; f < 6; ++f) aW1[f][j] = fmaf(c[f], d1, aW1[f][j]);
+        for (int jp = 0; jp < P1; ++jp) {
+            const u64 omn = ffma2(h1[jp], h1[jp], mone);
+            const u64 d1 = fmul2(pk(tn[2 * jp], tn[2 * jp + 1]), omn);        // (W2 delta2)(1 - h^2)
+            aD[jp] = fadd2(aD[jp], d1);
+#pragma unroll
+            for (int f = 0; f < 6; ++f) aW1[f][jp] = ffma2(c2[f], d1, aW1[f][jp]);
         }
     }
     // block reduction into this CTA's partial row; rows of W1 that belong to the other side stay zero
@@ -1863,11 +1893,11 @@ __global__ void __launch_bounds__(kThreads) precond_bulk_kernel(const float* __r
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         return v;
     };
-    for (int i = tid; i < kWarps * (NPc + 1); i += kThreads) (&sred[0][0])[i] = 0.0f;
+    for (int k = tid; k < kWarps * (NPc + 1); k += kPcThreads) (&sred[0][0])[k] = 0.0f;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < D1; ++j) {
-        float v = wsum(aD[j]);
+        float v = wsum(half(aD[j / 2], j & 1));
         if (lane == 0) {
             sred[warp][PN::ob1 + j] = v;
             sred[warp][PN::oW1 + (12 + S) * D1 + j] = vol * v;
@@ -1876,20 +1906,20 @@ __global__ void __launch_bounds__(kThreads) precond_bulk_kernel(const float* __r
         }
 #pragma unroll
         for (int f = 0; f < 6; ++f) {
-            v = wsum(aW1[f][j]);
+            v = wsum(half(aW1[f][j / 2], j & 1));
             if (lane == 0) sred[warp][PN::oW1 + (2 * f + S) * D1 + j] = v;
         }
 #pragma unroll
         for (int q = 0; q < D2; ++q) {
-            v = wsum(aW2[j][q]);
+            v = wsum(half(aW2[j][q / 2], q & 1));
             if (lane == 0) sred[warp][PN::oW2 + j * D2 + q] = v;
         }
     }
 #pragma unroll
     for (int q = 0; q < D2; ++q) {
-        float v = wsum(ab2[q]);
+        float v = wsum(half(ab2[q / 2], q & 1));
         if (lane == 0) sred[warp][PN::ob2 + q] = v;
-        v = wsum(aW3[q]);
+        v = wsum(half(aW3[q / 2], q & 1));
         if (lane == 0) sred[warp][PN::oW3 + q] = v;
     }
     {
@@ -1900,7 +1930,7 @@ __global__ void __launch_bounds__(kThreads) precond_bulk_kernel(const float* __r
     }
     __syncthreads();
     float* row = partials + (size_t)blockIdx.x * row_stride;
-    for (int i = tid; i <= NPc; i += kThreads) {
+    for (int i = tid; i <= NPc; i += kPcThreads) {
         float v = 0.0f;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) v += sred[w][i];
@@ -2219,10 +2249,10 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
                 const float ax = s.pc_d[1] * s.pc_d[2], ay = s.pc_d[0] * s.pc_d[2], az = s.pc_d[0] * s.pc_d[1];
                 const int gb = gridP / 3, gx = gridP - 2 * gb;
                 // (all three always launched: each also zero-fills its partial rows)
-                precond_bulk_kernel<8, 4, 0><<<gb, kThreads, 0, st>>>(s.coef26, ne, s.pc_nodes_m, s.n_pc_m, s.R, vol, ax, ay, az,
+                precond_bulk_kernel<8, 4, 0><<<gb, kPcThreads, 0, st>>>(s.coef26, ne, s.pc_nodes_m, s.n_pc_m, s.R, vol, ax, ay, az,
                                                                      s.pc_scale, s.inv_n_points, rows, pc_stride, NET::NP,
                                                                      NET::NP + n_pc);
-                precond_bulk_kernel<8, 4, 1><<<gb, kThreads, 0, st>>>(s.coef26, ne, s.pc_nodes_p, s.n_pc_p, s.R, vol, ax, ay, az,
+                precond_bulk_kernel<8, 4, 1><<<gb, kPcThreads, 0, st>>>(s.coef26, ne, s.pc_nodes_p, s.n_pc_p, s.R, vol, ax, ay, az,
                                                                      s.pc_scale, s.inv_n_points, rows + (size_t)gb * pc_stride,
                                                                      pc_stride, NET::NP, NET::NP + n_pc);
                 precond_kernel<8, 4><<<gx, kThreads, 0, st>>>(s.coef26, ne, s.R, s.c_node, s.n_crossed, s.pc_params, s.pc_scale,
