@@ -4,7 +4,9 @@
 // the rank-local lattice (fwd_nodes), crossed nodes get their far-side value from the 27-point
 // regression table (extrap), every row is a 7-point stencil on U (+ irregular corrections),
 // the adjoint stencil gathers d loss/d U per node, and one fused forward-recompute + backward
-// kernel turns it into per-CTA partial sums of d loss/d theta held in registers.
+// kernel (node_grad: 12 warps/SM, pair-split outer-product accumulators) turns it into per-CTA
+// partial sums of d loss/d theta held in registers.  Optional: the learned preconditioner kernels
+// between the residual and the adjoint stage; the TMA-staged fused adjoint + gradient kernel.
 //
 // The network parameters live in __constant__ memory so that every FFMA takes its weight as a
 // constant-bank operand (no load, no register).
@@ -1797,7 +1799,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) precond_bulk_kernel(const float
         for (int qp = 0; qp < P2; ++qp) aW2[j][qp] = 0ull;
 #pragma unroll
     for (int qp = 0; qp < P2; ++qp) { ab2[qp] = 0ull; aW3[qp] = 0ull; }
-    // the uncrossed row nodes of side S come as a list (built once per level); software pipeline (8 warps per SM cannot
+    // the uncrossed row nodes of side S come as a list (built once per level); software pipeline (12 warps per SM cannot
     // hide dependent global loads): node index two entries ahead, its residual and 6 coefficients one entry ahead
     const int64_t stride = (int64_t)gridDim.x * kPcThreads;
     int64_t i = (int64_t)blockIdx.x * kPcThreads + tid;
