@@ -274,16 +274,38 @@ def main():
         if int(flag.item()) == 0:
             comm = None
 
-    def step():
-        nplan.upload_params(net, params)
+    net_struct = net.struct()
+
+    def step_from(upload):
+        """one optimizer step: parameters into the constant bank (`upload`), loss + gradient partial rows, [all-reduce],
+        and ONE kernel for row reduction + optax chain + staging of the next step's parameter copies"""
+        upload()
+        partials, rows = None, 0
         if comm is not None:
             pl.loss_grad_launch(comm=comm)
-        else:
+        elif world > 1:
             pl.loss_grad_launch()
-            if world > 1:
-                dist.all_reduce(lg, op=dist.ReduceOp.SUM)
-        cabi.check(L.nbm_apply_update_f32(C.byref(ostruct), cabi.ptr(lg), cabi.ptr(params), cabi.ptr(opt_state),
-                                          cabi.ptr(opt_count), None, cabi.stream_ptr()))
+            dist.all_reduce(lg, op=dist.ReduceOp.SUM)
+        else:
+            pl.step.stages = 0x1f
+            try:
+                pl.loss_grad_launch()
+            finally:
+                pl.step.stages = 0
+            partials, rows = pl.partials, pl.step.n_partial_rows
+        cabi.check(L.nbm_finalize_step_f32(C.byref(ostruct), C.byref(net_struct), cabi.ptr(partials), rows, P + 1,
+                                           cabi.ptr(lg), cabi.ptr(params), cabi.ptr(opt_state), cabi.ptr(opt_count), None,
+                                           cabi.stream_ptr()), "nbm_finalize_step_f32")
+
+    # device-resident training: the previous step staged the parameter copies (what Trainer._step does)
+    def step():
+        step_from(lambda: cabi.check(L.nbm_upload_staged_params(cabi.stream_ptr()), "nbm_upload_staged_params"))
+
+    # parameters handed in by the host every step (the e2e leg): the full upload (prep kernel + copy)
+    def step_host_params():
+        step_from(lambda: nplan.upload_params(net, params))
+
+    nplan.upload_params(net, params)   # stages the initial parameters
 
     def barrier():
         if world > 1:
@@ -300,14 +322,19 @@ def main():
             for _ in range(2):
                 eager_step()
             barrier()
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream())
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.stream(side):
-                with torch.cuda.graph(graph, stream=side):
-                    eager_step()
-            torch.cuda.current_stream().wait_stream(side)
-            step = graph.replay
+
+            def capture(fn):
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(graph, stream=side):
+                        fn()
+                torch.cuda.current_stream().wait_stream(side)
+                return graph
+
+            g_dev, g_host = capture(step), capture(step_host_params)
+            step, step_host_params = g_dev.replay, g_host.replay
             used_graph = True
         except Exception as exc:  # noqa: BLE001
             if rank == 0:
@@ -315,8 +342,9 @@ def main():
             step = eager_step
             torch.cuda.synchronize()
 
-    # prep_params, fwd_nodes, residual, adjoint, node_grad, reduce, apply_update (+ 2 list kernels each for crossed sites / irregular rows)
-    launches_per_step = 7 + (1 if pl.sites.n > 0 else 0) * 2 + (1 if pl.n_irr > 0 else 0) * 2
+    # fwd_nodes, residual, adjoint, node_grad, finalize (+ 2 list kernels each for crossed sites / irregular rows); on several
+    # GPUs the peer all-reduce kernel in addition
+    launches_per_step = (6 if world > 1 else 5) + (1 if pl.sites.n > 0 else 0) * 2 + (1 if pl.n_irr > 0 else 0) * 2
 
     # ---------------- value: device-resident inputs -------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -353,7 +381,7 @@ def main():
     for _ in range(args.steps):
         params.copy_(h_params, non_blocking=True)
         d_coords.copy_(h_coords, non_blocking=True)
-        step()
+        step_host_params()
         h_out.copy_(lg, non_blocking=True)
         h_params.copy_(params, non_blocking=True)   # the host keeps the parameters: next step's input
         torch.cuda.current_stream().synchronize()

@@ -353,6 +353,19 @@ typedef struct {
 int nbm_apply_update_f32(const nbm_optimizer_t* opt, const float* loss_grad, float* params,
                          float* state, int32_t* count, float* loss_hist, nbm_stream_t stream);
 
+/* One kernel for the tail of an optimizer step (what the reference does in `optimizer.update` + `apply_updates` right
+ * after `value_and_grad`, trainer.py:786-788): [sum the partial rows of nbm_loss_grad_shared_f32 run with
+ * stages = everything but NBM_STAGE_REDUCE -> loss_grad] -> optax chain -> params, AND the refresh of the library's
+ * staged copies of the network parameters (plain, pre-scaled, transposed), so that the next step starts with
+ * nbm_upload_staged_params() (one device-to-device copy into the __constant__ bank) instead of nbm_upload_params().
+ * partials == NULL: loss_grad is taken as given (after an all-reduce, or from nbm_loss_grad_points_f32).
+ * opt->n_params may exceed the network's parameter count (learned preconditioner at the tail). */
+int nbm_finalize_step_f32(const nbm_optimizer_t* opt, const nbm_net_t* net, const float* partials, int rows,
+                          int row_stride, float* loss_grad, float* params, float* state, int32_t* count,
+                          float* loss_hist, nbm_stream_t stream);
+/* __constant__ bank <- the staged copies written by the last nbm_upload_params / nbm_finalize_step_f32 on this device */
+int nbm_upload_staged_params(nbm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K4 (multi-GPU): partial-row reduction FUSED with the gradient all-reduce over NVLink peer memory.
  * Replaces jax.lax.psum(grads) / psum(loss) (trainer.py:829-830) = SUM over devices.

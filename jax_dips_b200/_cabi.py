@@ -126,6 +126,8 @@ SYMBOLS = {
     "nbm_comm_error": (C.c_int, [C.c_void_p]),
     "nbm_reduce_allreduce_f32": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_void_p), c_fp, c_fp, c_fp]),
     "nbm_apply_update_f32": (C.c_int, [_P(Optimizer), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "nbm_finalize_step_f32": (C.c_int, [_P(Optimizer), _P(Net), c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "nbm_upload_staged_params": (C.c_int, [c_fp]),
     "nbm_evaluate_f32": (C.c_int, [_P(Net), _P(Lvl), c_fp, C.c_int64, c_f, c_f, c_f, c_fp, c_fp, c_fp, c_fp]),
 }
 

@@ -1987,9 +1987,9 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int r
 }
 
 // K4b: optax chain (solvers/optimizers.py:33-54, optax 0.1.5 semantics), one CTA
-__global__ void apply_update_kernel(nbm_optimizer_t o, const float* __restrict__ loss_grad, float* __restrict__ params,
-                                    float* __restrict__ state, int32_t* __restrict__ count,
-                                    float* __restrict__ loss_hist) {
+__device__ __forceinline__ void optax_update(const nbm_optimizer_t& o, const float* __restrict__ loss_grad,
+                                             float* __restrict__ params, float* __restrict__ state,
+                                             int32_t* __restrict__ count, float* __restrict__ loss_hist) {
     __shared__ float red[32];
     __shared__ float s_scale;
     int P = o.n_params;
@@ -2039,6 +2039,65 @@ __global__ void apply_update_kernel(nbm_optimizer_t o, const float* __restrict__
     }
 }
 
+__global__ void apply_update_kernel(nbm_optimizer_t o, const float* __restrict__ loss_grad, float* __restrict__ params,
+                                    float* __restrict__ state, int32_t* __restrict__ count,
+                                    float* __restrict__ loss_hist) {
+    optax_update(o, loss_grad, params, state, count, loss_hist);
+}
+
+// the three staged copies of network parameter i (see c_P): plain, pre-scaled by 2 log2(e), transposed + negated
+__device__ __forceinline__ void stage_param(const nbm_net_t& net, int i, float v, float* __restrict__ stage) {
+    int np = 3 * net.hidden_p + net.hidden_p + (net.layers_p - 1) * (net.hidden_p * net.hidden_p + net.hidden_p) +
+             net.hidden_p + 1;
+    int k = i < np ? i : i - np;
+    int H = i < np ? net.hidden_p : net.hidden_m;
+    int Lh = i < np ? net.layers_p : net.layers_m;
+    int hidden_len = 4 * H + (Lh - 1) * (H * H + H);  // everything before the output layer
+    stage[i] = v;
+    stage[NBM_MAXP + i] = k < hidden_len ? v * kTwoLog2e : v;
+    // third copy: hidden HxH matrices transposed in place AND negated: the backward pass forms (a^2 - 1) = -(1 - a^2)
+    // with one FFMA2 (no sign flips) and gets the sign back from -W^T
+    int dst = i;
+    float v3 = v;
+    if (k >= 4 * H && k < hidden_len) {
+        int q = (k - 4 * H) % (H * H + H);
+        if (q < H * H) {
+            dst = i - q + (q % H) * H + q / H;
+            v3 = -v;
+        }
+    }
+    stage[2 * NBM_MAXP + dst] = v3;
+}
+
+// K4 fused: [partial rows -> loss_grad] -> optax chain -> staged parameter copies for the next step.  One CTA of 1024.
+__global__ void __launch_bounds__(1024) finalize_step_kernel(nbm_optimizer_t o, nbm_net_t net, int n_net,
+                                                             const float* __restrict__ partials, int rows, int np1,
+                                                             float* __restrict__ loss_grad, float* __restrict__ params,
+                                                             float* __restrict__ state, int32_t* __restrict__ count,
+                                                             float* __restrict__ loss_hist, float* __restrict__ stage) {
+    extern __shared__ float sred[];   // [ngrp][np1]
+    const int t = threadIdx.x;
+    if (partials) {
+        const int ngrp = max(1, (int)blockDim.x / np1);
+        const int grp = t / np1, col = t - grp * np1;
+        if (grp < ngrp) {
+            float v = 0.0f;
+            for (int r = grp; r < rows; r += ngrp) v += partials[(size_t)r * np1 + col];
+            sred[grp * np1 + col] = v;
+        }
+        __syncthreads();
+        if (t < np1) {
+            float v = 0.0f;
+            for (int g = 0; g < ngrp; ++g) v += sred[g * np1 + t];
+            loss_grad[t] = v;
+        }
+        __syncthreads();
+    }
+    optax_update(o, loss_grad, params, state, count, loss_hist);
+    __syncthreads();
+    for (int i = t; i < n_net; i += blockDim.x) stage_param(net, i, params[i], stage);
+}
+
 // K5: evaluation (trainer.py:960-977)
 template <class NET, int LP, int HP, int LM, int HM>
 __global__ void evaluate_kernel(nbm_lvl_t L, const float* __restrict__ pts, int64_t n, float dx, float dy, float dz,
@@ -2073,27 +2132,7 @@ __global__ void evaluate_kernel(nbm_lvl_t L, const float* __restrict__ pts, int6
 __global__ void prep_params_kernel(nbm_net_t net, const float* __restrict__ params, float* __restrict__ stage, int P) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
-    float v = params[i];
-    int np = 3 * net.hidden_p + net.hidden_p + (net.layers_p - 1) * (net.hidden_p * net.hidden_p + net.hidden_p) +
-             net.hidden_p + 1;
-    int k = i < np ? i : i - np;
-    int H = i < np ? net.hidden_p : net.hidden_m;
-    int Lh = i < np ? net.layers_p : net.layers_m;
-    int hidden_len = 4 * H + (Lh - 1) * (H * H + H);  // everything before the output layer
-    stage[i] = v;
-    stage[NBM_MAXP + i] = k < hidden_len ? v * kTwoLog2e : v;
-    // third copy: hidden HxH matrices transposed in place AND negated: the backward pass forms (a^2 - 1) = -(1 - a^2)
-    // with one FFMA2 (no sign flips) and gets the sign back from -W^T
-    int dst = i;
-    float v3 = v;
-    if (k >= 4 * H && k < hidden_len) {
-        int q = (k - 4 * H) % (H * H + H);
-        if (q < H * H) {
-            dst = i - q + (q % H) * H + q / H;
-            v3 = -v;
-        }
-    }
-    stage[2 * NBM_MAXP + dst] = v3;
+    stage_param(net, i, params[i], stage);
 }
 
 
@@ -2760,6 +2799,40 @@ int nbm_apply_update_f32(const nbm_optimizer_t* opt, const float* loss_grad, flo
     apply_update_kernel<<<1, 256, 0, as_stream(stream)>>>(*opt, loss_grad, params, state, count, loss_hist);
     NBM_LAUNCH_CHECK("apply_update");
     return NBM_OK;
+}
+
+int nbm_finalize_step_f32(const nbm_optimizer_t* opt, const nbm_net_t* net, const float* partials, int rows,
+                          int row_stride, float* loss_grad, float* params, float* state, int32_t* count,
+                          float* loss_hist, nbm_stream_t stream) {
+    NBM_REQUIRE(opt && net && loss_grad && params && state && count, "null pointer");
+    NBM_REQUIRE(opt->n_params > 0 && opt->n_params <= NBM_MAXP, "bad parameter count");
+    if (opt->optimizer < 0 || opt->optimizer > 2 || opt->scheduler < 0 || opt->scheduler > 1) {
+        set_error("unknown optimizer id %d", opt->optimizer);
+        return NBM_ERR_UNSUPPORTED;
+    }
+    const int n_net = nbm_net_num_params(net);
+    NBM_REQUIRE(n_net > 0 && n_net <= opt->n_params, "the optimizer must cover at least the network's parameters");
+    NBM_REQUIRE(!partials || (rows > 0 && row_stride == opt->n_params + 1 && row_stride <= 1024),
+                "partial rows must be n_params + 1 <= 1024 floats wide");
+    cudaStream_t st = as_stream(stream);
+    float* stage = nullptr;
+    int rc = cuda_check(cudaGetSymbolAddress((void**)&stage, g_stage), "staging buffer");
+    if (rc) return rc;
+    const int threads = 1024;
+    const int ngrp = partials ? (threads / row_stride > 0 ? threads / row_stride : 1) : 0;
+    finalize_step_kernel<<<1, threads, sizeof(float) * (size_t)ngrp * (partials ? row_stride : 0), st>>>(
+        *opt, *net, n_net, partials, rows, row_stride, loss_grad, params, state, count, loss_hist, stage);
+    NBM_LAUNCH_CHECK("finalize_step");
+    return NBM_OK;
+}
+
+int nbm_upload_staged_params(nbm_stream_t stream) {
+    float* stage = nullptr;
+    int rc = cuda_check(cudaGetSymbolAddress((void**)&stage, g_stage), "staging buffer");
+    if (rc) return rc;
+    return cuda_check(cudaMemcpyToSymbolAsync(c_P, stage, sizeof(float) * 3 * NBM_MAXP, 0, cudaMemcpyDeviceToDevice,
+                                              as_stream(stream)),
+                      "upload staged params");
 }
 
 int nbm_evaluate_f32(const nbm_net_t* net, const nbm_lvl_t* lvl, const float* pts, int64_t n, float dx, float dy,

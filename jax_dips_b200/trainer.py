@@ -326,22 +326,40 @@ class Trainer:
         return plan.loss_grad_launch()
 
     def _step(self, plan, loss_hist: Optional[torch.Tensor], allreduce: bool):
-        """update (trainer.py:783-789) / update_multi_gpu (:824-834) on the current stream"""
+        """update (trainer.py:783-789) / update_multi_gpu (:824-834) on the current stream.  Inside the training loops
+        the parameters reach the constant bank from the copies the previous step's finalize kernel staged
+        (`_begin_training` stages the initial ones); the partial-row reduction, the optax chain and that staging are one
+        kernel."""
+        L = cabi.lib()
+        cabi.check(L.nbm_upload_staged_params(cabi.stream_ptr()), "nbm_upload_staged_params")
+        net = self.net.struct()
+        partials, rows = None, 0
         d = _dist() if allreduce else None
         if d is not None and d.get_world_size() > 1:
             comm = self._peer_comm() if (self.allreduce_kind == "peer" and isinstance(plan, (SharedPlan, EmptyPlan))) else None
-            upload_params(self.net, self.params)
             if comm is not None:
                 lg = plan.loss_grad_launch(comm=comm)    # reduction fused with the psum over NVLink peer memory
             else:
                 lg = plan.loss_grad_launch()
                 d.all_reduce(lg, op=d.ReduceOp.SUM)      # psum of grads and loss (:829-830)
+        elif isinstance(plan, SharedPlan):
+            plan.step.stages = 0x1f                      # everything but the reduction: the finalize kernel sums the rows
+            try:
+                lg = plan.loss_grad_launch()
+            finally:
+                plan.step.stages = 0
+            partials, rows = plan.partials, plan.step.n_partial_rows
         else:
-            lg = self.loss_and_grad(self.params, plan)
-        cabi.check(cabi.lib().nbm_apply_update_f32(C.byref(self._optimizer_struct()), cabi.ptr(lg),
-                                                   cabi.ptr(self.params), cabi.ptr(self.opt_state),
-                                                   cabi.ptr(self.opt_count), cabi.ptr(loss_hist),
-                                                   cabi.stream_ptr()), "nbm_apply_update_f32")
+            lg = plan.loss_grad_launch()
+        cabi.check(L.nbm_finalize_step_f32(C.byref(self._optimizer_struct()), C.byref(net), cabi.ptr(partials), rows,
+                                           self.n_params + 1, cabi.ptr(lg), cabi.ptr(self.params),
+                                           cabi.ptr(self.opt_state), cabi.ptr(self.opt_count), cabi.ptr(loss_hist),
+                                           cabi.stream_ptr()), "nbm_finalize_step_f32")
+
+    def _begin_training(self) -> None:
+        """stage the current parameters (plain / pre-scaled / transposed copies) for the first step of a loop"""
+        with torch.cuda.device(self.device):
+            upload_params(self.net, self.params)
 
     def _peer_comm(self):
         if self._comm is None:
@@ -442,6 +460,7 @@ class Trainer:
         self._warn_if_padded(DD)
         ranges = DD.ranges(0)
         nb = len(ranges)
+        self._begin_training()
         with torch.cuda.device(self.device):
             loss_hist = torch.zeros(self.num_epochs * nb + 1, dtype=torch.float32, device=self.device)
             base = int(self.opt_count.item())
@@ -483,6 +502,7 @@ class Trainer:
             self.allreduce_kind = "nccl"
         loss_epochs, epoch_store = [], []
         t0 = time.time()
+        self._begin_training()
         with torch.cuda.device(self.device):
             loss_hist = torch.zeros(self.num_epochs * nb + 1, dtype=torch.float32, device=self.device)
             base = int(self.opt_count.item())
