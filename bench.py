@@ -36,7 +36,7 @@ F_GRAD = 0.93e3       # FLOP per lattice node for the dominant kernel (forward r
 B_STEP_FACES = 52.0
 B_STEP_ROWS = 76.0
 # DRAM bytes (read + write) of one node_grad launch at 256^3, `ncu --set full` (profiles/r1_ncu_summary.md)
-NODE_GRAD_TRAFFIC_256 = 160000000   # 155.9 MB read + 4.1 MB written (profiles/r1c_ncu_summary.md)
+NODE_GRAD_TRAFFIC_256 = 160527360   # read + written, `ncu --set full` (profiles/r1d_ncu_summary.md)
 
 
 def parse():

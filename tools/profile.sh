@@ -3,7 +3,7 @@
 # step kernels.  Outputs go to gpurun_out/; summaries are copied into profiles/ by tools/summarise_profile.py.
 set -u
 TAG=${1:-r1b}
-K='regex:^(void )?(nbm::)?(fwd_nodes|residual|adjoint|node_grad|extrap|irregular|reduce_partials|apply_update|prep_params|precond)'
+K='regex:^(void )?(nbm::)?(fwd_nodes|residual|adjoint|node_grad|extrap|irregular|reduce_partials|apply_update|prep_params|precond|finalize_step)'
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 200 --csv \
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-graph \
     > gpurun_out/ncu_bench_${TAG}.log 2>&1

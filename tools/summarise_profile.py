@@ -22,7 +22,7 @@ P = os.path.join(ROOT, "profiles")
 
 STEP = ["prep_params_kernel", "fwd_nodes_kernel", "extrap_kernel", "residual", "irregular_fwd_kernel", "adjoint",
         "irregular_bwd_kernel", "extrap_bwd_kernel", "node_grad", "precond_kernel", "reduce_partials_kernel",
-        "apply_update_kernel"]
+        "apply_update_kernel", "finalize_step_kernel"]
 
 
 def short(name):
