@@ -230,3 +230,27 @@ def test_empty_plan_contributes_zeros():
             assert rows == 1 and np1 == 6 and float(partials.abs().sum()) == 0.0
             target.copy_(partials + 1.0)      # what the peers contributed
     assert float(pl.loss_grad_launch(comm=FakeComm()).sum()) == 6.0
+
+
+def test_parameter_tree_roundtrip_with_the_preconditioner():
+    """flat vector [network | preconditioner] <-> the checkpoint tree: haiku keys for the network (trainer.py:323), the flax
+    tree of nn/preconditioner.py under "preconditioner" (trainer.py:236-243)"""
+    from jax_dips_b200 import trainer as ntrainer
+    from jax_dips_b200.plan import NetShape, PrecondShape
+    net = NetShape()
+    pc = PrecondShape.from_model_dict({"preconditioner": {"enable": True, "layer_widths": [8, 4], "scaling_coeff": 2.0}})
+    assert pc.scale == 2.0 and pc.n_params == 26 * 8 + 8 + 8 * 4 + 4 + 4 + 1
+    assert PrecondShape.from_model_dict({"preconditioner": {"enable": False}}) is None
+    assert PrecondShape.from_model_dict({}) is None
+    with pytest.raises(NotImplementedError):
+        PrecondShape([8, 4, 2])
+    flat = torch.cat((ntrainer.haiku_init(net, 1), ntrainer.precond_init(pc, 1)))
+    assert flat.numel() == net.n_params + pc.n_params
+    tree = ntrainer.params_to_tree(net, flat, pc)
+    dense = tree["preconditioner"]["params"]
+    assert dense["Dense_0"]["kernel"].shape == (26, 8) and dense["Dense_1"]["kernel"].shape == (8, 4)
+    assert dense["Dense_2"]["kernel"].shape == (4, 1) and dense["Dense_2"]["bias"].shape == (1,)
+    lim = (6.0 / (26 + 8)) ** 0.5                          # glorot_uniform (nn/preconditioner.py:20)
+    assert float(np.abs(dense["Dense_0"]["kernel"]).max()) <= lim and float(np.abs(dense["Dense_0"]["bias"]).max()) == 0.0
+    assert torch.equal(ntrainer.tree_to_params(net, tree, pc), flat)
+    assert ntrainer.params_to_tree(net, flat[:net.n_params])["preconditioner"] == {}
