@@ -65,12 +65,17 @@ def reference_loss_fn(problem, n_tr, n_lvl, interp, point_idx, zoom):
     return loss, shape
 
 
-CASES = [("sphere_tri_z0", "sphere", "trilinear"), ("star_tri_z0", "star", "trilinear")]
+CASES = [("sphere_tri_z0", "sphere", "trilinear"), ("star_tri_z0", "star", "trilinear"),
+         ("sphere_tri_z1", "sphere", "trilinear"),      # zoom level 1: cell size = spacing / 2
+         ("sphere_quad_z0", "sphere", "quadratic")]     # non-oscillatory quadratic level-set interpolant
 
 
 def main():
     outdir = os.path.join(ROOT, "tests", "golden")
+    only = set(sys.argv[1:])
     for name, pname, interp in CASES:
+        if only and name not in only:
+            continue
         z = np.load(os.path.join(outdir, f"{name}.npz"))
         P = mg.problems.PROBLEMS[pname]()
         idx, n_tr, n_lvl, zoom = z["point_idx"], int(z["n_tr"]), int(z["n_lvl"]), int(z["zoom"])
