@@ -62,6 +62,19 @@ typedef struct {
     int gx, gy, gz;          /* ghosted dims = n+2 */
     int interp;              /* nbm_interp */
     float perturb_eps;       /* 1e-10 when the level set is wrapped in perturb_level_set_fn, else 0 */
+    /* SAMPLED level set (an analytic lvl_set_fn, as tests/test_poisson.py passes one: the reference calls the user's
+     * callable wherever it needs phi, discretization.py:90).  A callable cannot run inside a kernel, but every level-set
+     * evaluation of the path happens at positions known per level: the host evaluates the callable there (same fp32
+     * position arithmetic as the kernels) and hands the values in; phi_g/xg/yg/zg may then be NULL:
+     *   corner_phi[c*8 + v]  phi at the 8 cell corners of crossed site c (corner order of
+     *                        geometric_integrations_per_point.py:212-224)        -> nbm_cutcell_f32
+     *   cube_phi[c*27 + q]   phi at the 27 cube vertices s + X_q of crossed site c  -> nbm_regression_f32
+     *   eval_phi[i*7 + k]    phi at evaluation point i and at i +- dx, +- dy, +- dz (k = 0, x-, x+, y-, y+, z-, z+)
+     *                                                                             -> nbm_evaluate_f32
+     * (classification is then done by the host too: nbm_classify_f32 needs the grid form.) */
+    const float* corner_phi;
+    const float* cube_phi;
+    const float* eval_phi;
 } nbm_lvl_t;
 
 /* phi (nx,ny,nz) -> phi_g (nx+2,ny+2,nz+2) and x -> xg etc. (linear extrapolation, x then y then z). */

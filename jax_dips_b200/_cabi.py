@@ -25,7 +25,8 @@ class NbmError(RuntimeError):
 class Lvl(C.Structure):
     _fields_ = [("phi_g", c_fp), ("xg", c_fp), ("yg", c_fp), ("zg", c_fp),
                 ("gx", C.c_int), ("gy", C.c_int), ("gz", C.c_int),
-                ("interp", C.c_int), ("perturb_eps", c_f)]
+                ("interp", C.c_int), ("perturb_eps", c_f),
+                ("corner_phi", c_fp), ("cube_phi", c_fp), ("eval_phi", c_fp)]
 
 
 class Lattice(C.Structure):

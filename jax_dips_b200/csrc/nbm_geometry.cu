@@ -205,7 +205,17 @@ __global__ void cutcell_kernel(nbm_lvl_t L, nbm_lattice_t lat, float dx, float d
     if (c >= n) return;
     SitePos s = site_position(lat, idx[c]);
     float P[8][3], ph8[8];
-    corner_phis(L, s.x, s.y, s.z, dx, dy, dz, P, ph8);
+    if (L.corner_phi) {   // sampled level set: positions formed as in corner_phis, values handed in by the host
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            P[v][0] = (c_corner_sign[v][0] * dx) * 0.5f + s.x;
+            P[v][1] = (c_corner_sign[v][1] * dy) * 0.5f + s.y;
+            P[v][2] = (c_corner_sign[v][2] * dz) * 0.5f + s.z;
+            ph8[v] = L.corner_phi[c * 8 + v];
+        }
+    } else {
+        corner_phis(L, s.x, s.y, s.z, dx, dy, dz, P, ph8);
+    }
     const float face_coord[6] = {s.x - 0.5f * dx, s.x + 0.5f * dx, s.y - 0.5f * dy,
                                  s.y + 0.5f * dy, s.z - 0.5f * dz, s.z + 0.5f * dz};
     const float face_atol[6] = {1e-10f * dx, 1e-10f * dx, 1e-10f * dy, 1e-10f * dy, 1e-10f * dz, 1e-10f * dz};
@@ -388,7 +398,7 @@ __global__ void regression_kernel(nbm_lvl_t L, nbm_lattice_t lat, float dx, floa
     uint32_t wp_bits = 0, wm_bits = 0, side_bits = 0;
     for (int q = 0; q < 27; ++q) {
         float X0 = (float)(q % 3 - 1) * dx, X1 = (float)((q / 3) % 3 - 1) * dy, X2 = (float)(q / 9 - 1) * dz;
-        float ph = phi_at(L, s.x + X0, s.y + X1, s.z + X2);
+        float ph = L.cube_phi ? L.cube_phi[c * 27 + q] : phi_at(L, s.x + X0, s.y + X1, s.z + X2);
         if (ph >= 0.0f) side_bits |= (1u << q);
         if (ph > 0.0f) {
             wp_bits |= (1u << q);
@@ -399,12 +409,21 @@ __global__ void regression_kernel(nbm_lvl_t L, nbm_lattice_t lat, float dx, floa
         }
     }
     // normal (:199-218)
-    float gx = (phi_at(L, s.x + dx, s.y, s.z) - phi_at(L, s.x - dx, s.y, s.z)) / (2.0f * dx);
-    float gy = (phi_at(L, s.x, s.y + dy, s.z) - phi_at(L, s.x, s.y - dy, s.z)) / (2.0f * dy);
-    float gz = (phi_at(L, s.x, s.y, s.z + dz) - phi_at(L, s.x, s.y, s.z - dz)) / (2.0f * dz);
+    float gx, gy, gz, d0;
+    if (L.cube_phi) {   // s +- d e_a are the cube vertices 13 +- 1, 13 +- 3, 13 +- 9 (same fp32 positions)
+        const float* cp = L.cube_phi + c * 27;
+        gx = (cp[14] - cp[12]) / (2.0f * dx);
+        gy = (cp[16] - cp[10]) / (2.0f * dy);
+        gz = (cp[22] - cp[4]) / (2.0f * dz);
+        d0 = cp[13];
+    } else {
+        gx = (phi_at(L, s.x + dx, s.y, s.z) - phi_at(L, s.x - dx, s.y, s.z)) / (2.0f * dx);
+        gy = (phi_at(L, s.x, s.y + dy, s.z) - phi_at(L, s.x, s.y - dy, s.z)) / (2.0f * dy);
+        gz = (phi_at(L, s.x, s.y, s.z + dz) - phi_at(L, s.x, s.y, s.z - dz)) / (2.0f * dz);
+        d0 = phi_at(L, s.x, s.y, s.z);
+    }
     float nrm = sqrtf(gx * gx + gy * gy + gz * gz);
     float n0 = gx / nrm, n1 = gy / nrm, n2 = gz / nrm;
-    float d0 = phi_at(L, s.x, s.y, s.z);
     float Pp[6], Pm[6];
     pinv_sym3(Ap, Pp);
     pinv_sym3(Am, Pm);
@@ -672,8 +691,10 @@ int nbm_ghost_layer_f32(const float* phi, const float* x, const float* y, const 
     return NBM_OK;
 }
 
-static int check_lvl(const nbm_lvl_t* lvl) {
-    NBM_REQUIRE(lvl && lvl->phi_g && lvl->xg && lvl->yg && lvl->zg, "null lvl grid");
+static int check_lvl(const nbm_lvl_t* lvl, bool sampled_ok = false) {
+    NBM_REQUIRE(lvl, "null lvl");
+    if (sampled_ok && !lvl->phi_g) return NBM_OK;   // sampled level set: the caller hands the values in
+    NBM_REQUIRE(lvl->phi_g && lvl->xg && lvl->yg && lvl->zg, "null lvl grid");
     NBM_REQUIRE(lvl->gx >= 5 && lvl->gy >= 5 && lvl->gz >= 5, "ghosted lvl grid too small");
     if (lvl->interp != NBM_INTERP_TRILINEAR && lvl->interp != NBM_INTERP_QUADRATIC) {
         set_error("unknown interpolation kind %d", lvl->interp);
@@ -747,7 +768,7 @@ int nbm_compact_crossed(const int8_t* flag, int64_t n, int64_t* idx_out, int64_t
 
 int nbm_cutcell_f32(const nbm_lvl_t* lvl, const nbm_lattice_t* lat, float dx, float dy, float dz, const int64_t* idx,
                     int64_t n_crossed, float* frac, float* tri, float* tri_area, nbm_stream_t stream) {
-    int rc = check_lvl(lvl);
+    int rc = check_lvl(lvl, lvl && lvl->corner_phi);
     if (rc) return rc;
     rc = check_lat(lat);
     if (rc) return rc;
@@ -763,7 +784,7 @@ int nbm_cutcell_f32(const nbm_lvl_t* lvl, const nbm_lattice_t* lat, float dx, fl
 int nbm_regression_f32(const nbm_lvl_t* lvl, const nbm_lattice_t* lat, float dx, float dy, float dz,
                        const int64_t* idx, int64_t n_crossed, float* pos, float* proj, float* delta, float* Cm,
                        float* Cp, uint32_t* cube_side, nbm_stream_t stream) {
-    int rc = check_lvl(lvl);
+    int rc = check_lvl(lvl, lvl && lvl->cube_phi);
     if (rc) return rc;
     rc = check_lat(lat);
     if (rc) return rc;

@@ -2105,7 +2105,8 @@ __global__ void evaluate_kernel(nbm_lvl_t L, const float* __restrict__ pts, int6
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     float x = pts[3 * e], y = pts[3 * e + 1], z = pts[3 * e + 2];
-    float ph = phi_at(L, x, y, z);
+    const float* ep = L.eval_phi ? L.eval_phi + 7 * e : nullptr;   // sampled level set (see nbm_lvl_t)
+    float ph = ep ? ep[0] : phi_at(L, x, y, z);
     float gx[3], val;
     if (ph >= 0.0f) {
         float a[LP][HP];
@@ -2119,9 +2120,16 @@ __global__ void evaluate_kernel(nbm_lvl_t L, const float* __restrict__ pts, int6
     u[e] = val;
     if (grad_u) { grad_u[3 * e] = gx[0]; grad_u[3 * e + 1] = gx[1]; grad_u[3 * e + 2] = gx[2]; }
     if (grad_n) {
-        float px = (phi_at(L, x + dx, y, z) - phi_at(L, x - dx, y, z)) / (2.0f * dx);
-        float py = (phi_at(L, x, y + dy, z) - phi_at(L, x, y - dy, z)) / (2.0f * dy);
-        float pz = (phi_at(L, x, y, z + dz) - phi_at(L, x, y, z - dz)) / (2.0f * dz);
+        float px, py, pz;
+        if (ep) {
+            px = (ep[2] - ep[1]) / (2.0f * dx);
+            py = (ep[4] - ep[3]) / (2.0f * dy);
+            pz = (ep[6] - ep[5]) / (2.0f * dz);
+        } else {
+            px = (phi_at(L, x + dx, y, z) - phi_at(L, x - dx, y, z)) / (2.0f * dx);
+            py = (phi_at(L, x, y + dy, z) - phi_at(L, x, y - dy, z)) / (2.0f * dy);
+            pz = (phi_at(L, x, y, z + dz) - phi_at(L, x, y, z - dz)) / (2.0f * dz);
+        }
         float nrm = sqrtf(px * px + py * py + pz * pz);
         grad_n[e] = (px / nrm) * gx[0] + (py / nrm) * gx[1] + (pz / nrm) * gx[2];
     }
@@ -2837,7 +2845,7 @@ int nbm_upload_staged_params(nbm_stream_t stream) {
 
 int nbm_evaluate_f32(const nbm_net_t* net, const nbm_lvl_t* lvl, const float* pts, int64_t n, float dx, float dy,
                      float dz, float* u, float* grad_u, float* grad_n, nbm_stream_t stream) {
-    NBM_REQUIRE(net && lvl && lvl->phi_g && lvl->xg && lvl->yg && lvl->zg, "null pointer");
+    NBM_REQUIRE(net && lvl && (lvl->eval_phi || (lvl->phi_g && lvl->xg && lvl->yg && lvl->zg)), "null pointer");
     NBM_REQUIRE(n >= 0, "negative n");
     if (n == 0) return NBM_OK;
     NBM_REQUIRE(pts && u, "null pointer");

@@ -123,6 +123,7 @@ class PrecondShape:
 class LevelSet:
     """phi on `lvl_gstate` + the reference's interpolant, evaluated inside the kernels
     (interpolate.py:906-1021 trilinear, :388-569 non-oscillatory quadratic; level_set.py:34-48)."""
+    analytic = False
 
     def __init__(self, lvl_gstate, phi_values: torch.Tensor, interp: str = "trilinear",
                  perturb_eps: float = 1e-10, device=None):
@@ -158,6 +159,71 @@ class LevelSet:
         return out
 
 
+class AnalyticLevelSet:
+    """The level set given by the user's own (batched) callable, called wherever phi is needed - what the reference does
+    with an analytic `lvl_set_fn` (discretization.py:90; tests/test_poisson.py drives it that way).  A callable cannot
+    run inside a kernel, but every phi evaluation of the path happens at positions that are known per level (cell
+    corners, the 27-cube of crossed sites, evaluation points +- d): they are formed here with the kernels' own fp32
+    arithmetic, the callable is evaluated with torch on the device, and the kernels take the samples (nbm_lvl_t).
+    The callable is used as given (wrap it in `perturb_level_set_fn` yourself, as the reference's configs do)."""
+    analytic = True
+
+    def __init__(self, lvl_gstate, phi_fn: Callable, device=None):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.phi_fn = phi_fn
+        self.struct = cabi.Lvl()          # no grid: the per-call sample pointers are filled in where they are used
+        self.bounds = [float(v) for v in (lvl_gstate.xmin(), lvl_gstate.xmax(), lvl_gstate.ymin(),
+                                          lvl_gstate.ymax(), lvl_gstate.zmin(), lvl_gstate.zmax())]
+
+    def __call__(self, pts: torch.Tensor) -> torch.Tensor:
+        return _sample(self.phi_fn, pts.to(self.device, torch.float32))
+
+    def with_samples(self, corner_phi=None, cube_phi=None, eval_phi=None) -> cabi.Lvl:
+        s = cabi.Lvl()
+        s.corner_phi, s.cube_phi, s.eval_phi = cabi.ptr(corner_phi), cabi.ptr(cube_phi), cabi.ptr(eval_phi)
+        return s
+
+
+_CORNER_SIGN = ((-1, -1, -1), (1, -1, -1), (1, -1, 1), (-1, -1, 1), (-1, 1, -1), (1, 1, -1), (-1, 1, 1), (1, 1, 1))
+
+
+def _classify_analytic(lvl: "AnalyticLevelSet", coords, lo, hi, d, dev):
+    """flag / side of every lattice site from the callable (geometric_integrations_per_point.py:203-263), plane by
+    plane; positions as in site_position() and corner_phis() of the kernels: x = xs[i] + shift, corner = (sign*d)*0.5 + x."""
+    xs, ys, zs, shifts = coords
+    nx, ny, nz = xs.numel(), ys.numel(), zs.numel()
+    n = nx * ny * nz
+    flag = torch.empty(len(shifts) * n, dtype=torch.int8, device=dev)
+    side = torch.zeros(len(shifts) * n + 32, dtype=torch.uint8, device=dev)[:len(shifts) * n]
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32, device=dev)
+    half = [[(f32(sg[a]) * f32(d[a])) * f32(0.5) for a in range(3)] for sg in _CORNER_SIGN]
+    chunk = max(1, (1 << 21) // (ny * nz))
+    for k, sh in enumerate(shifts):
+        X, Y, Z = xs + f32(sh[0]), ys + f32(sh[1]), zs + f32(sh[2])
+        for i0 in range(0, nx, chunk):
+            i1 = min(nx, i0 + chunk)
+            gx, gy, gz = torch.meshgrid(X[i0:i1], Y, Z, indexing="ij")
+            P = torch.stack((gx.reshape(-1), gy.reshape(-1), gz.reshape(-1)), dim=1)
+            ph0 = lvl(P)
+            neg = torch.zeros(P.shape[0], dtype=torch.int32, device=dev)
+            first = None
+            for c in range(8):
+                pc = lvl(torch.stack((half[c][0] + P[:, 0], half[c][1] + P[:, 1], half[c][2] + P[:, 2]), dim=1))
+                neg += (pc < 0).to(torch.int32)
+                if c == 0:
+                    first = pc
+            fl = torch.where((neg == 0) | (neg == 8), torch.sign(first).to(torch.int8), torch.zeros_like(neg, dtype=torch.int8))
+            ii = torch.arange(i0, i1, device=dev)
+            ok = ((ii >= lo[0]) & (ii < hi[0]))[:, None, None] & \
+                 ((torch.arange(ny, device=dev) >= lo[1]) & (torch.arange(ny, device=dev) < hi[1]))[None, :, None] & \
+                 ((torch.arange(nz, device=dev) >= lo[2]) & (torch.arange(nz, device=dev) < hi[2]))[None, None, :]
+            fl = torch.where(ok.reshape(-1), fl, torch.full_like(fl, 2))
+            a, b = k * n + i0 * ny * nz, k * n + i1 * ny * nz
+            flag[a:b] = fl
+            side[a:b] = ((ph0 >= 0).to(torch.uint8) | ((ph0 > 0).to(torch.uint8) << 1))
+    return flag, side
+
+
 def _lattice(xs, ys, zs, lo=None, hi=None, shifts=None) -> cabi.Lattice:
     lat = cabi.Lattice()
     lat.xs, lat.ys, lat.zs = cabi.ptr(xs), cabi.ptr(ys), cabi.ptr(zs)
@@ -187,17 +253,24 @@ def _sample(fn: Callable, pts: torch.Tensor) -> torch.Tensor:
 class CrossedSites:
     """Crossed sites of a lattice: compaction, K1 cut-cell, K2a regression, K2b jump weights."""
 
-    def __init__(self, lvl: LevelSet, lat: cabi.Lattice, n_sites: int, d, fns, dev, n_cut_sites: int = None):
+    def __init__(self, lvl: LevelSet, lat: cabi.Lattice, n_sites: int, d, fns, dev, n_cut_sites: int = None,
+                 coords=None):
         """`n_cut_sites`: cut-cell geometry is only needed for crossed sites with id < n_cut_sites (the
-        training points themselves); default all."""
+        training points themselves); default all.  `coords` = (xs, ys, zs, shifts) of the lattice as tensors: needed
+        with an analytic level set, whose samples are taken here."""
         L = cabi.lib()
         st = cabi.stream_ptr()
         dx, dy, dz = d
-        self.flag = torch.empty(n_sites, dtype=torch.int8, device=dev)
-        # (16 bytes of slack: the fused gradient kernel stages `side` with 16-byte bulk copies)
-        self.side = torch.zeros(n_sites + 32, dtype=torch.uint8, device=dev)[:n_sites]
-        cabi.check(L.nbm_classify_f32(C.byref(lvl.struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.flag),
-                                      cabi.ptr(self.side), st), "nbm_classify_f32")
+        if lvl.analytic:
+            lo = [lat.lo[a] for a in range(3)]
+            hi = [lat.hi[a] for a in range(3)]
+            self.flag, self.side = _classify_analytic(lvl, coords, lo, hi, d, dev)
+        else:
+            self.flag = torch.empty(n_sites, dtype=torch.int8, device=dev)
+            # (16 bytes of slack: the fused gradient kernel stages `side` with 16-byte bulk copies)
+            self.side = torch.zeros(n_sites + 32, dtype=torch.uint8, device=dev)[:n_sites]
+            cabi.check(L.nbm_classify_f32(C.byref(lvl.struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.flag),
+                                          cabi.ptr(self.side), st), "nbm_classify_f32")
         # compaction
         idx = torch.empty(n_sites, dtype=torch.int64, device=dev)
         self.cidx = torch.empty(n_sites, dtype=torch.int32, device=dev)
@@ -228,10 +301,32 @@ class CrossedSites:
             return
         n_cut = nc if n_cut_sites is None else int((self.idx < n_cut_sites).sum().item())
         self.n_cut = n_cut
-        cabi.check(L.nbm_cutcell_f32(C.byref(lvl.struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.idx), n_cut,
+        lvl_struct = lvl.struct
+        if lvl.analytic:
+            # positions of the crossed sites (as site_position()), their 8 corners and their 27-cube, sampled here
+            xs, ys, zs, shifts = coords
+            nx, ny, nz = xs.numel(), ys.numel(), zs.numel()
+            f32 = lambda v: torch.tensor(v, dtype=torch.float32, device=dev)
+            kk = self.idx // (nx * ny * nz)
+            e = self.idx - kk * (nx * ny * nz)
+            sh = torch.tensor(shifts, dtype=torch.float32, device=dev)[kk]
+            sx = xs[e // (ny * nz)] + sh[:, 0]
+            sy = ys[(e // nz) % ny] + sh[:, 1]
+            sz = zs[e % nz] + sh[:, 2]
+            corner = torch.empty((nc, 8), dtype=torch.float32, device=dev)
+            for c, sg in enumerate(_CORNER_SIGN):
+                hx, hy, hz = ((f32(sg[a]) * f32(d[a])) * f32(0.5) for a in range(3))
+                corner[:, c] = lvl(torch.stack((hx + sx, hy + sy, hz + sz), dim=1))
+            cube = torch.empty((nc, 27), dtype=torch.float32, device=dev)
+            for q in range(27):
+                X0, X1, X2 = f32(float(q % 3 - 1)) * f32(dx), f32(float((q // 3) % 3 - 1)) * f32(dy), f32(float(q // 9 - 1)) * f32(dz)
+                cube[:, q] = lvl(torch.stack((sx + X0, sy + X1, sz + X2), dim=1))
+            self._corner_phi, self._cube_phi = corner.contiguous(), cube.contiguous()
+            lvl_struct = lvl.with_samples(corner_phi=self._corner_phi, cube_phi=self._cube_phi)
+        cabi.check(L.nbm_cutcell_f32(C.byref(lvl_struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.idx), n_cut,
                                      cabi.ptr(self.frac), cabi.ptr(self.tri), cabi.ptr(self.tri_area), st),
                    "nbm_cutcell_f32")
-        cabi.check(L.nbm_regression_f32(C.byref(lvl.struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.idx), nc,
+        cabi.check(L.nbm_regression_f32(C.byref(lvl_struct), C.byref(lat), dx, dy, dz, cabi.ptr(self.idx), nc,
                                         cabi.ptr(self.pos), cabi.ptr(self.proj), cabi.ptr(self.delta),
                                         cabi.ptr(self.Cm), cabi.ptr(self.Cp), cabi.ptr(self.cube_side), st),
                    "nbm_regression_f32")
@@ -310,7 +405,7 @@ class SharedPlan:
             lo = (gx_lo - (xa - self.HX), self.HY, self.HZ)
             hi = (gx_hi - (xa - self.HX), self.HY + Ny, self.HZ + Nz)
             lat = _lattice(self.xe, self.ye, self.ze, lo, hi)
-            self.sites = CrossedSites(lvl, lat, ne, self.d, fns, dev)
+            self.sites = CrossedSites(lvl, lat, ne, self.d, fns, dev, coords=(self.xe, self.ye, self.ze, [(0.0, 0.0, 0.0)]))
             cs = self.sites
 
             # ---- per-point coefficient samples
@@ -614,7 +709,8 @@ class GeneralLevel:
             dx, dy, dz = self.d
             shifts = [(0, 0, 0), (-dx, 0, 0), (dx, 0, 0), (0, -dy, 0), (0, dy, 0), (0, 0, -dz), (0, 0, dz)]
             lat = _lattice(self.xs, self.ys, self.zs, shifts=shifts)
-            self.sites = CrossedSites(lvl, lat, 7 * N, self.d, fns, dev, n_cut_sites=N)
+            self.sites = CrossedSites(lvl, lat, 7 * N, self.d, fns, dev, n_cut_sites=N,
+                                      coords=(self.xs, self.ys, self.zs, shifts))
             cs = self.sites
             mu_m_faces, mu_p_faces, k_m, k_p, f_m, f_p, g_dir = _point_samples(fns, self.xs, self.ys, self.zs,
                                                                                self.d, dev)

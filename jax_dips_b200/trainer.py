@@ -9,7 +9,8 @@ Differences a user of the reference must know (all documented in DESIGN.md):
   the (3, n) view of the point list (the role `vmap` plays at trainer.py:995-1005);
 * the level set is sampled once on `lvl_gstate` and read by the kernels through the reference's
   own grid interpolant (`phi_interp="trilinear"`: interpolate.py:906, `"quadratic"`: :388) - the
-  configuration examples/dragon uses (solve_dragon.py:177);
+  configuration examples/dragon uses (solve_dragon.py:177) - or, with `phi_interp="analytic"`, the
+  callable itself is the level set everywhere (sampled on the host at the positions the kernels need);
 * `nonlinear_op_m/p` must be None / zero / `Nonlinear.sinh(coef)`;
 * the initial parameters follow haiku's initialisers (TruncatedNormal(0.1) hidden, 1/sqrt(fan_in)
   output, zero bias; MLP.py:65,70) but are drawn from a torch generator seeded with 42, because
@@ -37,8 +38,8 @@ from . import _cabi as cabi
 from . import data_management
 from . import numpy as jnp
 from .optimizers import OptimizerSpec, get_optimizer
-from .plan import (EmptyPlan, GeneralLevel, LevelSet, NetShape, Nonlinear, PointsPlan, PrecondShape, SharedPlan,
-                   upload_params)
+from .plan import (AnalyticLevelSet, EmptyPlan, GeneralLevel, LevelSet, NetShape, Nonlinear, PointsPlan, PrecondShape,
+                   SharedPlan, upload_params)
 from .simulation_states import PoissonSimState, PoissonSimStateFn, replace
 
 logger = logging.getLogger(__name__)
@@ -208,8 +209,12 @@ class Trainer:
 
         with torch.cuda.device(self.device):
             # level set on the lvl grid, read by the kernels through the reference's interpolant
-            phi_lvl = sim_state_fn.phi_fn(lvl_gstate.R.to(self.device))
-            self.lvl = LevelSet(lvl_gstate, phi_lvl, interp=phi_interp, perturb_eps=perturb_eps, device=self.device)
+            if phi_interp == "analytic":
+                # the user's callable is the level set everywhere, as in the reference (discretization.py:90)
+                self.lvl = AnalyticLevelSet(lvl_gstate, sim_state_fn.phi_fn, device=self.device)
+            else:
+                phi_lvl = sim_state_fn.phi_fn(lvl_gstate.R.to(self.device))
+                self.lvl = LevelSet(lvl_gstate, phi_lvl, interp=phi_interp, perturb_eps=perturb_eps, device=self.device)
             P = self.n_params = self.net.n_params + (self.precond.n_params if self.precond is not None else 0)
             self.opt_state = torch.zeros(2 * P, dtype=torch.float32, device=self.device)
             self.opt_count = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -543,11 +548,30 @@ class Trainer:
             for s in range(0, n, chunk):
                 e = min(n, s + chunk)
                 pts = R[s:e].to(self.device).contiguous()
-                cabi.check(L.nbm_evaluate_f32(C.byref(net), C.byref(self.lvl.struct), cabi.ptr(pts), e - s, dx, dy, dz,
+                lvl_struct = self._eval_lvl(pts, (dx, dy, dz), normals=True)
+                cabi.check(L.nbm_evaluate_f32(C.byref(net), C.byref(lvl_struct), cabi.ptr(pts), e - s, dx, dy, dz,
                                               u[s:].data_ptr(), gu[3 * s:].data_ptr(), gn[s:].data_ptr(),
                                               cabi.stream_ptr()), "nbm_evaluate_f32")
                 torch.cuda.current_stream().synchronize()
         return u, gu.view(n, 3), gn
+
+    def _eval_lvl(self, pts: torch.Tensor, d, normals: bool):
+        """the level-set descriptor for nbm_evaluate_f32: the grid form, or - analytic level set - its samples at the
+        points and at +- d along the axes (discretization.py:199-218), positions formed in fp32 like the kernel's"""
+        if not self.lvl.analytic:
+            return self.lvl.struct
+        n = pts.shape[0]
+        ep = torch.zeros((n, 7), dtype=torch.float32, device=self.device)
+        ep[:, 0] = self.lvl(pts)
+        if normals:
+            for a in range(3):
+                h = torch.tensor(d[a], dtype=torch.float32, device=self.device)
+                for k, sg in ((1 + 2 * a, -1.0), (2 + 2 * a, 1.0)):
+                    q = pts.clone()
+                    q[:, a] = pts[:, a] + sg * h
+                    ep[:, k] = self.lvl(q)
+        self._eval_phi = ep.contiguous()
+        return self.lvl.with_samples(eval_phi=self._eval_phi)
 
     def evaluate_solution_fn(self, params: torch.Tensor, R_flat: torch.Tensor) -> torch.Tensor:
         """trainer.py:836-844"""
@@ -557,7 +581,8 @@ class Trainer:
             upload_params(self.net, params.to(self.device))
             pts = R_flat.to(self.device, torch.float32).contiguous()
             u = torch.empty(pts.shape[0], dtype=torch.float32, device=self.device)
-            cabi.check(L.nbm_evaluate_f32(C.byref(net), C.byref(self.lvl.struct), cabi.ptr(pts), pts.shape[0], 1.0, 1.0,
+            lvl_struct = self._eval_lvl(pts, (1.0, 1.0, 1.0), normals=False)
+            cabi.check(L.nbm_evaluate_f32(C.byref(net), C.byref(lvl_struct), cabi.ptr(pts), pts.shape[0], 1.0, 1.0,
                                           1.0, cabi.ptr(u), None, None, cabi.stream_ptr()), "nbm_evaluate_f32")
         return u
 

@@ -205,6 +205,86 @@ def test_config0_sphere_32_error_metrics_track_the_oracle(tmp_path):
     assert set(fields) == {"phi", "U", "U_exact", "U-U_exact"} and pts.shape[0] == n_ev ** 3
 
 
+def _analytic_case(P, n_tr, n_lvl):
+    """oracle problem whose level set is the analytic callable itself (evaluated in float32 like everywhere else)"""
+    tr, lv, phi_grid, oprob = util.make_case(P, n_tr, n_lvl, "trilinear", torch.float64)
+    v = jnp.vmap(P.phi_fn)
+    oprob.phi_fn = lambda R: v(R.to(torch.float32)).to(R.dtype)
+    return tr, lv, oprob
+
+
+@pytest.mark.parametrize("name", ["sphere", "star"])
+def test_analytic_level_set_rows_loss_and_gradient(name):
+    """the level set as the user's own callable (what tests/test_poisson.py hands to the reference,
+    discretization.py:90) instead of its interpolant on lvl_gstate: shared path and per-point path (zoom 1)"""
+    P = problems.PROBLEMS[name]()
+    dt = torch.float64
+    tr, lv, oprob = _analytic_case(P, 16, 32)
+    lvl = nplan.AnalyticLevelSet(lv, jnp.vmap(P.phi_fn), device=DEV)
+    shape = nplan.NetShape()
+    params = O.init_params(oprob.shape, seed=7, dtype=dt)
+    with torch.cuda.device(DEV):
+        pl = nplan.SharedPlan(lvl, tr, 0, 16, fns_of(P), shape, nplan.Nonlinear(), nplan.Nonlinear(), device=DEV)
+        nplan.upload_params(shape, params.float().to(DEV))
+        lg = pl.loss_grad_launch().cpu()
+    d = [tr.dx.to(dt), tr.dy.to(dt), tr.dz.to(dt)]
+    flag_o = O.is_cell_crossed(tr.R.to(dt), *d, oprob.phi_fn)
+    assert torch.equal(pl.point_view(pl.sites.flag).cpu().to(dt), flag_o)
+    # the interpolated level set is a different problem: the analytic one must not silently fall back to it
+    trg, lvg, phi_grid, og = util.make_case(P, 16, 32, "trilinear", dt)
+    lhs_o, rhs_o = O.compute_Ax_and_b(params, tr.R.to(dt), *d, oprob)
+    lhs_g, rhs_g = O.compute_Ax_and_b(params, tr.R.to(dt), *d, og)
+    assert util.rel_inf(lhs_g, lhs_o) > 1e-4
+    rhs_k = pl.point_view(pl.rhs_rows()).cpu()
+    lhs_k = pl.point_view(pl.R).cpu() + rhs_k
+    assert util.rel_inf(lhs_k, lhs_o) < TOL_ROW and util.rel_inf(rhs_k, rhs_o) < TOL_ROW
+    loss_o, grad_o = O.loss_and_grad(params, tr.R.to(dt), *d, oprob)
+    assert abs(float(lg[-1]) - float(loss_o)) / float(loss_o) < TOL_LOSS
+    assert util.rel_inf(lg[:-1], grad_o) < TOL_LOSS
+    # per-point path, zoom level 1
+    d32 = [float(torch.tensor(float(v), dtype=torch.float32) * torch.tensor(0.5, dtype=torch.float32))
+           for v in (tr.dx, tr.dy, tr.dz)]
+    with torch.cuda.device(DEV):
+        level = nplan.GeneralLevel(lvl, tr, d32, fns_of(P), shape, nplan.Nonlinear(), nplan.Nonlinear(), device=DEV)
+        lg1 = nplan.PointsPlan(level, 0, tr.num_points()).loss_grad_launch().cpu()
+    dd = [torch.tensor(v, dtype=dt) for v in d32]
+    loss_1, grad_1 = O.loss_and_grad(params, tr.R.to(dt), *dd, oprob)
+    assert abs(float(lg1[-1]) - float(loss_1)) / float(loss_1) < TOL_LOSS
+    assert util.rel_inf(lg1[:-1], grad_1) < TOL_LOSS
+
+
+def test_analytic_level_set_through_the_trainer():
+    """init_fn(..., phi_interp="analytic"): training loop and post-training evaluation (u, grad u, d u/d n) with the
+    callable as the level set, against the oracle driven the same way"""
+    P = problems.sphere()
+    n_tr, n_lvl = 8, 24
+    tr, lv, oprob = _analytic_case(P, n_tr, n_lvl)
+    p0 = O.init_params(oprob.shape, seed=42, dtype=torch.float64)
+    od = {"optimizer_name": "custom", "learning_rate": 1e-2, "sched": {"scheduler_name": "exponential", "decay_rate": 0.975}}
+    grid_d = [tr.dx.double(), tr.dy.double(), tr.dz.double()]
+    p_o, losses_o = O.single_gpu_train(p0.clone(), tr.R.double(), grid_d, oprob, num_epochs=8, batch_size=256,
+                                       optimizer_dict=od)
+    lo, hi = P.box
+    trk = mesh.linspace_grid(lo, hi, [n_tr] * 3); lvk = mesh.linspace_grid(lo, hi, [n_lvl] * 3)
+    ev = mesh.linspace_grid(lo, hi, [12] * 3)
+    init_fn = ntrainer.setup(*P.setup_args())
+    sim_state, solve_fn = init_fn(lvl_gstate=lvk, tr_gstate=trk, eval_gstate=ev, num_epochs=8, batch_size=256,
+                                  checkpoint_dir=None, optimizer_dict=od, init_params=p0.float(), device=DEV,
+                                  print_rate=0, phi_interp="analytic")
+    state, _, loss_epochs = solve_fn(sim_state)
+    T = solve_fn.trainer
+    lk = torch.as_tensor(loss_epochs).double()
+    lo_ = torch.tensor(losses_o, dtype=torch.float64)
+    assert ((lk - lo_).abs() / lo_).max() < 1e-3, (lk, lo_)
+    assert util.rel_inf(T.params.cpu(), p_o) < 1e-3
+    u_o, gu_o, gn_o = O.evaluate_solution_and_gradients(T.params.cpu().double(), ev.R.double(), ev.dx.double(),
+                                                        ev.dy.double(), ev.dz.double(), oprob)
+    assert util.rel_inf(state.solution.cpu(), u_o) < 1e-5
+    assert util.rel_inf(state.grad_solution.cpu(), gu_o) < 1e-5
+    fin = torch.isfinite(gn_o)
+    assert util.rel_inf(state.grad_normal_solution.cpu()[fin], gn_o[fin]) < 1e-4
+
+
 def test_ragged_batches_keep_their_real_points():
     """512 points in batches of 200 (200 + 200 + 112; the reference would pad the last one with 88 random points from
     jax PRNGKey(0), data_management.py:70-76): unaligned batches run on the per-point path at every zoom level."""
