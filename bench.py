@@ -48,7 +48,8 @@ def parse():
     ap.add_argument("--workload", default="sphere", choices=["sphere", "star", "stars", "dragon_like", "poisson_boltzmann"])
     ap.add_argument("--grid", type=int, default=256, help="training points per axis per GPU-slab (x grows with N: weak scaling)")
     ap.add_argument("--lvl", type=int, default=128)
-    ap.add_argument("--interp", default="trilinear", choices=["trilinear", "quadratic"])
+    ap.add_argument("--interp", default="trilinear", choices=["trilinear", "quadratic", "analytic"],
+                    help="level set: interpolant of the samples on the lvl grid, or (analytic) the callable itself")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--zoom", type=int, default=0, help=">0: time the general per-point path at cell size = spacing/2^zoom")
     ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
@@ -141,7 +142,12 @@ def cpu_baseline(problem, args, n_sample, steps=1, warmup=0):
     import util
     from oracle import nbm_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    tr, lv, phi_grid, oprob = util.make_case(problem, [args.grid] * 3, args.lvl, args.interp, torch.float32)
+    tr, lv, phi_grid, oprob = util.make_case(problem, [args.grid] * 3, args.lvl,
+                                             "trilinear" if args.interp == "analytic" else args.interp, torch.float32)
+    if args.interp == "analytic":
+        from jax_dips_b200 import numpy as jnp
+        v = jnp.vmap(problem.phi_fn)
+        oprob.phi_fn = lambda R: v(R.to(torch.float32)).to(R.dtype)
     n = tr.num_points()
     stride = max(1, n // n_sample)
     # build the sample without materialising the whole (n,3) point list
@@ -215,8 +221,11 @@ def main():
     net = nplan.NetShape()
     precond = nplan.PrecondShape((8, 4), 1.0) if args.precond else None
     P = net.n_params + (precond.n_params if precond is not None else 0)
-    phi_lvl = fns.phi_fn(lv.R.to(dev))
-    lvl = nplan.LevelSet(lv, phi_lvl, interp=args.interp, perturb_eps=1e-10, device=dev)
+    if args.interp == "analytic":
+        lvl = nplan.AnalyticLevelSet(lv, fns.phi_fn, device=dev)
+    else:
+        phi_lvl = fns.phi_fn(lv.R.to(dev))
+        lvl = nplan.LevelSet(lv, phi_lvl, interp=args.interp, perturb_eps=1e-10, device=dev)
     t_setup = time.time()
     if args.zoom > 0:
         if world != 1:
