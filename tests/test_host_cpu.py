@@ -254,3 +254,28 @@ def test_parameter_tree_roundtrip_with_the_preconditioner():
     assert float(np.abs(dense["Dense_0"]["kernel"]).max()) <= lim and float(np.abs(dense["Dense_0"]["bias"]).max()) == 0.0
     assert torch.equal(ntrainer.tree_to_params(net, tree, pc), flat)
     assert ntrainer.params_to_tree(net, flat[:net.n_params])["preconditioner"] == {}
+
+
+def test_cabi_argument_validation_without_a_gpu():
+    """error convention of the C ABI (include/nbm_b200.h): int status, nbm_last_error(); argument checks come before
+    any CUDA call, so they can be exercised on a host without a GPU"""
+    import ctypes as C
+    from jax_dips_b200 import _cabi as cabi
+    L = cabi.lib()
+    assert L.nbm_version() >= 100
+    net = cabi.Net(2, 10, 1, 1)
+    assert L.nbm_net_num_params(C.byref(net)) == 167                   # p 3-10-10-1: 161, m 3-1-1: 6 (SURVEY 8)
+    assert L.nbm_net_num_params(C.byref(cabi.Net(2, 10, 1, 3))) == 177  # README.md:137-142 of the reference
+    assert L.nbm_precond_num_params(8, 4) == 257
+    assert L.nbm_step_partial_rows() >= 148
+    assert L.nbm_loss_grad_shared_f32(None, None) == 1                  # NBM_ERR_BAD_ARG
+    assert b"null" in L.nbm_last_error()
+    step = cabi.SharedStep()
+    assert L.nbm_loss_grad_shared_f32(C.byref(step), None) == 1
+    assert L.nbm_loss_grad_points_f32(None, None) == 1
+    opt = cabi.Optimizer(167, 1e-3, 0.9, 1000.0, 1.0, 0.9, 0.999, 1e-8, 0, 0)
+    assert L.nbm_apply_update_f32(C.byref(opt), None, None, None, None, None, None) == 1
+    assert L.nbm_finalize_step_f32(C.byref(opt), C.byref(net), None, 0, 0, None, None, None, None, None, None) == 1
+    assert L.nbm_upload_params(C.byref(net), None, None) == 1
+    with pytest.raises(cabi.NbmError):
+        cabi.check(L.nbm_assemble_f32(None, None), "nbm_assemble_f32")
