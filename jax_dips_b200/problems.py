@@ -300,6 +300,19 @@ def poisson_boltzmann(n_atoms: int = 200, seed: int = 2, half_width: float = 2.5
                    box=((-hw, -hw, -hw), (hw, hw, hw)), name="poisson_boltzmann")
 
 
+def sphere_reaction() -> Problem:
+    """the sphere problem with variable reaction coefficients k^-, k^+ != 0 and a nonlinear operator on both sides
+    (N = c sinh u): every term of the row (discretization.py:366-386) is present.  No analytic solution is attached."""
+    P = sphere()
+    P.k_m_fn = lambda r: 0.7 + 0.2 * r[0]
+    P.k_p_fn = lambda r: 1.3 + 0.1 * r[1]
+    P.nonlinear_op_m = Nonlinear.sinh(40.0)
+    P.nonlinear_op_p = Nonlinear.sinh(150.0)
+    P.exact_sol_m_fn = P.exact_sol_p_fn = None
+    P.name = "sphere_reaction"
+    return P
+
+
 def sphere_at_boundary() -> Problem:
     """the sphere problem with the interface pushed against the x+ face of the box: crossed cells whose
     27-point regression cube leaves the box (the halo layer of the lattice)"""
@@ -308,5 +321,5 @@ def sphere_at_boundary() -> Problem:
     return P
 
 
-PROBLEMS = {"sphere": sphere, "sphere_at_boundary": sphere_at_boundary, "star": star, "no_jump": no_jump, "stars": stars, "dragon_like": dragon_like,
+PROBLEMS = {"sphere": sphere, "sphere_reaction": sphere_reaction, "sphere_at_boundary": sphere_at_boundary, "star": star, "no_jump": no_jump, "stars": stars, "dragon_like": dragon_like,
             "poisson_boltzmann": poisson_boltzmann}

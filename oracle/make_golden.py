@@ -68,6 +68,15 @@ def unpack(flat, L, H, off):
     return layers
 
 
+def nonlinear_callable(op):
+    """the reference takes the nonlinear operator as a callable on u (discretization.py:369;
+    examples/biomolecules/coefficients.py:126-131): build it from the product's named operator"""
+    if op is None or getattr(op, "kind", 0) == 0:
+        return lambda u: 0.0
+    coef = float(op.coef)
+    return lambda u: coef * jnp.sinh(u)
+
+
 class Hooked(Discretization):
     """Discretization + the three Trainer hooks (trainer.py:836-854), network = MLP.py:93-139"""
 
@@ -123,7 +132,7 @@ def run_case(name, problem, n_tr, n_lvl, interp, point_idx, zoom, dtype):
     fns = PoissonSimStateFn(b(problem.initial_value_fn), b(problem.dirichlet_bc_fn), phi_fn, b(problem.mu_m_fn),
                             b(problem.mu_p_fn), b(problem.k_m_fn), b(problem.k_p_fn), b(problem.f_m_fn),
                             b(problem.f_p_fn), b(problem.alpha_fn), b(problem.beta_fn),
-                            lambda u: 0.0, lambda u: 0.0)
+                            nonlinear_callable(problem.nonlinear_op_m), nonlinear_callable(problem.nonlinear_op_p))
     D = Hooked(lv, None, fns, precondition=1, algorithm=0)
     shape = O.NetShape()
     flat = O.init_params(shape, seed=7, dtype=torch.float64).numpy().astype(dtype)
@@ -168,13 +177,17 @@ CASES = [
     ("sphere_tri_z1", "sphere", 16, 32, "trilinear", 1),
     ("star_tri_z0", "star", 16, 32, "trilinear", 0),
     ("sphere_quad_z0", "sphere", 12, 24, "quadratic", 0),
+    ("sphere_reaction_tri_z0", "sphere_reaction", 16, 32, "trilinear", 0),   # k != 0 and N(u) = c sinh(u) on both sides
 ]
 
 
 def main():
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, pname, n_tr, n_lvl, interp, zoom in CASES:
+        if only and name not in only:
+            continue
         P = problems.PROBLEMS[pname]()
         n_near = 60 if interp == "trilinear" else 30
         idx = choose_points(P, n_tr, n_lvl, n_near=n_near)

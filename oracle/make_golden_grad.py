@@ -48,7 +48,7 @@ def reference_loss_fn(problem, n_tr, n_lvl, interp, point_idx, zoom):
     fns = mg.PoissonSimStateFn(b(problem.initial_value_fn), b(problem.dirichlet_bc_fn), phi_fn, b(problem.mu_m_fn),
                                b(problem.mu_p_fn), b(problem.k_m_fn), b(problem.k_p_fn), b(problem.f_m_fn),
                                b(problem.f_p_fn), b(problem.alpha_fn), b(problem.beta_fn),
-                               lambda u: 0.0, lambda u: 0.0)
+                               mg.nonlinear_callable(problem.nonlinear_op_m), mg.nonlinear_callable(problem.nonlinear_op_p))
     D = mg.Hooked(lv, None, fns, precondition=1, algorithm=0)
     shape = mg.O.NetShape()
     d = [dtype(np.float32(v) * np.float32(0.5 ** zoom)) for v in (tr.dx, tr.dy, tr.dz)]
@@ -67,7 +67,8 @@ def reference_loss_fn(problem, n_tr, n_lvl, interp, point_idx, zoom):
 
 CASES = [("sphere_tri_z0", "sphere", "trilinear"), ("star_tri_z0", "star", "trilinear"),
          ("sphere_tri_z1", "sphere", "trilinear"),      # zoom level 1: cell size = spacing / 2
-         ("sphere_quad_z0", "sphere", "quadratic")]     # non-oscillatory quadratic level-set interpolant
+         ("sphere_quad_z0", "sphere", "quadratic"),     # non-oscillatory quadratic level-set interpolant
+         ("sphere_reaction_tri_z0", "sphere_reaction", "trilinear")]   # k != 0, N(u) = c sinh(u)
 
 
 def main():

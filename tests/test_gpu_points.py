@@ -24,7 +24,7 @@ def general(problem, n_train, n_lvl, zoom, interp="trilinear", precond=None):
     return tr, oprob, level, shape, d32
 
 
-@pytest.mark.parametrize("name,zoom", [("sphere", 0), ("sphere", 1), ("star", 2), ("sphere", 3)])
+@pytest.mark.parametrize("name,zoom", [("sphere", 0), ("sphere", 1), ("star", 2), ("sphere", 3), ("sphere_reaction", 1)])
 def test_general_path_loss_and_gradient(name, zoom):
     P = problems.PROBLEMS[name]()
     tr, oprob, level, shape, d = general(P, 12, 32, zoom)
@@ -354,7 +354,8 @@ import numpy as np
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
                 if not os.path.basename(p).startswith("grad_"))
 CASE_PROBLEM = {"sphere_tri_z0": ("sphere", "trilinear"), "sphere_tri_z1": ("sphere", "trilinear"),
-                "star_tri_z0": ("star", "trilinear"), "sphere_quad_z0": ("sphere", "quadratic")}
+                "star_tri_z0": ("star", "trilinear"), "sphere_quad_z0": ("sphere", "quadratic"),
+                "sphere_reaction_tri_z0": ("sphere_reaction", "trilinear")}
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])

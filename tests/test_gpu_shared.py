@@ -102,7 +102,9 @@ def test_classification_and_cut_cells(name):
     ("sphere", 16, 32, True, True), ("star", 16, 32, True, True), ("no_jump", 12, 16, True, False),
     ("sphere", 24, 24, True, False), ("star", 32, 32, True, True), ("star", 15, 32, False, False),
     ("sphere", 16, 32, True, False), ("star", 16, 32, True, False),
-    ("sphere", 16, 32, False, False), ("star", 16, 32, False, False)])
+    ("sphere", 16, 32, False, False), ("star", 16, 32, False, False),
+    # variable reaction coefficients k^-, k^+ (the kv table of the faces layout) + sinh on both sides
+    ("sphere_reaction", 16, 32, True, False), ("sphere_reaction", 16, 32, False, False)])
 def test_rows_loss_and_gradient(name, n, nl, faces, fused):
     P = problems.PROBLEMS[name]()
     tr, lv, lvl, oprob, pl, shape = build(P, n, nl, faces=faces, fused=fused)

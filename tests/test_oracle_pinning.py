@@ -19,7 +19,8 @@ from oracle import nbm_oracle as O
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
                 if not os.path.basename(p).startswith("grad_"))
 CASE_PROBLEM = {"sphere_tri_z0": ("sphere", "trilinear"), "sphere_tri_z1": ("sphere", "trilinear"),
-                "star_tri_z0": ("star", "trilinear"), "sphere_quad_z0": ("sphere", "quadratic")}
+                "star_tri_z0": ("star", "trilinear"), "sphere_quad_z0": ("sphere", "quadratic"),
+                "sphere_reaction_tri_z0": ("sphere_reaction", "trilinear")}
 
 
 def test_reference_kat_sphere_area_and_volume():
@@ -76,7 +77,10 @@ def test_reference_noise_floor():
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
-@pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-5), ("f32", torch.float32, 1e-5)])
+# f64: the oracle in float64 against the reference in x64 mode, 1e-5.  f32: two float32 evaluations of the same formulas in
+# different operation orders; their spread is the reference's own float32 noise floor (3e-5, test_reference_noise_floor;
+# 1.2e-5 measured on the reaction + sinh problem, <= 1e-5 on the others)
+@pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-5), ("f32", torch.float32, 3e-5)])
 def test_oracle_matches_reference_sources(path, tag, dtype, tol):
     """rows, 26-vector of face coefficients, crossing flags, Gamma integral, u^-/u^+ and the
     regression weights (zeta, gamma) against the reference's own code on the same inputs."""
