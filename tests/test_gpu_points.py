@@ -471,6 +471,54 @@ def test_unsupported_network_shape_fails_loudly():
             pl.loss_grad_launch()
 
 
+def test_finalize_kernel_with_the_polynomial_schedule():
+    """nbm_finalize_step_f32 (row reduction + optax chain + staging) with optimizer "custom" and the "polynomial"
+    scheduler (optimizers.py:25-29: optax.polynomial_schedule(lr, 0, power 1, transition_steps)) against a float64
+    restatement; the staged copies are what nbm_upload_staged_params hands to the next step."""
+    import ctypes as C
+    from jax_dips_b200 import _cabi as cabi
+    net = nplan.NetShape()
+    n, rows, T = net.n_params, 5, 4.0
+    g = torch.Generator().manual_seed(1)
+    p0 = torch.randn(n, generator=g, dtype=torch.float64) * 0.1
+    lr = 1e-2
+    p = p0.clone(); m = torch.zeros(n, dtype=torch.float64); v = torch.zeros(n, dtype=torch.float64)
+    o = cabi.Optimizer(n, lr, 0.9, T, 1.0, 0.9, 0.999, 1e-8, 0, 1)
+    s = net.struct()
+    with torch.cuda.device(DEV):
+        pk = p0.float().to(DEV); st = torch.zeros(2 * n, device=DEV); cnt = torch.zeros(1, dtype=torch.int32, device=DEV)
+        lg = torch.zeros(n + 1, device=DEV)
+        for t in range(6):                     # the schedule reaches 0 after transition_steps = 4
+            part = torch.randn(rows, n + 1, generator=g, dtype=torch.float64) * (3.0 if t == 0 else 0.05)
+            gr = part[:, :n].sum(0)
+            gn = gr.norm()
+            gr = gr if gn < 1.0 else gr / gn
+            m = 0.9 * m + 0.1 * gr; v = 0.999 * v + 0.001 * gr * gr
+            upd = (m / (1 - 0.9 ** (t + 1))) / (torch.sqrt(v / (1 - 0.999 ** (t + 1))) + 1e-8)
+            p = p - lr * (1.0 - min(t, T) / T) * upd
+            pd = part.float().to(DEV).contiguous()
+            cabi.check(cabi.lib().nbm_finalize_step_f32(C.byref(o), C.byref(s), cabi.ptr(pd), rows, n + 1, cabi.ptr(lg),
+                                                        cabi.ptr(pk), cabi.ptr(st), cabi.ptr(cnt), None, cabi.stream_ptr()))
+            torch.cuda.synchronize()
+            assert util.rel_inf(lg.cpu(), part.sum(0)) < 1e-6
+        assert int(cnt.item()) == 6
+        assert util.rel_inf(pk.cpu(), p) < 1e-5
+        # the staged parameters are the updated ones: same network values as after a full upload
+        cabi.check(cabi.lib().nbm_upload_staged_params(cabi.stream_ptr()))
+        P = problems.sphere()
+        tr, lv, phi_grid, oprob = util.make_case(P, 8, 16, "trilinear", torch.float64)
+        lvl = nplan.LevelSet(lv, phi_grid, device=DEV)
+        pts = tr.R[:64].to(DEV).contiguous()
+        u1 = torch.empty(64, device=DEV); u2 = torch.empty(64, device=DEV)
+        ev = lambda out: cabi.check(cabi.lib().nbm_evaluate_f32(C.byref(s), C.byref(lvl.struct), cabi.ptr(pts), 64, 1.0, 1.0,
+                                                                1.0, cabi.ptr(out), None, None, cabi.stream_ptr()))
+        ev(u1)
+        nplan.upload_params(net, pk)
+        ev(u2)
+        torch.cuda.synchronize()
+    assert torch.equal(u1, u2)
+
+
 @pytest.mark.parametrize("name", ["custom", "adam", "rmsprop"])
 def test_update_kernel_matches_optax_semantics(name):
     """nbm_apply_update_f32 against a float64 restatement of the optax chains (optimizers.py:33-54, 76-88)."""
