@@ -14,7 +14,7 @@ Pinning status
 --------------
 * geometry: pinned by the reference's own known-answer test (sphere r=0.5 in [-2,2]^3 at
   128^3: area = pi +- 0.02, volume = pi/6 +- 0.02; tests/test_geometric_integrations.py:181-182)
-  -> tests/test_oracle_kat.py
+  -> tests/test_oracle_pinning.py::test_reference_kat_sphere_area_and_volume
 * geometry / regression / residual rows: pinned against the reference's OWN source files
   executed in the build container through a minimal numpy stand-in for the jax API
   (oracle/jax_shim + oracle/make_golden.py -> tests/golden/*.npz).
