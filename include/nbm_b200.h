@@ -389,10 +389,18 @@ int nbm_upload_staged_params(nbm_stream_t stream);
  * slot of EVERY rank's block over NVLink (slot = step parity; remote stores do not wait) -> fence -> raise this
  * rank's step flag in every block -> poll the LOCAL flags of all peers -> add the local slots in rank order
  * (bitwise identical result on every rank) -> out.
- * A spin that lasts longer than ~2 s sets comm error state instead of hanging (nbm_comm_error()).
+ * A wait longer than the timeout (nbm_comm_set_timeout, default 30 s, 0 = unbounded like NCCL) sets the block's error
+ * word and fills THAT rank's output with NaN; the host must poll nbm_comm_error() (per checkpoint / at the end of
+ * training) and raise: a timed-out rank never continues with a plausible-looking partial sum.
  * ---------------------------------------------------------------------------------------- */
 #define NBM_IPC_HANDLE_BYTES 64
 #define NBM_COMM_MAX_RANKS 8
+/* process-wide wait bound of the exchange kernel in seconds (0 = wait for ever) */
+int nbm_comm_set_timeout(double seconds);
+/* single-process multi-device (the reference's pmap model, trainer.py:727-743): a block on the current device without
+ * an IPC handle, and peer access `device` -> `peer` so that kernels on `device` can store into `peer`'s block */
+int nbm_comm_alloc_local(void** local_block);
+int nbm_enable_peer_access(int device, int peer);
 /* allocate + zero the local block on the current device, export its IPC handle */
 int nbm_comm_alloc(void** local_block, unsigned char handle[NBM_IPC_HANDLE_BYTES]);
 /* map a peer's block (handle obtained from that peer's nbm_comm_alloc) */

@@ -120,6 +120,9 @@ SYMBOLS = {
     "nbm_ffma_probe_f32": (C.c_int, [C.c_int, c_fp, _P(C.c_double), c_fp]),
     "nbm_loss_grad_shared_f32": (C.c_int, [_P(SharedStep), c_fp]),
     "nbm_loss_grad_points_f32": (C.c_int, [_P(PointsStep), c_fp]),
+    "nbm_comm_set_timeout": (C.c_int, [C.c_double]),
+    "nbm_comm_alloc_local": (C.c_int, [_P(C.c_void_p)]),
+    "nbm_enable_peer_access": (C.c_int, [C.c_int, C.c_int]),
     "nbm_comm_alloc": (C.c_int, [_P(C.c_void_p), C.c_char_p]),
     "nbm_comm_open_peer": (C.c_int, [C.c_char_p, _P(C.c_void_p)]),
     "nbm_comm_close_peer": (C.c_int, [C.c_void_p]),

@@ -30,7 +30,11 @@ def _newer(src: str, dst: str) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "nbm_b200.h")]
+    # sources only: the generated objects (and their ptxas logs) must not make every unit look stale
+    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    deps.append(os.path.join(HERE, "..", "include", "nbm_b200.h"))
+    logdir = os.path.join(HERE, "..", "build", "ptxas")
+    os.makedirs(logdir, exist_ok=True)
     objs = []
     for src, extra in UNITS:
         s = os.path.join(CSRC, src)
@@ -42,7 +46,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
             if r.returncode:
                 raise RuntimeError(f"nvcc failed on {src}")
-            with open(o + ".log", "w") as f:
+            # ptxas -v output (registers / spills per kernel): kept outside the tracked tree; copies that are
+            # evidence live under profiles/
+            with open(os.path.join(logdir, src.replace(".cu", ".ptxas.log")), "w") as f:
                 f.write(r.stdout + r.stderr)
         objs.append(o)
     if force or any(_newer(o, LIB) for o in objs):

@@ -9,10 +9,19 @@ only used to exchange the 64-byte IPC handles at construction time.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
 from . import _cabi as cabi
+
+
+def _apply_timeout() -> float:
+    """NBM_PEER_TIMEOUT_S: how long the exchange kernel waits for a peer before it reports an error (default 30 s;
+    0 = wait without a bound, as NCCL does).  Returns the value in force."""
+    t = float(os.environ.get("NBM_PEER_TIMEOUT_S", "30"))
+    cabi.check(cabi.lib().nbm_comm_set_timeout(t), "nbm_comm_set_timeout")
+    return t
 
 
 class PeerComm:
@@ -25,6 +34,7 @@ class PeerComm:
             raise cabi.NbmError("peer all-reduce supports up to 8 ranks on one node")
         self.device = torch.device(device)
         L = cabi.lib()
+        self.timeout_s = _apply_timeout()
         with torch.cuda.device(self.device):
             local = C.c_void_p()
             handle = C.create_string_buffer(64)
@@ -65,3 +75,66 @@ class PeerComm:
             if self.local is not None:
                 L.nbm_comm_free(self.local)
                 self.local = None
+
+
+class LocalPeerComm:
+    """The same exchange inside ONE process that drives several devices (the reference's `pmap` model,
+    trainer.py:727-743): one block per device, peer access enabled pairwise, no IPC.  `handle(r)` is device r's view
+    (what `SharedPlan.loss_grad_launch(comm=...)` takes)."""
+
+    class _Handle:
+        def __init__(self, parent, rank):
+            self.parent, self.rank = parent, rank
+
+        def reduce_allreduce(self, partials, rows, np1, out):
+            p = self.parent
+            cabi.check(cabi.lib().nbm_reduce_allreduce_f32(cabi.ptr(partials), rows, np1, self.rank, p.world, p.blocks,
+                                                           cabi.ptr(p.steps[self.rank]), cabi.ptr(out),
+                                                           cabi.stream_ptr()), "nbm_reduce_allreduce_f32")
+            return out
+
+    def __init__(self, devices):
+        self.devices = [torch.device(d) for d in devices]
+        self.world = len(self.devices)
+        if not 1 <= self.world <= 8:
+            raise cabi.NbmError("peer all-reduce supports up to 8 devices")
+        L = cabi.lib()
+        self.timeout_s = _apply_timeout()
+        for a in self.devices:
+            for b in self.devices:
+                if a != b:
+                    cabi.check(L.nbm_enable_peer_access(a.index, b.index), "nbm_enable_peer_access")
+        self.blocks = (C.c_void_p * self.world)()
+        self.steps = []
+        for r, dev in enumerate(self.devices):
+            with torch.cuda.device(dev):
+                p = C.c_void_p()
+                cabi.check(L.nbm_comm_alloc_local(C.byref(p)), "nbm_comm_alloc_local")
+                self.blocks[r] = p.value
+                self.steps.append(torch.zeros(1, dtype=torch.int32, device=dev))
+                torch.cuda.synchronize(dev)
+        self._handles = [self._Handle(self, r) for r in range(self.world)]
+
+    def handle(self, r: int):
+        return self._handles[r]
+
+    def error(self) -> int:
+        e = 0
+        for r, dev in enumerate(self.devices):
+            with torch.cuda.device(dev):
+                e |= int(cabi.lib().nbm_comm_error(self.blocks[r]))
+        return e
+
+    def raise_on_error(self, where: str) -> None:
+        if self.error():
+            raise cabi.NbmError(f"peer all-reduce timed out ({where}): a device did not reach the exchange within "
+                                f"{self.timeout_s:g} s (NBM_PEER_TIMEOUT_S)")
+
+    def close(self):
+        L = cabi.lib()
+        for r, dev in enumerate(self.devices):
+            with torch.cuda.device(dev):
+                torch.cuda.synchronize(dev)
+                if self.blocks[r]:
+                    L.nbm_comm_free(self.blocks[r])
+                    self.blocks[r] = None

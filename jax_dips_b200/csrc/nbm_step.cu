@@ -1236,12 +1236,14 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
 
 template <class NET, bool GENERAL>
 static cudaError_t launch_node_grad(dim3 grid, const NodeView& v, const Tasks& T, cudaStream_t st) {
-    static bool configured = false;   // per instantiation; the attribute is a property of the function
+    static unsigned long long configured = 0ull;   // per instantiation AND per device (one process may drive several)
     constexpr int bytes = grad_smem_bytes<NET>();
-    if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!((configured >> (dev & 63)) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(node_grad_kernel<NET, GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured |= 1ull << (dev & 63);
     }
     node_grad_kernel<NET, GENERAL><<<grid, kGradThreads, bytes, st>>>(v, T);
     return cudaSuccess;
@@ -1580,12 +1582,14 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_fused_kernel(FusedV
 
 template <class NET>
 static cudaError_t launch_node_grad_fused(int grid, const FusedView& v, const Tasks& T, cudaStream_t st) {
-    static int configured = 0;
+    static int configured[64] = {0};   // per device
     const int bytes = fused_smem_bytes<NET>(v.ez);
-    if (configured < bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured[dev & 63] < bytes) {
         cudaError_t e = cudaFuncSetAttribute(node_grad_fused_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
-        configured = bytes;
+        configured[dev & 63] = bytes;
     }
     node_grad_fused_kernel<NET><<<grid, kGradThreads, bytes, st>>>(v, T);
     return cudaSuccess;
@@ -2177,9 +2181,19 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
 // then raises its flag in every block;  (3) each rank polls only its LOCAL flags and adds the slots in rank order, so the
 // result is bitwise identical on all ranks.  Slots are double-buffered by step parity: a peer can be at most one step
 // ahead (it cannot finish step k+1 before this rank has raised its k+1 flags, which happens after step k's reads).
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// `timeout_ns` == 0: wait for the peers without a bound (what NCCL does).  Otherwise a rank that has waited that long
+// sets the block's error word and poisons ITS output with NaN - never a plausible-looking partial sum; the host turns
+// the error word into an exception (Trainer._check_comm, bench.py).
 __global__ void __launch_bounds__(1024) reduce_allreduce_kernel(const float* __restrict__ partials, int rows, int np1,
                                                                 int rank, int world, CommPeers peers,
-                                                                int32_t* __restrict__ step_dev, float* __restrict__ out) {
+                                                                int32_t* __restrict__ step_dev, float* __restrict__ out,
+                                                                unsigned long long timeout_ns) {
     extern __shared__ float sred[];   // [ngrp][np1]
     const int t = threadIdx.x;
     const unsigned int step = (unsigned int)*step_dev;
@@ -2208,9 +2222,10 @@ __global__ void __launch_bounds__(1024) reduce_allreduce_kernel(const float* __r
     __syncthreads();
     if (t < world && t != rank) {
         const unsigned int* f = &mine->flag[par][t];
-        long long t0 = clock64();
+        const unsigned long long t0 = timeout_ns ? global_ns() : 0ull;
+        unsigned int spins = 0;
         while ((int)(ld_acquire_sys(f) - (step + 1)) < 0) {
-            if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz: report instead of hanging the device
+            if (timeout_ns && ((++spins & 1023u) == 0u) && global_ns() - t0 > timeout_ns) {
                 atomicExch(&mine->error, 1u);
                 atomicExch(&s_fail, 1);
                 break;
@@ -2745,6 +2760,46 @@ int nbm_loss_grad_points_f32(const nbm_points_step_t* s, nbm_stream_t stream) {
 }
 
 
+static unsigned long long g_comm_timeout_ns = 30ull * 1000000000ull;
+
+int nbm_comm_set_timeout(double seconds) {
+    NBM_REQUIRE(seconds >= 0.0 && seconds < 1e9, "timeout must be >= 0 seconds (0 = wait without a bound)");
+    g_comm_timeout_ns = (unsigned long long)(seconds * 1e9);
+    return NBM_OK;
+}
+
+int nbm_comm_alloc_local(void** local_block) {
+    NBM_REQUIRE(local_block, "null pointer");
+    void* p = nullptr;
+    int rc = cuda_check(cudaMalloc(&p, sizeof(CommBlock)), "cudaMalloc(comm block)");
+    if (rc) return rc;
+    rc = cuda_check(cudaMemset(p, 0, sizeof(CommBlock)), "memset(comm block)");
+    if (rc) return rc;
+    *local_block = p;
+    return NBM_OK;
+}
+
+int nbm_enable_peer_access(int device, int peer) {
+    NBM_REQUIRE(device >= 0 && peer >= 0 && device != peer, "bad device pair");
+    int can = 0;
+    int rc = cuda_check(cudaDeviceCanAccessPeer(&can, device, peer), "cudaDeviceCanAccessPeer");
+    if (rc) return rc;
+    if (!can) {
+        set_error("device %d cannot access device %d's memory (no NVLink / PCIe peer path)", device, peer);
+        return NBM_ERR_UNSUPPORTED;
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    cudaSetDevice(cur);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return NBM_OK;
+    }
+    return cuda_check(e, "cudaDeviceEnablePeerAccess");
+}
+
 int nbm_comm_alloc(void** local_block, unsigned char handle[NBM_IPC_HANDLE_BYTES]) {
     NBM_REQUIRE(local_block && handle, "null pointer");
     static_assert(sizeof(cudaIpcMemHandle_t) == NBM_IPC_HANDLE_BYTES, "IPC handle size");
@@ -2790,8 +2845,8 @@ int nbm_reduce_allreduce_f32(const float* partials, int rows, int np1, int rank,
     const int threads = 1024;   // np1 <= 1025 columns... one column per thread in the last phase needs np1 <= 1024
     NBM_REQUIRE(np1 <= 1024, "np1 must be <= 1024");
     const int ngrp = threads / np1 > 0 ? threads / np1 : 1;
-    reduce_allreduce_kernel<<<1, threads, sizeof(float) * (size_t)ngrp * np1, as_stream(stream)>>>(partials, rows, np1, rank,
-                                                                                                 world, peers, step_dev, out);
+    reduce_allreduce_kernel<<<1, threads, sizeof(float) * (size_t)ngrp * np1, as_stream(stream)>>>(
+        partials, rows, np1, rank, world, peers, step_dev, out, g_comm_timeout_ns);
     NBM_LAUNCH_CHECK("reduce_allreduce");
     return NBM_OK;
 }

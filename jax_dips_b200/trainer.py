@@ -7,10 +7,11 @@ Differences a user of the reference must know (all documented in DESIGN.md):
 * coefficient callables are the reference's per-point callables written against
   `jax_dips_b200.numpy` (torch) instead of `jax.numpy`; they are batched by calling them once on
   the (3, n) view of the point list (the role `vmap` plays at trainer.py:995-1005);
-* the level set is sampled once on `lvl_gstate` and read by the kernels through the reference's
-  own grid interpolant (`phi_interp="trilinear"`: interpolate.py:906, `"quadratic"`: :388) - the
-  configuration examples/dragon uses (solve_dragon.py:177) - or, with `phi_interp="analytic"`, the
-  callable itself is the level set everywhere (sampled on the host at the positions the kernels need);
+* the level set: by default (`phi_interp="analytic"`) the user's callable itself is the level set
+  everywhere, as in the reference (discretization.py:90; sampled on the host at the positions the
+  kernels need).  `phi_interp="trilinear"` (interpolate.py:906) / `"quadratic"` (:388) sample it once on
+  `lvl_gstate` and let the kernels read it through the reference's own grid interpolant - what a
+  reference user gets by passing such an interpolant as `lvl_set_fn` (examples/dragon, solve_dragon.py:177);
 * `nonlinear_op_m/p` must be None / zero / `Nonlinear.sinh(coef)`;
 * the initial parameters follow haiku's initialisers (TruncatedNormal(0.1) hidden, 1/sqrt(fan_in)
   output, zero bias; MLP.py:65,70) but are drawn from a torch generator seeded with 42, because
@@ -160,24 +161,35 @@ class Trainer:
                  batch_size: int = 131072, checkpoint_dir: str = "./checkpoints", checkpoint_interval: int = 2,
                  results_dir: str = "./", loss_plot_name: str = "solver_loss", optimizer_dict: dict = None,
                  restart: bool = False, restart_checkpoint_dir: str = "./checkpoints", print_rate: int = 1,
-                 model_dict: dict = None, phi_interp: str = "trilinear", perturb_eps: float = 1e-10,
+                 model_dict: dict = None, phi_interp: str = "analytic", perturb_eps: float = 1e-10,
                  device=None, init_params: Optional[torch.Tensor] = None, use_cuda_graph: bool = True,
-                 allreduce: str = "peer"):
+                 allreduce: str = "peer", n_devices: Optional[int] = None):
         global stop_training
+        stop_training = False   # a SIGINT that stopped an earlier Trainer of this process must not stop this one
         if algorithm != 0:
             # discretization.py:146-148 references undefined attributes for algorithm=1
             raise NotImplementedError("only algorithm=0 (regression extrapolation) exists on this path")
         optimizer_dict = optimizer_dict or _DEFAULT_OPT
         model_dict = model_dict or _DEFAULT_MODEL
+        self._optimizer_dict, self._model_dict = optimizer_dict, model_dict
+        self._phi_interp, self._perturb_eps = phi_interp, perturb_eps
         self.device = torch.device(device) if device is not None else default_device()
         self.lvl_gstate, self.tr_gstate, self.eval_gstate = lvl_gstate, tr_gstate, eval_gstate
         self.sim_state, self.sim_state_fn = sim_state, sim_state_fn
         self.batch_size, self.num_epochs, self.multi_gpu = batch_size, num_epochs, multi_gpu
         self.checkpoint_dir, self.checkpoint_interval = checkpoint_dir, checkpoint_interval
         self.results_dir, self.loss_plot_name, self.print_rate = results_dir, loss_plot_name, print_rate
+        # the reference stores this factor and never reads it outside the private, unused `__update`
+        # (trainer.py:791-816): the public `update` / `update_multi_gpu` ignore it.  Anything but 1 would silently
+        # train differently from what the caller asked for, so say so.
         self.mgrad_over_pgrad_scalefactor = mgrad_over_pgrad_scalefactor
+        if mgrad_over_pgrad_scalefactor != 1:
+            logger.warning("mgrad_over_pgrad_scalefactor=%s is accepted for API compatibility but, as in the reference "
+                           "(only its unused `__update` reads it, trainer.py:791-816), it does not enter the update",
+                           mgrad_over_pgrad_scalefactor)
         self.restart_checkpoint_dir = restart_checkpoint_dir
         self.use_cuda_graph = use_cuda_graph
+        self.n_devices = n_devices       # single-process multi_gpu: how many local devices (default: all visible)
         if allreduce not in ("peer", "nccl"):
             raise ValueError("allreduce must be 'peer' (fused NVLink peer-memory kernel) or 'nccl'")
         self.allreduce_kind = allreduce
@@ -223,8 +235,10 @@ class Trainer:
                 if state is None:
                     raise FileNotFoundError(f"no checkpoint under {self.restart_checkpoint_dir}")
                 self.params = tree_to_params(self.net, state["params"], self.precond).to(self.device)
-                self.opt_state.copy_(torch.as_tensor(state["opt_state"]["moments"]).to(self.device))
-                self.opt_count.fill_(int(state["opt_state"]["count"]))
+                ost = state.get("opt_state") or {}
+                if "moments" in ost:     # checkpoints of the lbfgs path carry scipy's result instead (warm start)
+                    self.opt_state.copy_(torch.as_tensor(ost["moments"]).to(self.device))
+                    self.opt_count.fill_(int(ost.get("count", 0)))
                 self.batch_size = state["batch_size"]
                 logger.info(f"Resuming training from epoch {state['epoch']} with batch_size {self.batch_size}, "
                             f"resolution {state['resolution']}.")
@@ -330,17 +344,19 @@ class Trainer:
         upload_params(self.net, params)
         return plan.loss_grad_launch()
 
-    def _step(self, plan, loss_hist: Optional[torch.Tensor], allreduce: bool):
+    def _step(self, plan, loss_hist: Optional[torch.Tensor], allreduce: bool, local_comm=None):
         """update (trainer.py:783-789) / update_multi_gpu (:824-834) on the current stream.  Inside the training loops
         the parameters reach the constant bank from the copies the previous step's finalize kernel staged
         (`_begin_training` stages the initial ones); the partial-row reduction, the optax chain and that staging are one
-        kernel."""
+        kernel.  `local_comm`: this device's handle of an in-process peer exchange (single-process multi-device)."""
         L = cabi.lib()
         cabi.check(L.nbm_upload_staged_params(cabi.stream_ptr()), "nbm_upload_staged_params")
         net = self.net.struct()
         partials, rows = None, 0
         d = _dist() if allreduce else None
-        if d is not None and d.get_world_size() > 1:
+        if local_comm is not None:
+            lg = plan.loss_grad_launch(comm=local_comm)
+        elif d is not None and d.get_world_size() > 1:
             comm = self._peer_comm() if (self.allreduce_kind == "peer" and isinstance(plan, (SharedPlan, EmptyPlan))) else None
             if comm is not None:
                 lg = plan.loss_grad_launch(comm=comm)    # reduction fused with the psum over NVLink peer memory
@@ -384,10 +400,21 @@ class Trainer:
         return self._comm
 
     def _graph_step(self, plan, loss_hist, allreduce: bool):
-        """replay the step as a CUDA graph (launch-bound at small grids)"""
-        if not self.use_cuda_graph or allreduce:
+        """replay the step as a CUDA graph (launch-bound at small grids).  The multi-GPU step is captured too when its
+        exchange is the peer-memory kernel (an ordinary kernel launch); with NCCL the collective stays eager."""
+        peer = False
+        if allreduce:
+            d = _dist()
+            if d is not None and d.get_world_size() > 1:
+                peer = (self.allreduce_kind == "peer" and isinstance(plan, (SharedPlan, EmptyPlan))
+                        and self._peer_comm() is not None)
+                if not peer:
+                    return self._step(plan, loss_hist, allreduce)
+            else:
+                allreduce = False
+        if not self.use_cuda_graph:
             return self._step(plan, loss_hist, allreduce)
-        key = (id(plan), loss_hist.data_ptr() if loss_hist is not None else 0)
+        key = (id(plan), loss_hist.data_ptr() if loss_hist is not None else 0, bool(allreduce))
         g = self._graphs.get(key)
         if g is None:
             side = torch.cuda.Stream(device=self.device)
@@ -396,11 +423,18 @@ class Trainer:
                 # warm-up outside capture on scratch copies would change the state: capture directly
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=side):
-                    self._step(plan, loss_hist, False)
+                    self._step(plan, loss_hist, allreduce)
             torch.cuda.current_stream().wait_stream(side)
             self._graphs[key] = g
             # the capture itself does not execute the step
         g.replay()
+
+    def _check_comm(self, where: str) -> None:
+        """a peer wait that timed out poisons the result with NaN on that rank only: turn it into an exception on the
+        host instead of letting the replicas diverge silently"""
+        if self._comm is not None and self._comm.error():
+            raise cabi.NbmError(f"peer all-reduce timed out ({where}): a rank did not reach the exchange within "
+                                f"{self._comm.timeout_s:g} s (NBM_PEER_TIMEOUT_S); parameters on this rank are invalid")
 
     # ------------------------------------------------------------------------------------------
     # training loops
@@ -414,8 +448,9 @@ class Trainer:
         torch.cuda.synchronize(self.device)
         logger.info(f"solve took {time.time() - start_time} (sec)")
         d = _dist()
+        last_epoch = int(self.epoch_store[-1]) + 1 if len(self.epoch_store) else self.epoch_start
         if d is None or d.get_rank() == 0:
-            self.save_checkpoint(self.checkpoint_dir, self._checkpoint_state(int(self.epoch_store[-1]) + 1))
+            self.save_checkpoint(self.checkpoint_dir, self._checkpoint_state(last_epoch))
         final_solution, grad_u, grad_u_normal = self.evaluate_solution_and_gradients(self.params, self.eval_gstate)
         return final_solution, grad_u, grad_u_normal, self.epoch_store, self.loss_epochs
 
@@ -488,11 +523,19 @@ class Trainer:
         return np.arange(self.epoch_start, self.num_epochs), losses
 
     def multi_GPU_train(self):
-        """trainer.py:715-779: one process per GPU; the points are split in contiguous blocks
-        (x-slabs, data_management.py:121-130), no multi-resolution schedule, grads and loss are
-        SUMMED over devices (:829-830) and every rank applies the identical update."""
+        """trainer.py:715-779: the points are split in contiguous blocks (x-slabs, data_management.py:121-130), no
+        multi-resolution schedule, grads and loss are SUMMED over devices (:829-830) and every device applies the
+        identical update.  Two launch models: one process per GPU under `torchrun` (torch.distributed initialised), or -
+        like the reference's single-process `pmap` over `jax.local_device_count()` (:727-743) - this process driving every
+        local device itself (`_multi_device_train`)."""
         global stop_training
         d = _dist()
+        if d is None:
+            n_local = min(torch.cuda.device_count(), self.n_devices or torch.cuda.device_count())
+            if n_local > 1:
+                return self._multi_device_train(n_local)
+            logger.warning("multi_gpu=True with one visible device and no torch.distributed group: training on one GPU "
+                           "(jax.local_device_count() == 1 gives the reference the same)")
         world = d.get_world_size() if d is not None else 1
         rank = d.get_rank() if d is not None else 0
         DD = data_management.DatasetDict(num_points=self.tr_gstate.num_points(), batch_size=world * self.batch_size,
@@ -509,27 +552,156 @@ class Trainer:
         t0 = time.time()
         self._begin_training()
         with torch.cuda.device(self.device):
-            loss_hist = torch.zeros(self.num_epochs * nb + 1, dtype=torch.float32, device=self.device)
+            # every plan of an epoch is built BEFORE the first exchange (set-up cost differs a lot between ranks: the
+            # interface may lie in a few slabs only), then the ranks meet at a barrier
+            plans = [self.plan_for(0, p0, p1) for (p0, p1) in ranges]
+            if d is not None and world > 1:
+                if self.allreduce_kind == "peer":
+                    self._peer_comm()
+                torch.cuda.synchronize(self.device)
+                d.barrier()
+            n_steps = (self.num_epochs - self.epoch_start) * nb
+            loss_hist = torch.zeros(n_steps + 1, dtype=torch.float32, device=self.device)
             base = int(self.opt_count.item())
+            # the finalize kernel files the loss under the optimizer's step count: a restarted run (count != 0) gets
+            # a view that starts `base` entries earlier so that its steps land in [0, n_steps)
+            hist = loss_hist if base == 0 else None
+            per_step = [] if hist is None else None
+            stop_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
             for epoch in range(self.epoch_start, self.num_epochs):
-                if stop_training:
+                # SIGINT reaches the ranks at different times (or only one of them): agree on the epoch to stop at
+                stop = bool(stop_training)
+                if d is not None and world > 1:
+                    stop_flag.fill_(1 if stop else 0)
+                    d.all_reduce(stop_flag, op=d.ReduceOp.MAX)
+                    stop = bool(int(stop_flag.item()))
+                if stop:
                     break
-                for (p0, p1) in ranges:
-                    plan = self.plan_for(0, p0, p1)
-                    self._step(plan, loss_hist if base == 0 else None, allreduce=True)
+                for plan in plans:
+                    self._graph_step(plan, hist, allreduce=True)
+                    if per_step is not None:
+                        per_step.append(plan.loss_grad[-1:].clone())
                 epoch_store.append(epoch)
                 if self.print_rate and epoch % self.print_rate == 0 and logger.isEnabledFor(logging.INFO):
                     dt_avg = (time.time() - t0) / self.print_rate
                     t0 = time.time()
                     logger.info(f"Epoch # {epoch} \t avg epoch time is {dt_avg} (sec)")
-                if (epoch + 1) % self.checkpoint_interval == 0 and rank == 0:
-                    self.save_checkpoint(self.checkpoint_dir, self._checkpoint_state(epoch + 1))
+                if (epoch + 1) % self.checkpoint_interval == 0:
+                    self._check_comm(f"epoch {epoch}")       # (host read: synchronises this rank's stream)
+                    if rank == 0:
+                        self.save_checkpoint(self.checkpoint_dir, self._checkpoint_state(epoch + 1))
             torch.cuda.synchronize(self.device)
+            self._check_comm("end of training")
             n_done = len(epoch_store)
-            per_epoch = loss_hist[: n_done * nb].view(n_done, nb).mean(dim=1).cpu()
+            if hist is not None:
+                per_epoch = loss_hist[: n_done * nb].view(n_done, nb).mean(dim=1).cpu()
+            else:
+                per_epoch = (torch.cat(per_step).view(n_done, nb).mean(dim=1).cpu() if n_done
+                             else torch.zeros(0))
         # the reference returns a list of per-device arrays (all entries equal after the psum)
         loss_epochs = [per_epoch[e].repeat(world) for e in range(n_done)]
         return epoch_store, loss_epochs
+
+    def _multi_device_train(self, n_dev: int):
+        """`multi_gpu=True` without a torch.distributed group: ONE process drives all local devices, as the reference's
+        `pmap(update_multi_gpu, axis_name="devices")` does (trainer.py:727-756).  Every device holds a replica
+        (parameters, optimizer state, level set, its x-slab's row tables); per step every device runs its slab's
+        kernels on its own stream and the [grad, loss] SUM (psum, :829-830) is the peer-memory exchange kernel between
+        the devices' blocks (peer access inside the process instead of CUDA IPC); each replica's step is one CUDA graph."""
+        global stop_training
+        from .comm import LocalPeerComm
+        devices = [torch.device("cuda", r) for r in range(n_dev)]
+        DD = data_management.DatasetDict(num_points=self.tr_gstate.num_points(), batch_size=n_dev * self.batch_size,
+                                         num_gpus=n_dev)
+        self._warn_if_padded(DD)
+        plane = self.tr_gstate.shape()[1] * self.tr_gstate.shape()[2]
+        if not all(p0 % plane == 0 and p1 % plane == 0 for r in range(n_dev) for (p0, p1) in DD.ranges(r) if p1 > p0):
+            raise NotImplementedError(
+                "single-process multi-device training needs batches of whole x planes on every device (the fused peer "
+                "exchange serves the shared-evaluation path); launch one process per GPU with torchrun for ragged "
+                "partitions (NCCL exchange)")
+        reps = [self]
+        for dev in devices:
+            if dev == self.device:
+                continue
+            reps.append(Trainer(self.lvl_gstate, self.tr_gstate, self.eval_gstate, self.sim_state, self.sim_state_fn,
+                                0, lvl_set_fn=None, num_epochs=self.num_epochs, multi_gpu=False,
+                                batch_size=self.batch_size, checkpoint_dir=None, optimizer_dict=self._optimizer_dict,
+                                model_dict=self._model_dict, phi_interp=self._phi_interp, perturb_eps=self._perturb_eps,
+                                device=dev, init_params=self.params.detach().cpu(), use_cuda_graph=self.use_cuda_graph,
+                                print_rate=0))
+        reps.sort(key=lambda t: t.device.index)
+        for t in reps:
+            if t is not self:          # replicate the optimizer state too (a restarted run)
+                t.opt_state.copy_(self.opt_state.to(t.device))
+                t.opt_count.copy_(self.opt_count.to(t.device))
+        comm = LocalPeerComm([t.device for t in reps])
+        nb = len(DD.ranges(0))
+        n_steps = (self.num_epochs - self.epoch_start) * nb
+        base = int(self.opt_count.item())
+        hists, plans, graphs = [], [], []
+        for r, t in enumerate(reps):
+            with torch.cuda.device(t.device):
+                t._begin_training()
+                hists.append(torch.zeros(n_steps + 1, dtype=torch.float32, device=t.device))
+                plans.append([t.plan_for(0, p0, p1) for (p0, p1) in DD.ranges(r)])
+                torch.cuda.synchronize(t.device)
+        per_step = [] if base != 0 else None
+
+        def launch(r, b):
+            t = reps[r]
+            with torch.cuda.device(t.device):
+                hist = hists[r] if base == 0 else None
+                if not self.use_cuda_graph:
+                    return t._step(plans[r][b], hist, True, local_comm=comm.handle(r))
+                key = (r, b)
+                g = t._graphs.get(key)
+                if g is None:
+                    side = torch.cuda.Stream(device=t.device)
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=side):
+                            t._step(plans[r][b], hist, True, local_comm=comm.handle(r))
+                    torch.cuda.current_stream().wait_stream(side)
+                    t._graphs[key] = g
+                g.replay()
+
+        epoch_store = []
+        t0 = time.time()
+        try:
+            for epoch in range(self.epoch_start, self.num_epochs):
+                if stop_training:
+                    break
+                for b in range(nb):
+                    for r in range(n_dev):
+                        launch(r, b)
+                    if per_step is not None:
+                        with torch.cuda.device(self.device):
+                            per_step.append(plans[reps.index(self)][b].loss_grad[-1:].clone())
+                epoch_store.append(epoch)
+                if self.print_rate and epoch % self.print_rate == 0 and logger.isEnabledFor(logging.INFO):
+                    dt_avg = (time.time() - t0) / self.print_rate
+                    t0 = time.time()
+                    logger.info(f"Epoch # {epoch} \t avg epoch time is {dt_avg} (sec)")
+                if (epoch + 1) % self.checkpoint_interval == 0:
+                    comm.raise_on_error(f"epoch {epoch}")
+                    self.save_checkpoint(self.checkpoint_dir, self._checkpoint_state(epoch + 1))
+            for t in reps:
+                torch.cuda.synchronize(t.device)
+            comm.raise_on_error("end of training")
+        finally:
+            for t in reps:
+                t._graphs.clear()
+            comm.close()
+        n_done = len(epoch_store)
+        with torch.cuda.device(self.device):
+            if per_step is None:
+                per_epoch = hists[reps.index(self)][: n_done * nb].view(n_done, nb).mean(dim=1).cpu()
+            else:
+                per_epoch = torch.cat(per_step).view(n_done, nb).mean(dim=1).cpu() if n_done else torch.zeros(0)
+        self._replicas = reps       # (tests compare the replicas' parameters)
+        return epoch_store, [per_epoch[e].repeat(n_dev) for e in range(n_done)]
 
     # ------------------------------------------------------------------------------------------
     # post-training evaluation (trainer.py:960-977)
@@ -609,7 +781,8 @@ def setup(initial_value_fn, dirichlet_bc_fn, lvl_set_fn, mu_m_fn_, mu_p_fn_, k_m
                 loss_plot_name: str = "solver_loss", optimizer_dict: dict = None, model_dict: dict = None,
                 restart: bool = False, restart_checkpoint_dir: str = "./checkpoints", print_rate: int = 1,
                 **extensions) -> Tuple[PoissonSimState, Callable]:
-        """`extensions` (not in the reference): phi_interp, perturb_eps, device, init_params, use_cuda_graph."""
+        """`extensions` (not in the reference): phi_interp, perturb_eps, device, init_params, use_cuda_graph, allreduce,
+        n_devices."""
         device = torch.device(extensions["device"]) if extensions.get("device") is not None else default_device()
         optimizer_dict = optimizer_dict or {"optimizer_name": "custom", "learning_rate": 1e-3,
                                             "sched": {"scheduler_name": "exponential", "decay_rate": 0.9}}

@@ -63,7 +63,7 @@ def test_general_and_shared_paths_agree_at_native_spacing():
 
 
 def _solve(problem, n_tr, n_lvl, n_eval, num_epochs, batch_size, init, multi_gpu=False, optimizer_dict=None,
-           model_dict=None):
+           model_dict=None, phi_interp="trilinear"):
     lo, hi = problem.box
     init_mesh_fn, _ = mesh.construct(3)
     tr = mesh.linspace_grid(lo, hi, [n_tr] * 3)
@@ -74,7 +74,8 @@ def _solve(problem, n_tr, n_lvl, n_eval, num_epochs, batch_size, init, multi_gpu
                             "sched": {"scheduler_name": "exponential", "decay_rate": 0.975}}
     sim_state, solve_fn = init_fn(lvl_gstate=lv, tr_gstate=tr, eval_gstate=ev, num_epochs=num_epochs,
                                   batch_size=batch_size, multi_gpu=multi_gpu, checkpoint_dir=None,
-                                  optimizer_dict=od, model_dict=model_dict, init_params=init, device=DEV, print_rate=0)
+                                  optimizer_dict=od, model_dict=model_dict, init_params=init, device=DEV, print_rate=0,
+                                  phi_interp=phi_interp)   # the oracle cases below use the gridded level set
     out = solve_fn(sim_state)
     return out, solve_fn.trainer, (tr, lv, ev)
 

@@ -27,7 +27,7 @@ def main():
     init_fn = ntrainer.setup(*P.setup_args())
     sim_state, solve_fn = init_fn(lvl_gstate=lv, tr_gstate=tr, eval_gstate=ev, num_epochs=epochs, batch_size=131072,
                                   multi_gpu=True, checkpoint_dir=None, optimizer_dict=od, init_params=p0.float(),
-                                  print_rate=0)
+                                  print_rate=0, phi_interp="trilinear")
     (state, epoch_store, loss_epochs) = solve_fn(sim_state)
     T = solve_fn.trainer
     if rank == 0:
@@ -49,7 +49,8 @@ def main():
     tr2 = mesh.linspace_grid(*P.box, [15, 16, 16])
     tr2o, lv2, phi2, oprob2 = util.make_case(P, [15, 16, 16], n_lvl, "trilinear", torch.float64)
     sim2, solve2 = init_fn(lvl_gstate=lv, tr_gstate=tr2, eval_gstate=ev, num_epochs=2, batch_size=700,
-                           multi_gpu=True, checkpoint_dir=None, optimizer_dict=od, init_params=p0.float(), print_rate=0)
+                           multi_gpu=True, checkpoint_dir=None, optimizer_dict=od, init_params=p0.float(), print_rate=0,
+                           phi_interp="trilinear")
     (_, _, le2) = solve2(sim2)
     T2 = solve2.trainer
     assert T2.allreduce_kind == "nccl"
