@@ -35,6 +35,7 @@ F_GRAD = 0.93e3       # FLOP per lattice node for the dominant kernel (forward r
 # with the 7-weight row table 40 B + 36 B (SURVEY section 8(d) quotes 64 B/point for a streamed K2 table)
 B_STEP_FACES = 52.0
 B_STEP_ROWS = 76.0
+B_STEP_TMA = 36.0        # fused residual + adjoint: U, 3 face coefficients, 1/diag, rhs read once; R and G written
 # DRAM bytes (read + write) of one node_grad launch at 256^3, `ncu --set full` (profiles/r1_ncu_summary.md)
 NODE_GRAD_TRAFFIC_256 = 160527360
 NODE_GRAD_TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one node_grad launch at sphere 256^3, "
@@ -63,6 +64,7 @@ def parse():
                     help="peer: partial-row reduction fused with the all-reduce over NVLink peer memory; nccl: ncclAllReduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--faces", type=int, default=-1, help="1/0: face-coefficient row table on/off (default: auto)")
+    ap.add_argument("--stencil-tma", type=int, default=-1, help="1/0: residual + adjoint stencils as one TMA-fed kernel (default: auto)")
     ap.add_argument("--fused", type=int, default=-1, help="1/0: adjoint stencil fused into the gradient kernel (default: auto)")
     ap.add_argument("--precond", action="store_true",
                     help="train the learned preconditioner too (model_dict['preconditioner'], lpbe.yaml:62-67): 257 more "
@@ -265,7 +267,8 @@ def main():
     def make_plan(tr_, xa_, xb_, n_mean=None):
         return nplan.SharedPlan(lvl, tr_, xa_, xb_, fns, net, nl_m, nl_p, device=dev, n_mean=n_mean,
                                 faces=None if args.faces < 0 else bool(args.faces),
-                                fused=None if args.fused < 0 else bool(args.fused), precond=precond)
+                                fused=None if args.fused < 0 else bool(args.fused), precond=precond,
+                                stencil_tma=None if args.stencil_tma < 0 else bool(args.stencil_tma))
 
     pl = make_plan(tr, xa, xb)
     torch.cuda.synchronize()
@@ -456,7 +459,9 @@ def main():
 
     # launches per step: constant-bank upload (memcpy node), fwd_nodes, residual, adjoint, node_grad, finalize
     # (+ 2 list kernels each for crossed sites / irregular rows); on several GPUs the peer all-reduce kernel in addition
-    launches_per_step = (6 if world > 1 else 5) + (1 if pl.sites.n > 0 else 0) * 2 + (1 if pl.n_irr > 0 else 0) * 2
+    dense_launches = 3 if pl.stencil_tma_active else 4      # fwd_nodes, (residual + adjoint | stencil_tma), node_grad
+    launches_per_step = ((2 if world > 1 else 1) + dense_launches + (1 if pl.sites.n > 0 else 0) * 2
+                         + (1 if pl.n_irr > 0 else 0) * 2)
 
     # ---------------- value: device-resident inputs -------------------------------------------
     sampler = ClockSampler(local)          # NVML initialised here, outside the timed window
@@ -541,6 +546,10 @@ def main():
         # per-stage device time, live, on the launching stream
         stage_ms = {}
         names = {1: "fwd_nodes", 2: "extrap", 4: "residual", 8: "adjoint", 16: "node_grad"}
+        if pl.stencil_tma_active:
+            # residual rows + adjoint stencil are one kernel; the list kernels (irregular rows, extrapolation adjoint) follow it
+            names = {1: "fwd_nodes", 2: "extrap", 4 | 8 | 64: "stencil_tma", 4 | 8 | 128: "lists", 16: "node_grad",
+                     4 | 64: "residual_alone", 8 | 64: "adjoint_alone"}
         nplan.upload_params(net, params)
         pl.step.stages = 0
         pl.loss_grad_launch()
@@ -566,6 +575,9 @@ def main():
         ach = F_GRAD * ne / (stage_ms["node_grad"] * 1e-3) / 1e12
         step_ach = F_STEP * n_points_total / ((ms / args.steps) * 1e-3) / 1e12 / world
         b_step = B_STEP_FACES if pl.faces else B_STEP_ROWS
+        t_stencil = stage_ms["residual"] + stage_ms["adjoint"] if "residual" in stage_ms else stage_ms["stencil_tma"]
+        if pl.stencil_tma_active:
+            b_step = B_STEP_TMA + (4.0 if pl.kv is not None else 0.0) + (8.0 if pl.nl is not None else 0.0)
         is_256 = (args.workload == "sphere" and args.grid == 256 and world == 1)
         roof = {"bound": "fp32", "kernel": "node_grad_kernel", "achieved": ach, "peak": ffma_peak, "unit": "TFLOP/s",
                 "frac": ach / ffma_peak if ffma_peak else None,
@@ -578,8 +590,9 @@ def main():
                 "stage_ms": stage_ms,
                 "step": {"achieved": step_ach, "per": "GPU", "frac": step_ach / ffma_peak if ffma_peak else None,
                          "frac_nominal": step_ach / FP32_NOMINAL, "algorithmic_flop_per_point": F_STEP},
-                "hbm": {"achieved": b_step * ne / ((stage_ms["residual"] + stage_ms["adjoint"]) * 1e-3) / 1e9,
-                        "peak": hbm_peak, "unit": "GB/s", "kernels": "residual + adjoint",
+                "hbm": {"achieved": b_step * ne / (t_stencil * 1e-3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s",
+                        "kernels": "stencil_tma (residual + adjoint, one kernel)" if pl.stencil_tma_active else "residual + adjoint",
                         "algorithmic_bytes_per_node": b_step,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"}}
         roof["hbm"]["frac"] = roof["hbm"]["achieved"] / hbm_peak
@@ -600,7 +613,9 @@ def main():
                                   f"row tables + work arrays are {table_mb:.0f} MB per GPU (fit in the 126 MB L2): L2 flushed "
                                   "before every timed step by writing a 252 MB buffer (untimed; per-step CUDA events, summed)"),
                            "row_table": "faces (3 face coefficients + 1/diag per node)" if pl.faces else "7 row weights per node",
-                           "adjoint": "fused into the gradient kernel (TMA ring)" if pl.fused else "separate stencil pass",
+                           "adjoint": ("fused into the gradient kernel (TMA ring)" if pl.fused else
+                                       ("residual rows + adjoint stencil in one kernel fed by 3-D TMA boxes (T never leaves the SM)"
+                                        if pl.stencil_tma_active else "separate stencil pass")),
                            "cuda_graph": used_graph,
                            "allreduce": ("peer-memory kernel fused with the partial reduction" if comm is not None
                                          else ("nccl" if world > 1 else "none")),

@@ -289,6 +289,11 @@ typedef struct {
     const int32_t* ge_ptr; const int32_t* ge_ent;
     const int64_t* list_nodes; int64_t n_list;
     const int32_t* g_ptr; const int32_t* g_ent;
+    /* Dense stencil stage with the faces table: 0 = automatic (residual rows + adjoint stencil as ONE kernel fed by 3-D
+     * TMA boxes, `stencil_tma_kernel`, whenever lattice rows are 16-byte multiples, no preconditioner sits between the
+     * two stages and the deterministic list gathers are not combined with a nonlinear operator), -1 = always the two
+     * separate kernels. */
+    int stencil_tma;
 } nbm_shared_step_t;
 
 /* number of preconditioner parameters for hidden widths (d1, d2) */
@@ -301,7 +306,10 @@ enum nbm_stage {
     NBM_STAGE_RESIDUAL = 4,   /* rows: 7-point stencil on U (+ irregular rows) */
     NBM_STAGE_ADJOINT = 8,    /* G = d loss / d U (adjoint stencil + adjoint of irregular rows / extrapolation) */
     NBM_STAGE_GRAD = 16,      /* forward recompute + backward per node, per-CTA partial sums */
-    NBM_STAGE_REDUCE = 32     /* partial rows -> [grad, loss] */
+    NBM_STAGE_REDUCE = 32,    /* partial rows -> [grad, loss] */
+    /* modifiers for timing a selection: leave out the list kernels (crossed sites, irregular rows) / the dense kernels */
+    NBM_STAGE_NO_LISTS = 64,
+    NBM_STAGE_NO_DENSE = 128
 };
 
 int nbm_step_partial_rows(void);

@@ -73,7 +73,8 @@ class SharedStep(C.Structure):
                 ("pc_scale", c_f), ("n_pc_rows", C.c_int), ("pc_nodes_m", c_fp), ("n_pc_m", C.c_int64), ("pc_nodes_p", c_fp), ("n_pc_p", C.c_int64),
                 ("pc_d", c_f * 3),
                 ("ge_ptr", c_fp), ("ge_ent", c_fp), ("list_nodes", c_fp), ("n_list", C.c_int64), ("g_ptr", c_fp),
-                ("g_ent", c_fp)]
+                ("g_ent", c_fp),
+                ("stencil_tma", C.c_int)]
 
 
 class PointsStep(C.Structure):

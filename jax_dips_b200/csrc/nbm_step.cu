@@ -10,6 +10,7 @@
 //
 // The network parameters live in __constant__ memory so that every FFMA takes its weight as a
 // constant-bank operand (no load, no register).
+#include <stdlib.h>
 #include <string.h>
 #include "nbm_common.cuh"
 
@@ -629,8 +630,49 @@ static NodeView view_of(const nbm_shared_step_t& s) {
 }
 
 // A: U[e] = u(node e)   (evaluate_solution_fn, trainer.py:836-844)
+// one thread's part of a task: cell `m` of the flattened (y,z) plane, x planes [x0, x1)
 template <class NET, bool GENERAL>
-__global__ void __launch_bounds__(kThreads) fwd_nodes_kernel(NodeView v, Tasks T) {
+__device__ __forceinline__ void fwd_task(const NodeView& v, const int plane, const float* __restrict__ xe,
+                                         const float* __restrict__ ye, const float* __restrict__ ze,
+                                         const uint8_t* __restrict__ side, float* __restrict__ U, const int m, const int x0,
+                                         const int x1) {
+    if (m >= plane) return;
+    const int iy = m / v.ez, iz = m - iy * v.ez;
+    const float y = __ldg(ye + iy), z = __ldg(ze + iz);
+    typename NET::YZ yz;
+    NET::first_layer_yz(y, z, yz);
+    int64_t e = (int64_t)x0 * plane + m;
+    // two x planes per iteration (they share y, z and every weight fetch); loads one pair ahead
+    float xa_n = __ldg(xe + x0), xb_n = (x0 + 1 < x1) ? __ldg(xe + x0 + 1) : 0.0f;
+    uint8_t sa_n = __ldg(side + e), sb_n = (x0 + 1 < x1) ? __ldg(side + e + plane) : (uint8_t)0;
+    for (int ix = x0; ix < x1; ix += 2) {
+        const float xa = xa_n, xb = xb_n;
+        const bool pa = (sa_n & 1) != 0, pb = (sb_n & 1) != 0;
+        const int64_t e_cur = e;
+        const bool has_b = ix + 1 < x1;
+        if (ix + 2 < x1) {
+            e += 2 * (int64_t)plane;
+            sa_n = __ldg(side + e);
+            xa_n = __ldg(xe + ix + 2);
+            if (ix + 3 < x1) {
+                sb_n = __ldg(side + e + plane);
+                xb_n = __ldg(xe + ix + 3);
+            }
+        }
+        float ua, ub;
+        if (has_b) {
+            NET::eval2(pa, pb, xa, xb, y, z, yz, ua, ub);
+        } else {
+            ua = NET::eval(pa, xa, y, z);
+            ub = 0.0f;
+        }
+        if (!GENERAL || (e_cur >= v.lo && e_cur < v.hi)) U[e_cur] = ua;
+        if (has_b && (!GENERAL || (e_cur + plane >= v.lo && e_cur + plane < v.hi))) U[e_cur + plane] = ub;
+    }
+}
+
+template <class NET, bool GENERAL>
+__global__ void __launch_bounds__(kThreads, 3) fwd_nodes_kernel(NodeView v, Tasks T) {
     const int rep = blockIdx.y;
     const float* xe = v.xe + (size_t)rep * v.ex;
     const float* ye = v.ye + (size_t)rep * v.ey;
@@ -638,42 +680,9 @@ __global__ void __launch_bounds__(kThreads) fwd_nodes_kernel(NodeView v, Tasks T
     const uint8_t* side = v.side + rep * v.rep_nodes;
     float* U = v.U + rep * v.rep_nodes;
     for (int task = blockIdx.x; task < T.total; task += gridDim.x) {
-        int mb = task % T.mblocks, xc = task / T.mblocks;
-        int m = mb * kThreads + threadIdx.x;
-        if (m >= T.plane) continue;
-        int iy = m / v.ez, iz = m - iy * v.ez;
-        float y = __ldg(ye + iy), z = __ldg(ze + iz);
-        typename NET::YZ yz;
-        NET::first_layer_yz(y, z, yz);
-        int x0 = v.x_begin + xc * T.xchunk, x1 = min(v.x_end, x0 + T.xchunk);
-        int64_t e = (int64_t)x0 * T.plane + m;
-        // two x planes per iteration (they share y, z and every weight fetch); loads one pair ahead
-        float xa_n = __ldg(xe + x0), xb_n = (x0 + 1 < x1) ? __ldg(xe + x0 + 1) : 0.0f;
-        uint8_t sa_n = __ldg(side + e), sb_n = (x0 + 1 < x1) ? __ldg(side + e + T.plane) : (uint8_t)0;
-        for (int ix = x0; ix < x1; ix += 2) {
-            const float xa = xa_n, xb = xb_n;
-            const bool pa = (sa_n & 1) != 0, pb = (sb_n & 1) != 0;
-            const int64_t e_cur = e;
-            const bool has_b = ix + 1 < x1;
-            if (ix + 2 < x1) {
-                e += 2 * (int64_t)T.plane;
-                sa_n = __ldg(side + e);
-                xa_n = __ldg(xe + ix + 2);
-                if (ix + 3 < x1) {
-                    sb_n = __ldg(side + e + T.plane);
-                    xb_n = __ldg(xe + ix + 3);
-                }
-            }
-            float ua, ub;
-            if (has_b) {
-                NET::eval2(pa, pb, xa, xb, y, z, yz, ua, ub);
-            } else {
-                ua = NET::eval(pa, xa, y, z);
-                ub = 0.0f;
-            }
-            if (!GENERAL || (e_cur >= v.lo && e_cur < v.hi)) U[e_cur] = ua;
-            if (has_b && (!GENERAL || (e_cur + T.plane >= v.lo && e_cur + T.plane < v.hi))) U[e_cur + T.plane] = ub;
-        }
+        const int mb = task % T.mblocks, xc = task / T.mblocks;
+        const int x0 = v.x_begin + xc * T.xchunk, x1 = min(v.x_end, x0 + T.xchunk);
+        fwd_task<NET, GENERAL>(v, T.plane, xe, ye, ze, side, U, mb * kThreads + (int)threadIdx.x, x0, x1);
     }
 }
 
@@ -917,11 +926,8 @@ __device__ __forceinline__ Faces4 load_faces4(const nbm_shared_step_t& s, int64_
 }
 #define NBM_DIAG(F, c) ((((((F).cxm.c + (F).cxp.c) + (F).cym.c) + (F).cyp.c) + (F).czm.c) + (F).czp.c)
 
-__global__ void __launch_bounds__(kThreads) residual_faces4_kernel(nbm_shared_step_t s) {
-    const int plane = s.ey * s.ez;
-    const int m = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int ix = blockIdx.y + 1;
-    if (m >= plane) return;
+// rows of the 4 consecutive cells m..m+3 of plane ix (1 <= ix <= ex-2)
+__device__ __forceinline__ void residual_faces4_body(const nbm_shared_step_t& s, const int plane, const int m, const int ix) {
     const int64_t sx = plane, sy = s.ez;
     const int64_t ne = sx * s.ex;
     const int64_t e = ix * sx + m;
@@ -949,21 +955,26 @@ __global__ void __launch_bounds__(kThreads) residual_faces4_kernel(nbm_shared_st
     NBM_ROW(x) NBM_ROW(y) NBM_ROW(z) NBM_ROW(w)
 #undef NBM_ROW
     if (s.nl) {
+        // (rows without a dense row - irregular rows live in the list - stay exactly 0 here)
         float4 a = ld4(s.nl + e), b = ld4(s.nl + ne + e);
-        r.x += a.x * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.x) + b.x * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.x);
-        r.y += a.y * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.y) + b.y * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.y);
-        r.z += a.z * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.z) + b.z * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.z);
-        r.w += a.w * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.w) + b.w * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.w);
+        if (di.x != 0.f) r.x += a.x * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.x) + b.x * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.x);
+        if (di.y != 0.f) r.y += a.y * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.y) + b.y * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.y);
+        if (di.z != 0.f) r.z += a.z * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.z) + b.z * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.z);
+        if (di.w != 0.f) r.w += a.w * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.w) + b.w * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.w);
     }
     *reinterpret_cast<float4*>(s.R + e) = r;
     if (s.S) *reinterpret_cast<float4*>(s.S + e) = tval4(di, r);
 }
 
-__global__ void __launch_bounds__(kThreads) adjoint_faces4_kernel(nbm_shared_step_t s) {
+__global__ void __launch_bounds__(kThreads) residual_faces4_kernel(nbm_shared_step_t s) {
     const int plane = s.ey * s.ez;
     const int m = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int ix = blockIdx.y;
     if (m >= plane) return;
+    residual_faces4_body(s, plane, m, blockIdx.y + 1);
+}
+
+// G of the 4 consecutive cells m..m+3 of plane ix (0 <= ix <= ex-1)
+__device__ __forceinline__ void adjoint_faces4_body(const nbm_shared_step_t& s, const int plane, const int m, const int ix) {
     const int64_t sx = plane, sy = s.ez;
     const int64_t ne = sx * s.ex;
     const int64_t e = ix * sx + m;
@@ -1000,6 +1011,13 @@ __global__ void __launch_bounds__(kThreads) adjoint_faces4_kernel(nbm_shared_ste
         g.w += (a.w * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.w) + b.w * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.w)) * r0.w;
     }
     *reinterpret_cast<float4*>(s.G + e) = g;
+}
+
+__global__ void __launch_bounds__(kThreads) adjoint_faces4_kernel(nbm_shared_step_t s) {
+    const int plane = s.ey * s.ez;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (m >= plane) return;
+    adjoint_faces4_body(s, plane, m, blockIdx.y);
 }
 
 // C0 (deterministic form): the adjoint of the lists GATHERED through the transposed incidence (CSR built once per
@@ -1047,12 +1065,19 @@ __global__ void gather_G_kernel(nbm_shared_step_t s) {
     s.G[s.list_nodes[i]] += acc;
 }
 
-// C0: adjoint of the irregular rows: gE[c] += wE * R[p]
-__global__ void irregular_bwd_kernel(nbm_shared_step_t s) {
+// C0: adjoint of the irregular rows: gE[c] += wE * R[p].  `nl_center`: the dense adjoint ran BEFORE this row's
+// residual existed (fused dense stage), so the U-part of the row's nonlinear term is added here instead.
+__global__ void irregular_bwd_kernel(nbm_shared_step_t s, bool nl_center) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= s.n_irr) return;
     const int64_t e = s.irr_point[q];
     float r = s.R[e];
+    if (nl_center && s.nl) {
+        const int64_t ne = (int64_t)s.ex * s.ey * s.ez;
+        const float u0 = s.U[e];
+        atomicAdd(s.G + e, (s.nl[e] * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0) +
+                            s.nl[ne + e] * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0)) * r);
+    }
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         int32_t c = s.irr_c[q * 7 + k];
@@ -1594,6 +1619,8 @@ static cudaError_t launch_node_grad_fused(int grid, const FusedView& v, const Ta
     node_grad_fused_kernel<NET><<<grid, kGradThreads, bytes, st>>>(v, T);
     return cudaSuccess;
 }
+
+#include "nbm_stencil_tma.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Learned preconditioner (nn/preconditioner.py:10-35; discretization.py:339, 418-419): every row is scaled by
@@ -2284,14 +2311,29 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     const int gridP = pc ? min(s.n_pc_rows, 3 * sms) : 0;
     int gridC = min(Tg.total, min(kPartialRows, sms));
     if (gridC > s.n_partial_rows - gridP) gridC = s.n_partial_rows - gridP;
-    if (stages & NBM_STAGE_FWD) {
+    // K_B: residual rows + adjoint stencil of the faces table as one TMA-fed kernel whenever both stages are wanted and
+    // nothing sits between them (the preconditioner rescales R; the r1 fused gradient kernel wants S)
+    const int dense2 = NBM_STAGE_RESIDUAL | NBM_STAGE_ADJOINT;
+    const bool fusedA = s.stencil_tma >= 0 && s.faces && !pc && !s.S && !(s.nl && s.g_ptr) && ((stages & dense2) == dense2) &&
+                        stencil_tma::applicable(s);
+    // timing modifiers: run only the dense kernels / only the list kernels of the selected stages
+    const bool lists_on = !(stages & NBM_STAGE_NO_LISTS), dense_on = !(stages & NBM_STAGE_NO_DENSE);
+    if (dense_on && (stages & NBM_STAGE_FWD)) {
         int gridA = min(T.total, sms * 8);
         fwd_nodes_kernel<NET, false><<<gridA, kThreads, 0, st>>>(view_of(s), T);
     }
-    if ((stages & NBM_STAGE_EXTRAP) && s.n_crossed > 0)
+    if ((stages & NBM_STAGE_EXTRAP) && lists_on && s.n_crossed > 0)
         extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
-    if (stages & NBM_STAGE_RESIDUAL) {
-        if (s.faces) {
+    if (fusedA) {
+        if (dense_on) {
+            int rc = stencil_tma::launch(s, sms, st);
+            if (rc) return rc;
+        }
+        // (the dense adjoint ran before these rows' residuals exist: irregular_bwd adds their nonlinear centre term)
+        if (lists_on && s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
+    } else if (stages & NBM_STAGE_RESIDUAL) {
+        if (!dense_on) {
+        } else if (s.faces) {
             dim3 g((s.ey * s.ez / 4 + kThreads - 1) / kThreads, s.ex - 2);
             residual_faces4_kernel<<<g, kThreads, 0, st>>>(s);
         } else if (vec4) {
@@ -2301,7 +2343,7 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
             dim3 g((s.ey * s.ez + kThreads - 1) / kThreads, s.ex - 2);
             residual_kernel<<<g, kThreads, 0, st>>>(s);
         }
-        if (s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
+        if (lists_on && s.n_irr > 0) irregular_fwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
         if (pc) {
             // rows [gridC, gridC + gridP) of the partials: preconditioner gradient + the loss.  Uncrossed cells: one
             // launch per side (inputs reduce to 6 face coefficients); crossed cells: the generic kernel on their list
@@ -2330,7 +2372,9 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     }
     const bool fused = s.faces && s.S && !s.nl && !pc;
     if (stages & NBM_STAGE_ADJOINT) {
-        if (fused) {
+        if (fusedA || !dense_on) {
+            // (dense adjoint already done inside K_B / not wanted)
+        } else if (fused) {
             // the dense adjoint stencil runs inside the gradient kernel; G only collects the list contributions.
             // A profiling run that stops before the gradient stage would leave them behind: clear first.
             if (!(stages & NBM_STAGE_GRAD))
@@ -2345,11 +2389,12 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
             dim3 g((s.ey * s.ez + kThreads - 1) / kThreads, s.ex);
             adjoint_kernel<<<g, kThreads, 0, st>>>(s);
         }
-        if (s.g_ptr) {   // deterministic gathers through the transposed incidence
+        if (!lists_on) {
+        } else if (s.g_ptr) {   // deterministic gathers through the transposed incidence
             if (s.n_crossed > 0) gather_gE_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
             if (s.n_list > 0) gather_G_kernel<<<(unsigned)((s.n_list + 127) / 128), 128, 0, st>>>(s);
         } else {
-            if (s.n_irr > 0) irregular_bwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s);
+            if (s.n_irr > 0) irregular_bwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s, fusedA);
             if (s.n_crossed > 0) extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, st>>>(s);
         }
     }

@@ -12,6 +12,7 @@ callables there with torch on the device, and K2 consumes the sample arrays.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Optional, Sequence
 
 import torch
@@ -359,14 +360,15 @@ class SharedPlan:
     def __init__(self, lvl: LevelSet, tr_gstate, xa: int, xb: int, fns, net: NetShape,
                  nonlinear_m: Nonlinear, nonlinear_p: Nonlinear, n_mean: Optional[int] = None, device=None,
                  faces: Optional[bool] = None, fused: Optional[bool] = None, precond: Optional[PrecondShape] = None,
-                 deterministic: bool = False):
+                 deterministic: bool = False, stencil_tma: Optional[bool] = None):
         """`faces`: store one coefficient per cell FACE + 1/diag (16 B/node) instead of the 7 row weights
-        (28 B/node); irregular rows move into the list.  Default: on whenever the 16-byte stencil kernels
-        apply (even Ny, Nz).
+        (28 B/node); irregular rows move into the list.  Default: on (lattice rows are padded to 16-byte multiples).
         `fused`: evaluate the dense adjoint stencil inside the gradient kernel from TMA-staged row tables
         instead of a separate pass (needs faces and no nonlinear operator).  Default OFF: measured on B200 at
         256^3 the fused kernel takes 516-585 us against 370 + 122 us for gradient + adjoint kernels (the
         shared ring couples the 12 warps of a CTA to the slowest one).
+        `stencil_tma`: residual rows and adjoint stencil of the faces table as ONE kernel whose x planes arrive as 3-D
+        TMA boxes (halo included) in a shared-memory ring (`csrc/nbm_stencil_tma.cuh`).  Default: on where it applies.
         `deterministic`: gather the adjoint of the lists (irregular rows, extrapolation) through their transposed
         incidence instead of scattering it with fp32 atomics: the whole step becomes bitwise reproducible, for
         ~5 us more per step at 256^3 (the atomics are faster than the doubly indirect gathers)."""
@@ -383,10 +385,10 @@ class SharedPlan:
             nxl = xb - xa
             self.n_points = nxl * Ny * Nz
 
-            def extend(a, lo, hi, h, step):
-                # coordinates of global indices [lo-h, hi+h): grid values inside, a[0]-k*step / a[-1]+k*step outside
+            def extend(a, lo, hi, h, step, h_hi=None):
+                # coordinates of global indices [lo-h, hi+h_hi): grid values inside, a[0]-k*step / a[-1]+k*step outside
                 n = a.numel()
-                gi = torch.arange(lo - h, hi + h, device=dev)
+                gi = torch.arange(lo - h, hi + (h if h_hi is None else h_hi), device=dev)
                 inside = a[gi.clamp(0, n - 1)]
                 st32 = torch.tensor(step, dtype=torch.float32, device=dev)
                 below = a[0] - (-gi).clamp(min=0).to(torch.float32) * st32
@@ -395,7 +397,10 @@ class SharedPlan:
 
             self.xe = extend(xs, xa, xb, self.HX, dx)
             self.ye = extend(ys, 0, Ny, self.HY, dy)
-            self.ze = extend(zs, 0, Nz, self.HZ, dz)
+            # the z halo is widened on the high side until a lattice row is a whole number of 16-byte groups: rows
+            # start 16-byte aligned (float4 stencil kernels on any grid) and the lattice arrays are legal TMA tensors
+            self.hz_hi = self.HZ + (-(Nz + 2 * self.HZ)) % 4
+            self.ze = extend(zs, 0, Nz, self.HZ, dz, self.hz_hi)
             ex, ey, ez = self.xe.numel(), self.ye.numel(), self.ze.numel()
             self.dims = (ex, ey, ez)
             ne = ex * ey * ez
@@ -415,9 +420,9 @@ class SharedPlan:
 
             # ---- K2c row assembly into lattice layout
             use_nl = (nonlinear_m.kind != NL_NONE) or (nonlinear_p.kind != NL_NONE)
-            can_faces = (ey % 2 == 0) and (ez % 2 == 0)
+            can_faces = (ez % 4 == 0)
             if faces and not can_faces:
-                raise ValueError("faces=True needs even Ny and Nz (16-byte aligned lattice rows)")
+                raise ValueError("faces=True needs 16-byte aligned lattice rows")
             self.faces = can_faces if faces is None else bool(faces)
             self.w = None if self.faces else torch.zeros(7 * ne, dtype=torch.float32, device=dev)
             self.cface = torch.zeros(3 * ne, dtype=torch.float32, device=dev) if self.faces else None
@@ -595,6 +600,12 @@ class SharedPlan:
                 s.ge_ptr, s.ge_ent = cabi.ptr(self.ge_ptr), cabi.ptr(self.ge_ent)
                 s.list_nodes, s.n_list = cabi.ptr(self.list_nodes), self.n_list
                 s.g_ptr, s.g_ent = cabi.ptr(self.g_ptr), cabi.ptr(self.g_ent)
+            # dense stencil stage: one TMA-fed kernel for residual rows + adjoint (default) or the two separate kernels
+            self.stencil_tma = (os.environ.get("NBM_STENCIL_TMA", "1") != "0") if stencil_tma is None else bool(stencil_tma)
+            s.stencil_tma = 0 if self.stencil_tma else -1
+            # (mirrors the library's own test, nbm_step.cu launch_shared)
+            self.stencil_tma_active = bool(self.stencil_tma and self.faces and precond is None and not self.fused
+                                           and ez % 4 == 0 and not (use_nl and self.g_ptr is not None))
             if precond is not None:
                 s.coef26 = cabi.ptr(self.coef26)
                 s.pc_d1, s.pc_d2, s.pc_scale = precond.widths[0], precond.widths[1], precond.scale
@@ -602,7 +613,7 @@ class SharedPlan:
                 # uncrossed row nodes per side: they take the per-side preconditioner kernels (6 inputs instead of 26)
                 assert ne < 2 ** 31
                 fl = torch.zeros((ex, ey, ez), dtype=torch.int8, device=dev)
-                pv = (slice(self.HX, ex - self.HX), slice(self.HY, ey - self.HY), slice(self.HZ, ez - self.HZ))
+                pv = (slice(self.HX, ex - self.HX), slice(self.HY, ey - self.HY), slice(self.HZ, ez - self.hz_hi))
                 fl[pv] = cs.flag.view(ex, ey, ez)[pv]
                 fl = fl.reshape(-1)
                 self.pc_nodes_m = torch.nonzero(fl < 0).reshape(-1).to(torch.int32).contiguous()
@@ -658,7 +669,7 @@ class SharedPlan:
     def point_view(self, t: torch.Tensor) -> torch.Tensor:
         """lattice-layout array -> (n_points,) in the reference's point order"""
         ex, ey, ez = self.dims
-        return t.view(ex, ey, ez)[self.HX:ex - self.HX, self.HY:ey - self.HY, self.HZ:ez - self.HZ].reshape(-1)
+        return t.view(ex, ey, ez)[self.HX:ex - self.HX, self.HY:ey - self.HY, self.HZ:ez - self.hz_hi].reshape(-1)
 
 
 def upload_params(net: NetShape, params: torch.Tensor) -> None:

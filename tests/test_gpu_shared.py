@@ -32,13 +32,14 @@ def fns_of(problem):
                              problem.nonlinear_op_m, problem.nonlinear_op_p)
 
 
-def build(problem, n_train, n_lvl, interp="trilinear", net=None, xa=0, xb=None, faces=None, fused=None):
+def build(problem, n_train, n_lvl, interp="trilinear", net=None, xa=0, xb=None, faces=None, fused=None, stencil_tma=None):
     tr, lv, phi_grid, oprob = util.make_case(problem, n_train, n_lvl, interp, torch.float64, net=net)
     lvl = nplan.LevelSet(lv, phi_grid, interp=interp, perturb_eps=1e-10, device=DEV)
     shape = nplan.NetShape(oprob.shape.Lp, oprob.shape.Hp, oprob.shape.Lm, oprob.shape.Hm)
     pl = nplan.SharedPlan(lvl, tr, xa, xb if xb is not None else tr.shape()[0], fns_of(problem), shape,
                           nplan.Nonlinear.coerce(problem.nonlinear_op_m),
-                          nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=DEV, faces=faces, fused=fused)
+                          nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=DEV, faces=faces, fused=fused,
+                          stencil_tma=stencil_tma)
     return tr, lv, lvl, oprob, pl, shape
 
 
@@ -249,7 +250,7 @@ def test_learned_preconditioner(name, faces):
     Pc = O.precond_eval(params[shape.n_params:], oprob.precond, parts["coeffs"])
     assert float(Pc.max() - Pc.min()) > 1e-2, "the test must exercise a varying preconditioner"
     # the 26 inputs the kernels hand to the preconditioner
-    c26 = pl.coef26.view(26, *pl.dims)[:, pl.HX:-pl.HX, pl.HY:-pl.HY, pl.HZ:-pl.HZ].reshape(26, -1).T.cpu()
+    c26 = pl.coef26.view(26, *pl.dims)[:, pl.HX:-pl.HX, pl.HY:-pl.HY, pl.HZ:-pl.hz_hi].reshape(26, -1).T.cpu()
     assert util.rel_inf(c26, parts["coeffs"]) < TOL_FRAC
     p_dev = params.float().to(DEV)
     with torch.cuda.device(DEV):
@@ -265,3 +266,38 @@ def test_learned_preconditioner(name, faces):
     r_o = (lhs_o - rhs_o) / Pc
     got = pl.point_view(pl.R).cpu()
     assert util.rel_inf(got, Pc * Pc * r_o) < 10 * TOL_ROW
+
+
+# The TMA-fed kernel computes residual rows and adjoint stencil in one pass (T stays in shared memory); its arithmetic
+# order is that of the two separate kernels, so R and the dense part of G must be BITWISE equal; with the list kernels
+# (fp32 atomics) the whole [grad, loss] agrees to the last bits.  Slabs (xa, xb) exercise the x halo planes, odd sizes the
+# padded lattice rows, tiny/large grids the tile chooser, sphere_reaction the kv table and the nonlinear terms.
+@pytest.mark.parametrize("name,n,nl,xa,xb", [
+    ("sphere", 16, 32, 0, None), ("star", 32, 32, 0, None), ("star", 15, 32, 0, None), ("sphere", 24, 24, 5, 17),
+    ("sphere_reaction", 16, 32, 0, None), ("sphere_reaction", 20, 32, 3, 12), ("sphere", 64, 64, 0, None),
+    ("sphere", 6, 16, 0, None)])
+def test_stencil_tma_is_bitwise_the_two_stencil_kernels(name, n, nl, xa, xb):
+    P = problems.PROBLEMS[name]()
+    tr, lv, lvl, oprob, pa, shape = build(P, n, nl, xa=xa, xb=xb, faces=True, stencil_tma=True)
+    _, _, _, _, pb, _ = build(P, n, nl, xa=xa, xb=xb, faces=True, stencil_tma=False)
+    assert pa.stencil_tma_active and not pb.stencil_tma_active
+    params = O.init_params(oprob.shape, seed=11, dtype=torch.float64).float().to(DEV)
+    with torch.cuda.device(DEV):
+        nplan.upload_params(shape, params)
+        for pl in (pa, pb):
+            pl.G.fill_(float("nan"))     # every node of G must be written by the dense stage
+            pl.step.stages = 1 | 2 | 4 | 8 | 64   # forward, extrapolation, dense residual + adjoint, no list kernels
+            pl.loss_grad_launch()
+            pl.step.stages = 0
+        torch.cuda.synchronize()
+        assert torch.equal(pa.U, pb.U)
+        assert torch.equal(pa.R, pb.R)
+        assert not torch.isnan(pa.G).any()
+        assert torch.equal(pa.G, pb.G)
+        la = pa.loss_grad_launch().clone()
+        lb = pb.loss_grad_launch().clone()
+        la2 = pa.loss_grad_launch().clone()      # repeated launches (ring/barrier state starts clean every time)
+        torch.cuda.synchronize()
+    assert util.rel_inf(la.cpu(), lb.cpu()) < 2e-6, util.rel_inf(la.cpu(), lb.cpu())
+    assert util.rel_inf(la2.cpu(), la.cpu()) < 2e-6
+    assert abs(float(la[-1]) - float(lb[-1])) <= 1e-6 * abs(float(lb[-1]))
