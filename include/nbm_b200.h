@@ -294,6 +294,12 @@ typedef struct {
      * two stages and the deterministic list gathers are not combined with a nonlinear operator), -1 = always the two
      * separate kernels. */
     int stencil_tma;
+    /* Activation stash (optional, NULL = recompute): ceil(hidden_p / 4) planes of ex*ey*ez 16-byte chunks
+     * (48 bytes per node for hidden_p = 10), 16-byte aligned.  The forward kernel writes the last hidden layer of
+     * every plus-side node there; the gradient kernel reads it back (cp.async ring in shared memory) instead of
+     * recomputing that layer (for the default 3-10-10-1 head: 100 of the 140 forward FMAs and half of the tanh
+     * evaluations of its forward part). */
+    float* Hst;
 } nbm_shared_step_t;
 
 /* number of preconditioner parameters for hidden widths (d1, d2) */

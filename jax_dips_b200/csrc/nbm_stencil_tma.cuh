@@ -19,11 +19,12 @@
 
 namespace stencil_tma {
 
-constexpr int kMain = 256;                   // one float4 group of the tile per thread
-constexpr int kHalo = 96;                    // the T halo: 2 gzq groups (rows -1, gy) + 2 gy single cells (columns -1, 4 gzq)
-constexpr int kConsumers = kMain + kHalo;
-constexpr int kThreadsS = kConsumers + 32;   // + the producer warp
-constexpr int kTRing = 4;
+// CTA = n_main threads (one float4 group of the tile each) + n_halo threads (the T halo: 2 gzq groups of rows -1, gy
+// and 2 gy single cells of columns -1, 4 gzq) + the producer warp.  Two sizes: 256 + 96 (one CTA per SM) and
+// 128 + 64 (two CTAs per SM: twice as many independent warps to hide the shared-memory and barrier latency).
+constexpr int kMainMax = 256, kHaloMax = 96;
+constexpr int kThreadsS = kMainMax + kHaloMax + 32;
+constexpr int kTRing = 2;
 
 struct Geom {
     int ex, ey, ez;
@@ -33,6 +34,8 @@ struct Geom {
     int bw, bh;           // box: bh = gy + 4 rows of bw = 4 gzq + 8 floats
     int slot_floats;      // bh * bw rounded up to 128 bytes
     int nsu, nst;         // ring depths: U planes, table planes
+    int n_main, n_halo;   // thread roles (multiples of 32)
+    int dbg;              // timing experiments: 1 = consumers skip the arithmetic (fill rate of the TMA pipeline alone)
 };
 
 struct Maps {
@@ -54,7 +57,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
-__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+__device__ __forceinline__ void bar_consumers(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
 // one row value; same expression order as NBM_ROW of residual_faces4_body
@@ -67,6 +70,26 @@ __device__ __forceinline__ float row_val(float di, float rh, float dsum, float u
     return di > 0.f ? fmaf(di, acc, -rh) : (di < 0.f ? u0 - rh : 0.f);
 }
 
+// explicit shared-window accesses (32-bit addresses): the compiler cannot prove that pointers derived from the aligned
+// dynamic-shared base are shared, and generic LD/ST cost address arithmetic and long-scoreboard stalls
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void mbar_init_a(uint32_t a, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+
 template <bool KV, bool NL>
 __global__ void __launch_bounds__(kThreadsS, 1)
 stencil_tma_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Geom g, nbm_shared_step_t s) {
@@ -74,16 +97,15 @@ stencil_tma_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Ge
     constexpr int NT = n_tables<KV, NL>();
     // table order inside a table-ring slot
     constexpr int T_CX = 0, T_CY = 1, T_CZ = 2, T_DI = 3, T_RH = 4, T_KV = 5, T_NA = 5 + (KV ? 1 : 0), T_NB = T_NA + 1;
-    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base);   // fullU[nsu] emptyU[nsu] fullT[nst] emptyT[nst]  (<= 16 barriers)
-    float* ringU = reinterpret_cast<float*>(base + 128);
-    float* ringT = ringU + (size_t)g.nsu * g.slot_floats;
-    float* Ts = ringT + (size_t)g.nst * NT * g.slot_floats;
-    const int nsu = g.nsu, nst = g.nst;
-    const uint32_t bars_a = smem_u32(bars);
-    const uint32_t fullU = bars_a, emptyU = bars_a + 8u * nsu, fullT = bars_a + 16u * nsu, emptyT = bars_a + 16u * nsu + 8u * nst;
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t nsu = (uint32_t)g.nsu, nst = (uint32_t)g.nst;
+    const uint32_t slot_b = (uint32_t)g.slot_floats * 4u;
+    // barriers: fullU[nsu] emptyU[nsu] fullT[nst] emptyT[nst]  (<= 16)
+    const uint32_t fullU = base, emptyU = base + 8u * nsu, fullT = base + 16u * nsu, emptyT = fullT + 8u * nst;
+    const uint32_t ringU = base + 128u, ringT = ringU + nsu * slot_b, Ts = ringT + nst * NT * slot_b;
 
     const int tid = threadIdx.x;
+    const int kMain = g.n_main, kConsumers = g.n_main + g.n_halo;
     const int nt = g.ny_t * g.nz_t;
     const int tile = blockIdx.x % nt, chunk = blockIdx.x / nt;
     const int ty_i = tile / g.nz_t, tz_i = tile - ty_i * g.nz_t;
@@ -91,16 +113,17 @@ stencil_tma_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Ge
     const int xa = chunk * g.xchunk, xb = min(g.ex, xa + g.xchunk);
     const int n_iter = xb - xa + 2;           // p = xa-1 .. xb
     const int bw = g.bw;
+    const uint32_t bw4 = (uint32_t)bw * 4u;
     const uint32_t box_bytes = (uint32_t)(g.bh * bw * sizeof(float));
 
     if (tid == 0) {
-        for (int i = 0; i < nsu; ++i) {
-            mbar_init(bars + i, 1);
-            mbar_init(bars + nsu + i, kConsumers / 32);
+        for (uint32_t i = 0; i < nsu; ++i) {
+            mbar_init_a(fullU + 8u * i, 1);
+            mbar_init_a(emptyU + 8u * i, kConsumers / 32);
         }
-        for (int i = 0; i < nst; ++i) {
-            mbar_init(bars + 2 * nsu + i, 1);
-            mbar_init(bars + 2 * nsu + nst + i, kConsumers / 32);
+        for (uint32_t i = 0; i < nst; ++i) {
+            mbar_init_a(fullT + 8u * i, 1);
+            mbar_init_a(emptyT + 8u * i, kConsumers / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -110,36 +133,36 @@ stencil_tma_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Ge
         // ---------------- producer warp: one lane issues the TMA boxes ----------------
         if (tid == kConsumers) {
             const int cz0 = z0 - 4, cy0 = y0 - 2;
-            const uint32_t ringU_a = smem_u32(ringU), ringT_a = smem_u32(ringT);
-            const uint32_t slot_b = (uint32_t)g.slot_floats * 4u;
-            auto load_u = [&](int j) {   // U plane xa - 2 + j
-                const int st = j % nsu;
-                if (j >= nsu) mbar_wait_a(emptyU + 8u * st, ((j / nsu) + 1u) & 1u);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullU + 8u * st), "r"(box_bytes) : "memory");
-                tma_load_3d(ringU_a + st * slot_b, &maps.U, cz0, cy0, xa - 2 + j, fullU + 8u * st);
+            uint32_t iu = 0, ku = 0, it = 0, kt = 0;      // ring slot, wrap parity
+            bool wrapped_u = false, wrapped_t = false;
+            auto load_u = [&](int px) {
+                if (wrapped_u) mbar_wait_a(emptyU + 8u * iu, ku ^ 1u);   // every consumer warp released the previous use
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullU + 8u * iu), "r"(box_bytes) : "memory");
+                tma_load_3d(ringU + iu * slot_b, &maps.U, cz0, cy0, px, fullU + 8u * iu);
+                if (++iu == nsu) { iu = 0; ku ^= 1u; wrapped_u = true; }
             };
-            auto load_t = [&](int n) {   // tables of plane xa - 1 + n
-                const int st = n % nst;
-                if (n >= nst) mbar_wait_a(emptyT + 8u * st, ((n / nst) + 1u) & 1u);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fullT + 8u * st), "r"(box_bytes * NT) : "memory");
-                const uint32_t d = ringT_a + (uint32_t)st * NT * slot_b;
-                const int px = xa - 1 + n;
-                tma_load_3d(d + T_CX * slot_b, &maps.cx, cz0, cy0, px, fullT + 8u * st);
-                tma_load_3d(d + T_CY * slot_b, &maps.cy, cz0, cy0, px, fullT + 8u * st);
-                tma_load_3d(d + T_CZ * slot_b, &maps.cz, cz0, cy0, px, fullT + 8u * st);
-                tma_load_3d(d + T_DI * slot_b, &maps.dinv, cz0, cy0, px, fullT + 8u * st);
-                tma_load_3d(d + T_RH * slot_b, &maps.rhs, cz0, cy0, px, fullT + 8u * st);
-                if (KV) tma_load_3d(d + T_KV * slot_b, &maps.kv, cz0, cy0, px, fullT + 8u * st);
+            auto load_t = [&](int px) {
+                if (wrapped_t) mbar_wait_a(emptyT + 8u * it, kt ^ 1u);
+                const uint32_t bar = fullT + 8u * it;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(box_bytes * NT) : "memory");
+                const uint32_t d = ringT + it * NT * slot_b;
+                tma_load_3d(d + T_CX * slot_b, &maps.cx, cz0, cy0, px, bar);
+                tma_load_3d(d + T_CY * slot_b, &maps.cy, cz0, cy0, px, bar);
+                tma_load_3d(d + T_CZ * slot_b, &maps.cz, cz0, cy0, px, bar);
+                tma_load_3d(d + T_DI * slot_b, &maps.dinv, cz0, cy0, px, bar);
+                tma_load_3d(d + T_RH * slot_b, &maps.rhs, cz0, cy0, px, bar);
+                if (KV) tma_load_3d(d + T_KV * slot_b, &maps.kv, cz0, cy0, px, bar);
                 if (NL) {
-                    tma_load_3d(d + T_NA * slot_b, &maps.nla, cz0, cy0, px, fullT + 8u * st);
-                    tma_load_3d(d + T_NB * slot_b, &maps.nlb, cz0, cy0, px, fullT + 8u * st);
+                    tma_load_3d(d + T_NA * slot_b, &maps.nla, cz0, cy0, px, bar);
+                    tma_load_3d(d + T_NB * slot_b, &maps.nlb, cz0, cy0, px, bar);
                 }
+                if (++it == nst) { it = 0; kt ^= 1u; wrapped_t = true; }
             };
-            load_u(0);
-            load_u(1);
+            load_u(xa - 2);
+            load_u(xa - 1);
             for (int n = 0; n < n_iter; ++n) {
-                load_u(n + 2);
-                load_t(n);
+                load_u(xa + n);          // U[p+1]
+                load_t(xa - 1 + n);      // tables of plane p
             }
         }
         return;
@@ -148,23 +171,27 @@ stencil_tma_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Ge
     // ---------------- consumers ----------------
     // role: main thread = group (r, gq) of the tile; halo thread = a group of row -1 / gy, or one cell of column -1 / 4 gzq
     const bool is_main = tid < kMain;
-    int r, cz;            // tile row (-1 .. gy) and box column of the (first) cell
+    const int lane = tid & 31;
+    int r, gq, cz;        // tile row (-1 .. gy), group in the row, box column of the (first) cell
     bool active, vec;
     if (is_main) {
         r = tid / g.gzq;
-        cz = 4 + 4 * (tid - r * g.gzq);
+        gq = tid - r * g.gzq;
+        cz = 4 + 4 * gq;
         active = tid < g.gy * g.gzq;
         vec = true;
     } else {
         const int h = tid - kMain;
         if (h < 2 * g.gzq) {
             r = h < g.gzq ? -1 : g.gy;
-            cz = 4 + 4 * (h % g.gzq);
+            gq = h < g.gzq ? h : h - g.gzq;
+            cz = 4 + 4 * gq;
             active = true;
             vec = true;
         } else {
             const int h2 = h - 2 * g.gzq;
-            r = h2 % g.gy;
+            r = h2 < g.gy ? h2 : h2 - g.gy;
+            gq = 0;
             cz = h2 < g.gy ? 3 : 4 + 4 * g.gzq;
             active = h2 < 2 * g.gy;
             vec = false;
@@ -172,121 +199,144 @@ stencil_tma_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Ge
     }
     if (!active) {   // idle threads of a small tile: harmless addresses, no stores
         r = 0;
+        gq = 0;
         cz = 4;
     }
-    const int ry = r + 2;                         // box row
+    // z neighbours inside a row come from the adjacent lane (shuffle); the ends of a row / of the warp read shared memory
+    const unsigned vmask = __ballot_sync(0xffffffffu, vec);
+    const bool left_lane = vec && gq > 0 && lane > 0, right_lane = vec && gq < g.gzq - 1 && lane < 31;
     const int yy = y0 + r, zz = z0 + cz - 4;      // lattice coordinates of the (first) cell
     const bool in_lat = active && yy >= 0 && yy < g.ey && zz >= 0 && zz < g.ez;
     const bool stores = is_main && in_lat;
     const int64_t plane = (int64_t)g.ey * g.ez;
-    const int64_t ne = plane * g.ex;
     const int64_t e_yz = (int64_t)yy * g.ez + zz;
-    const int so = ry * bw + cz;                  // offset of the (first) cell inside a box
-    const int to = (r + 1) * bw + cz;             // ... inside a T plane
-    const int tplane = (g.gy + 2) * bw;
+    const uint32_t so4 = (uint32_t)((r + 2) * bw + cz) * 4u;   // byte offset of the (first) cell inside a box
+    const uint32_t to4 = (uint32_t)((r + 1) * bw + cz) * 4u;   // ... inside a T plane
+    const uint32_t tplane_b = (uint32_t)(g.gy + 2) * bw4;
+    // iterations whose residual plane this CTA writes: xa <= p < xb and 1 <= p <= ex-2
+    const int n_r_lo = max(xa, 1) - (xa - 1), n_r_hi = min(xb, g.ex - 1) - (xa - 1);
+    float* pR = s.R + (int64_t)(xa - 1) * plane + e_yz;       // plane p of this thread's cells (running)
+    float* pG = s.G + (int64_t)(xa - 2) * plane + e_yz;       // plane p - 1
 
-    // carried per-cell coefficients (plane p-1 while plane p is being computed)
-    float4 k_cxm = make_float4(0.f, 0.f, 0.f, 0.f), k_cxp = k_cxm, k_cym = k_cxm, k_cyp = k_cxm, k_czp = k_cxm, k_acc = k_cxm,
-           k_gnl = k_cxm;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // carried per-cell state: coefficients of plane p-1 (for G[p-1]), own U of planes p-1, p, own T of planes p-2, p-1
+    float4 k_cxm = z4, k_cxp = z4, k_cym = z4, k_cyp = z4, k_czp = z4, k_acc = z4, k_gnl = z4, k_r0 = z4;
     float k_czl = 0.f;
-    float4 cxm = make_float4(0.f, 0.f, 0.f, 0.f);   // -x face coefficients of the plane about to be computed
+    float4 t_m2 = z4, t_m1 = z4;
+    float4 cxm = z4;   // -x face coefficients of the plane about to be computed
     if (in_lat && xa - 2 >= 0) {
         const float* q = s.cface + (int64_t)(xa - 2) * plane + e_yz;
         if (vec) cxm = ld4(q); else cxm.x = __ldg(q);
     }
 
-    // the first two U planes
-    mbar_wait_a(fullU + 0u, 0u);
-    mbar_wait_a(fullU + 8u * (1 % nsu), (uint32_t)(1 / nsu) & 1u);
+    // the first two U planes (slots 0, 1): own cells only
+    mbar_wait_a(fullU, 0u);
+    mbar_wait_a(fullU + 8u, 0u);
+    float4 u_m1, u_0;
+    if (vec) {
+        u_m1 = lds128(ringU + so4);
+        u_0 = lds128(ringU + slot_b + so4);
+    } else {
+        u_m1 = z4; u_0 = z4;
+        u_m1.x = lds32(ringU + so4);
+        u_0.x = lds32(ringU + slot_b + so4);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a(emptyU);
+    uint32_t i1 = 1, i2 = 2, ph2 = 0, it = 0, pht = 0, tw = 0;   // slots: U[p], U[p+1] (+ parity), tables (+ parity), T[p]
 
+#pragma unroll 2
     for (int n = 0; n < n_iter; ++n) {
-        const int p = xa - 1 + n;
-        const int su0 = n % nsu, su1 = (n + 1) % nsu, su2 = (n + 2) % nsu, stb = n % nst;
-        mbar_wait_a(fullU + 8u * su2, (uint32_t)((n + 2) / nsu) & 1u);
-        mbar_wait_a(fullT + 8u * stb, (uint32_t)(n / nst) & 1u);
-        const float* U0 = ringU + (size_t)su0 * g.slot_floats + so;
-        const float* U1 = ringU + (size_t)su1 * g.slot_floats + so;
-        const float* U2 = ringU + (size_t)su2 * g.slot_floats + so;
-        const float* tb = ringT + (size_t)stb * NT * g.slot_floats + so;
-        float* Tw = Ts + (size_t)(n % kTRing) * tplane + to;
-        float4 n_cxp, n_cym, n_cyp, n_czp, n_acc, n_gnl = make_float4(0.f, 0.f, 0.f, 0.f);
-        float n_czl;
-        if (vec) {
-            const float4 di = lds4(tb + T_DI * g.slot_floats), rh = lds4(tb + T_RH * g.slot_floats);
-            n_cxp = lds4(tb + T_CX * g.slot_floats);
-            n_cyp = lds4(tb + T_CY * g.slot_floats);
-            n_cym = lds4(tb + T_CY * g.slot_floats - bw);
-            n_czp = lds4(tb + T_CZ * g.slot_floats);
-            n_czl = tb[T_CZ * g.slot_floats - 1];
+        mbar_wait_a(fullU + 8u * i2, ph2);
+        mbar_wait_a(fullT + 8u * it, pht);
+        const uint32_t aC = ringU + i2 * slot_b + so4;      // U[p+1], own cells
+        const uint32_t aN = ringU + i1 * slot_b + so4;      // U[p]: y / z neighbours
+        const uint32_t aT = ringT + it * (NT * slot_b) + so4;
+        const uint32_t aTw = Ts + tw * tplane_b + to4;      // T[p] (written), T[p-1] in the other slot
+        const uint32_t aTr = Ts + (tw ^ 1u) * tplane_b + to4;
+        float4 n_cxp = z4, n_cym = z4, n_cyp = z4, n_czp = z4, n_acc = z4, n_gnl = z4, n_r0 = z4, u_p1 = z4, t_0 = z4;
+        float n_czl = 0.f;
+        const bool do_g = is_main && n >= 2 && !(g.dbg & 1);
+        if (g.dbg & 1) {
+        } else if (vec) {
+            u_p1 = lds128(aC);
+            const float4 uym = lds128(aN - bw4), uyp = lds128(aN + bw4);
+            const float4 di = lds128(aT + T_DI * slot_b), rh = lds128(aT + T_RH * slot_b);
+            n_cxp = lds128(aT + T_CX * slot_b);
+            n_cyp = lds128(aT + T_CY * slot_b);
+            n_cym = lds128(aT + T_CY * slot_b - bw4);
+            n_czp = lds128(aT + T_CZ * slot_b);
+            float4 kv = z4;
+            if (KV) kv = lds128(aT + T_KV * slot_b);
+            float4 nla = z4, nlb = z4;
+            if (NL) {
+                nla = lds128(aT + T_NA * slot_b);
+                nlb = lds128(aT + T_NB * slot_b);
+            }
+            float ul = __shfl_up_sync(vmask, u_0.w, 1), ur = __shfl_down_sync(vmask, u_0.x, 1);
+            n_czl = __shfl_up_sync(vmask, n_czp.w, 1);
+            if (!left_lane) {
+                ul = lds32(aN - 4u);
+                n_czl = lds32(aT + T_CZ * slot_b - 4u);
+            }
+            if (!right_lane) ur = lds32(aN + 16u);
             const float4 czm = make_float4(n_czl, n_czp.x, n_czp.y, n_czp.z);
-            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (KV) kv = lds4(tb + T_KV * g.slot_floats);
-            const float4 u0 = lds4(U1), uxm = lds4(U0), uxp = lds4(U2), uym = lds4(U1 - bw), uyp = lds4(U1 + bw);
-            const float ul = U1[-1], ur = U1[4];
-            const float4 uzm = make_float4(ul, u0.x, u0.y, u0.z), uzp = make_float4(u0.y, u0.z, u0.w, ur);
+            const float4 uzm = make_float4(ul, u_0.x, u_0.y, u_0.z), uzp = make_float4(u_0.y, u_0.z, u_0.w, ur);
             float4 rr, dsum;
 #define NBM_ST_ROW(c)                                                                                                \
     dsum.c = (((((cxm.c + n_cxp.c) + n_cym.c) + n_cyp.c) + czm.c) + n_czp.c) + kv.c;                                   \
-    rr.c = row_val(di.c, rh.c, dsum.c, u0.c, cxm.c, uxm.c, n_cxp.c, uxp.c, n_cym.c, uym.c, n_cyp.c, uyp.c, czm.c, uzm.c, \
-                   n_czp.c, uzp.c);
+    rr.c = row_val(di.c, rh.c, dsum.c, u_0.c, cxm.c, u_m1.c, n_cxp.c, u_p1.c, n_cym.c, uym.c, n_cyp.c, uyp.c, czm.c,   \
+                   uzm.c, n_czp.c, uzp.c);
             NBM_ST_ROW(x) NBM_ST_ROW(y) NBM_ST_ROW(z) NBM_ST_ROW(w)
 #undef NBM_ST_ROW
             if (NL) {
-                const float4 a = lds4(tb + T_NA * g.slot_floats), b = lds4(tb + T_NB * g.slot_floats);
+                const float4 a = nla, b = nlb;
 #define NBM_ST_NL(c)                                                                                                 \
-    if (di.c != 0.f) rr.c += a.c * nl_apply(s.nonlinear_m, s.nl_coef_m, u0.c) + b.c * nl_apply(s.nonlinear_p, s.nl_coef_p, u0.c); \
-    n_gnl.c = (a.c * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.c) + b.c * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.c)) * rr.c;
+    if (di.c != 0.f) rr.c += a.c * nl_apply(s.nonlinear_m, s.nl_coef_m, u_0.c) + b.c * nl_apply(s.nonlinear_p, s.nl_coef_p, u_0.c); \
+    n_gnl.c = nl_dfac(s, a.c, b.c, u_0.c);
                 NBM_ST_NL(x) NBM_ST_NL(y) NBM_ST_NL(z) NBM_ST_NL(w)
 #undef NBM_ST_NL
             }
-            const float4 t0 = tval4(di, rr);
-            if (active) *reinterpret_cast<float4*>(Tw) = t0;
-            n_acc = make_float4(di.x > 0.f ? dsum.x * t0.x : (di.x < 0.f ? rr.x : 0.f),
-                                di.y > 0.f ? dsum.y * t0.y : (di.y < 0.f ? rr.y : 0.f),
-                                di.z > 0.f ? dsum.z * t0.z : (di.z < 0.f ? rr.z : 0.f),
-                                di.w > 0.f ? dsum.w * t0.w : (di.w < 0.f ? rr.w : 0.f));
-            if (stores && p >= xa && p < xb && p >= 1 && p <= g.ex - 2)
-                *reinterpret_cast<float4*>(s.R + (int64_t)p * plane + e_yz) = rr;
+            t_0 = tval4(di, rr);
+            n_r0 = rr;
+            if (active) sts128(aTw, t_0);
+            n_acc = make_float4(di.x > 0.f ? dsum.x * t_0.x : (di.x < 0.f ? rr.x : 0.f),
+                                di.y > 0.f ? dsum.y * t_0.y : (di.y < 0.f ? rr.y : 0.f),
+                                di.z > 0.f ? dsum.z * t_0.z : (di.z < 0.f ? rr.z : 0.f),
+                                di.w > 0.f ? dsum.w * t_0.w : (di.w < 0.f ? rr.w : 0.f));
+            if (stores && n >= n_r_lo && n < n_r_hi) *reinterpret_cast<float4*>(pR) = rr;
         } else {
             // one cell of a z halo column: only T is needed
-            const float di = tb[T_DI * g.slot_floats], rh = tb[T_RH * g.slot_floats];
-            const float cxp = tb[T_CX * g.slot_floats], cyp = tb[T_CY * g.slot_floats], cym = tb[T_CY * g.slot_floats - bw];
-            const float czp = tb[T_CZ * g.slot_floats], czm = tb[T_CZ * g.slot_floats - 1];
-            const float kv = KV ? tb[T_KV * g.slot_floats] : 0.f;
-            const float u0 = U1[0];
+            u_p1.x = lds32(aC);
+            const float di = lds32(aT + T_DI * slot_b), rh = lds32(aT + T_RH * slot_b);
+            const float cxp = lds32(aT + T_CX * slot_b), cyp = lds32(aT + T_CY * slot_b), cym = lds32(aT + T_CY * slot_b - bw4);
+            const float czp = lds32(aT + T_CZ * slot_b), czm = lds32(aT + T_CZ * slot_b - 4u);
+            const float kv = KV ? lds32(aT + T_KV * slot_b) : 0.f;
             const float dsum = (((((cxm.x + cxp) + cym) + cyp) + czm) + czp) + kv;
-            float rr = row_val(di, rh, dsum, u0, cxm.x, U0[0], cxp, U2[0], cym, U1[-bw], cyp, U1[bw], czm, U1[-1], czp, U1[1]);
+            float rr = row_val(di, rh, dsum, u_0.x, cxm.x, u_m1.x, cxp, u_p1.x, cym, lds32(aN - bw4), cyp, lds32(aN + bw4), czm,
+                               lds32(aN - 4u), czp, lds32(aN + 4u));
             if (NL) {
                 if (di != 0.f)
-                    rr += tb[T_NA * g.slot_floats] * nl_apply(s.nonlinear_m, s.nl_coef_m, u0) +
-                          tb[T_NB * g.slot_floats] * nl_apply(s.nonlinear_p, s.nl_coef_p, u0);
+                    rr += lds32(aT + T_NA * slot_b) * nl_apply(s.nonlinear_m, s.nl_coef_m, u_0.x) +
+                          lds32(aT + T_NB * slot_b) * nl_apply(s.nonlinear_p, s.nl_coef_p, u_0.x);
             }
-            if (active) *Tw = tval(di, rr);
+            if (active) sts32(aTw, tval(di, rr));
             n_cxp = make_float4(cxp, 0.f, 0.f, 0.f);
-            n_cym = n_cyp = n_czp = n_acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            n_czl = 0.f;
         }
-        // tables of plane p and U[p-1] are consumed
-        __syncwarp();
-        if ((tid & 31) == 0) {
-            mbar_arrive_a(emptyT + 8u * stb);
-            mbar_arrive_a(emptyU + 8u * su0);
-        }
-        bar_consumers();   // T[p] complete
-        // G[p-1] on the tile
-        if (is_main && n >= 2) {
-            const float* Tb = Ts + (size_t)((n - 1) % kTRing) * tplane + to;
-            const float* Ta = Ts + (size_t)((n - 2) % kTRing) * tplane + to;
-            const float* Tc = Ts + (size_t)(n % kTRing) * tplane + to;
-            const float4 t0 = lds4(Tb), txm = lds4(Ta), txp = lds4(Tc), tym = lds4(Tb - bw), typ = lds4(Tb + bw);
-            const float tl = Tb[-1], tr = Tb[4];
-            const float4 tzm = make_float4(tl, t0.x, t0.y, t0.z), tzp = make_float4(t0.y, t0.z, t0.w, tr);
+        // G[p-1] on the tile: own T of planes p-2, p-1, p from registers, the y / z neighbours of T[p-1] from shared memory
+        // (written before the previous iteration's barrier), coefficients of plane p-1 carried from the previous iteration
+        if (do_g) {
+            const float4 tym = lds128(aTr - bw4), typ = lds128(aTr + bw4);
+            float tl = __shfl_up_sync(0xffffffffu, t_m1.w, 1), tr = __shfl_down_sync(0xffffffffu, t_m1.x, 1);
+            if (!left_lane) tl = lds32(aTr - 4u);
+            if (!right_lane) tr = lds32(aTr + 16u);
+            const float4 tzm = make_float4(tl, t_m1.x, t_m1.y, t_m1.z), tzp = make_float4(t_m1.y, t_m1.z, t_m1.w, tr);
             const float4 czm = make_float4(k_czl, k_czp.x, k_czp.y, k_czp.z);
             float4 gg;
 #define NBM_ST_ADJ(c)                                                                                                \
     {                                                                                                                \
         float acc = k_acc.c;                                                                                         \
-        acc = fmaf(-k_cxm.c, txm.c, acc); acc = fmaf(-k_cxp.c, txp.c, acc);                                          \
+        acc = fmaf(-k_cxm.c, t_m2.c, acc); acc = fmaf(-k_cxp.c, t_0.c, acc);                                         \
         acc = fmaf(-k_cym.c, tym.c, acc); acc = fmaf(-k_cyp.c, typ.c, acc);                                          \
         acc = fmaf(-czm.c, tzm.c, acc); acc = fmaf(-k_czp.c, tzp.c, acc);                                            \
         gg.c = acc;                                                                                                  \
@@ -294,14 +344,29 @@ stencil_tma_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Ge
             NBM_ST_ADJ(x) NBM_ST_ADJ(y) NBM_ST_ADJ(z) NBM_ST_ADJ(w)
 #undef NBM_ST_ADJ
             if (NL) {
-                gg.x += k_gnl.x; gg.y += k_gnl.y; gg.z += k_gnl.z; gg.w += k_gnl.w;
+                gg.x = fmaf(k_gnl.x, k_r0.x, gg.x); gg.y = fmaf(k_gnl.y, k_r0.y, gg.y);
+                gg.z = fmaf(k_gnl.z, k_r0.z, gg.z); gg.w = fmaf(k_gnl.w, k_r0.w, gg.w);
             }
-            if (stores) *reinterpret_cast<float4*>(s.G + (int64_t)(p - 1) * plane + e_yz) = gg;
+            if (stores) *reinterpret_cast<float4*>(pG) = gg;
         }
-        k_cxm = cxm; k_cxp = n_cxp; k_cym = n_cym; k_cyp = n_cyp; k_czp = n_czp; k_czl = n_czl; k_acc = n_acc; k_gnl = n_gnl;
+        // the tables of plane p and the neighbour plane U[p] are consumed; T[p] is complete after the barrier
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive_a(emptyT + 8u * it);
+            mbar_arrive_a(emptyU + 8u * i1);
+        }
+        bar_consumers(kConsumers);
+        k_cxm = cxm; k_cxp = n_cxp; k_cym = n_cym; k_cyp = n_cyp; k_czp = n_czp; k_czl = n_czl; k_acc = n_acc; k_gnl = n_gnl; k_r0 = n_r0;
         cxm = n_cxp;
+        t_m2 = t_m1; t_m1 = t_0;
+        u_m1 = u_0; u_0 = u_p1;
+        i1 = i2;
+        if (++i2 == nsu) { i2 = 0; ph2 ^= 1u; }
+        if (++it == nst) { it = 0; pht ^= 1u; }
+        tw ^= 1u;
+        pR += plane;
+        pG += plane;
     }
-    (void)ne;
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------
@@ -340,12 +405,17 @@ static Geom choose_geom(int ex, int ey, int ez, int sms, int n_tab, size_t smem_
     const int ez4 = ez / 4;
     auto env_i = [](const char* k) { const char* v = getenv(k); return v ? atoi(v) : 0; };
     const int f_gy = env_i("NBM_ST_GY"), f_gzq = env_i("NBM_ST_GZQ"), f_nxc = env_i("NBM_ST_NXC"), f_pf = env_i("NBM_ST_PF");
+    const int f_main = env_i("NBM_ST_MAIN"), f_dbg = env_i("NBM_ST_DBG");
+    for (int n_main = 128; n_main <= kMainMax; n_main += 128)
     for (int gzq = 4; gzq <= 44; ++gzq) {
         if (f_gzq && gzq != f_gzq) continue;
+        if (f_main && n_main != f_main) continue;
         for (int gy = 2; gy <= 44; ++gy) {
             if (f_gy && gy != f_gy) continue;
-            if (gy * gzq > kMain || 2 * (gy + gzq) > kHalo) continue;
+            const int n_halo = n_main == 256 ? kHaloMax : 64;
+            if (gy * gzq > n_main || 2 * (gy + gzq) > n_halo || gy * gzq <= n_main / 2) continue;
             Geom g{};
+            g.n_main = n_main; g.n_halo = n_halo; g.dbg = f_dbg;
             g.ex = ex; g.ey = ey; g.ez = ez; g.gy = gy; g.gzq = gzq;
             g.bw = 4 * gzq + 8; g.bh = gy + 4;
             if (g.bw > 256 || g.bh > 256) continue;
@@ -355,7 +425,7 @@ static Geom choose_geom(int ex, int ey, int ez, int sms, int n_tab, size_t smem_
             // deepest prefetch that fits (at least one plane ahead)
             int pf = f_pf ? f_pf : 3;
             for (; pf >= 1; --pf) {
-                g.nsu = 3 + pf; g.nst = 1 + pf;
+                g.nsu = 2 + pf; g.nst = 1 + pf;
                 const size_t b = 256 + 4 * ((size_t)g.slot_floats * (g.nsu + (size_t)g.nst * n_tab) + (size_t)kTRing * (gy + 2) * g.bw);
                 if (b <= smem_limit && 2 * (g.nsu + g.nst) <= 16) break;
             }
@@ -365,10 +435,17 @@ static Geom choose_geom(int ex, int ey, int ez, int sms, int n_tab, size_t smem_
                 const int xchunk = (ex + nxc - 1) / nxc;
                 if ((nxc - 1) * xchunk >= ex) continue;   // an empty last chunk
                 const int64_t nb = (int64_t)nt * nxc;
-                const int64_t waves = (nb + sms - 1) / sms;
+                // CTAs per SM: shared memory, and 128 registers per thread of a 64 K file
+                const size_t smem_cta = 256 + 4 * ((size_t)g.slot_floats * (g.nsu + (size_t)g.nst * n_tab) + (size_t)kTRing * (gy + 2) * g.bw);
+                const int per_sm = (int)fmin(fmin((double)(smem_limit / (smem_cta + 1024)), 512.0 / (n_main + n_halo + 32)), 2.0);
+                if (per_sm < 1) continue;
+                const int64_t waves = (nb + (int64_t)sms * per_sm - 1) / ((int64_t)sms * per_sm);
                 // per plane and CTA: box traffic through L2 (~48 B/clk/SM) against a ~500-clock compute + barrier floor
                 const double t_plane = fmax((double)g.bh * g.bw * 4.0 * (n_tab + 1) / 48.0, 500.0) * (pf >= 2 ? 1.0 : 1.15);
-                const double cost = (double)waves * (xchunk + 3) * t_plane;
+                const double cost = (double)waves * (xchunk + 3) * t_plane * (per_sm == 2 ? 1.6 : 1.0);
+                if (getenv("NBM_ST_VERBOSE"))
+                    fprintf(stderr, "stencil_tma cand: main %d gy %d gzq %d nxc %d pf %d per_sm %d waves %d cost %.0f\n", n_main, gy,
+                            gzq, nxc, pf, per_sm, (int)waves, cost);
                 if (cost < best_cost) {
                     best_cost = cost;
                     best = g;
@@ -407,6 +484,10 @@ static int launch_t(const nbm_shared_step_t& s, int sms, cudaStream_t st) {
             set_error("stencil_tma: no tile shape fits");
             return NBM_ERR_UNSUPPORTED;
         }
+        if (getenv("NBM_ST_DEBUG"))
+            fprintf(stderr, "stencil_tma: lattice %dx%dx%d main %d halo %d tile %dx%d tiles %dx%d nxc %d xchunk %d nsu %d nst %d smem %zu\n",
+                    s.ex, s.ey, s.ez, g.n_main, g.n_halo, g.gy, g.gzq, g.ny_t, g.nz_t, g.nxc, g.xchunk, g.nsu, g.nst,
+                    smem_bytes<KV, NL>(g));
         Maps& m = cache.maps;
         bool ok = encode(&m.U, s.U, g) && encode(&m.cx, s.cface, g) && encode(&m.cy, s.cface + ne, g) &&
                   encode(&m.cz, s.cface + 2 * ne, g) && encode(&m.dinv, s.dinv, g) && encode(&m.rhs, s.rhs, g);
@@ -426,11 +507,13 @@ static int launch_t(const nbm_shared_step_t& s, int sms, cudaStream_t st) {
         int smem_max = 0;
         cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         cudaError_t e = cudaFuncSetAttribute(stencil_tma_kernel<KV, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(stencil_tma_kernel<KV, NL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return cuda_check(e, "stencil_tma attribute");
         configured |= 1ull << (dev & 63);
     }
     const int grid = g.ny_t * g.nz_t * g.nxc;
-    stencil_tma_kernel<KV, NL><<<grid, kThreadsS, smem_bytes<KV, NL>(g), st>>>(cache.maps, g, s);
+    stencil_tma_kernel<KV, NL><<<grid, g.n_main + g.n_halo + 32, smem_bytes<KV, NL>(g), st>>>(cache.maps, g, s);
     return 0;
 }
 

@@ -255,6 +255,18 @@ struct MlpP {
         return lo32(o2) + hi32(o2);
     }
 
+    // Activation stash: the last hidden layer of every plus-side node, written by the forward kernel as HPQ planes of
+    // 16-byte chunks (two feature pairs each; a warp writes 512 contiguous bytes per plane) and read back by the
+    // gradient kernel, which then recomputes only the layers below it.
+    static constexpr int HPQ = (HP + 1) / 2;
+    __device__ __forceinline__ static void stash_store(float4* __restrict__ hp, int64_t hstride, const u64 (&a)[HP]) {
+#pragma unroll
+        for (int q = 0; q < HPQ; ++q) {
+            const u64 lo = a[2 * q], hi = (2 * q + 1 < HP) ? a[2 * q + 1] : 0ull;
+            __stcs(hp + q * hstride, make_float4(lo32(lo), hi32(lo), lo32(hi), hi32(hi)));
+        }
+    }
+
     // forward of NB nodes that share (y, z): every constant-bank pair is fetched once and used NB times, and the
     // NB dependency chains interleave (more ILP for the ex2/rcp latency)
     // the part of the first layer that does not depend on x: b1 + y W1[1] + z W1[2] (pre-scaled); a thread that
@@ -269,7 +281,9 @@ struct MlpP {
     }
 
     template <int OFF, int NB>
-    __device__ __forceinline__ static void forward_many(const float (&x)[NB], const u64 (&yz)[HP], float (&out)[NB]) {
+    __device__ __forceinline__ static void forward_many(const float (&x)[NB], const u64 (&yz)[HP], float (&out)[NB],
+                                                        float4* __restrict__ hp = nullptr, int64_t hstride = 0,
+                                                        int64_t hnode = 0) {
         constexpr int S = NBM_MAXP + OFF;
         u64 a[NB][HP], b[NB][HP];
 #pragma unroll
@@ -309,6 +323,7 @@ struct MlpP {
 #pragma unroll
             for (int j = 0; j < HP; ++j) o2 = ffma2(a[n][j], cpair(oo + 2 * j), o2);
             out[n] = lo32(o2) + hi32(o2);
+            if (hp) stash_store(hp + n * hnode, hstride, a[n]);   // node n of the batch sits hnode chunks further
         }
     }
 
@@ -408,14 +423,23 @@ struct MlpP {
 
     // forward recompute (first layer from the hoisted yz part) + backward with g = d loss / d u(node).
     // Must be called by all 32 lanes (g = 0 for lanes that have nothing to add).
-    __device__ __forceinline__ static void grad_split(float x, const u64 (&yz)[HP], float g, AccS& A, bool par) {
+    // STASH: the last hidden layer `aLast` comes from the forward kernel's stash instead of being recomputed.
+    template <bool STASH = false>
+    __device__ __forceinline__ static void grad_split(float x, const u64 (&yz)[HP], float g, AccS& A, bool par,
+                                                      const u64* aLast = nullptr) {
         constexpr int S = NBM_MAXP;
         u64 a[L][HP];
         const u64 x2 = pk(x, x);
+        if (STASH) {
 #pragma unroll
-        for (int j = 0; j < HP; ++j) a[0][j] = tanh2_prescaled_4mufu(ffma2(x2, cpair(S + 2 * j), yz[j]));
+            for (int j = 0; j < HP; ++j) a[L - 1][j] = aLast[j];
+        }
+        if (!STASH || L > 1) {
 #pragma unroll
-        for (int l = 1; l < L; ++l) {
+            for (int j = 0; j < HP; ++j) a[0][j] = tanh2_prescaled_4mufu(ffma2(x2, cpair(S + 2 * j), yz[j]));
+        }
+#pragma unroll
+        for (int l = 1; l < (STASH ? L - 1 : L); ++l) {
             const int o = S + 4 * H + (l - 1) * (H * H + H);
             u64 acc[HP];
 #pragma unroll
@@ -546,18 +570,30 @@ struct Net {
     __device__ __forceinline__ static void first_layer_yz(float y, float z, u64 (&yz)[HP / 2]) {
         P::template first_layer_yz<0>(y, z, yz);
     }
+    // `hp`: stash of node 0's last hidden layer (node 1 sits `hnode` 16-byte chunks further), null = not kept
     __device__ __forceinline__ static void eval2(bool plus0, bool plus1, float x0, float x1, float y, float z,
-                                                 const u64 (&yz)[HP / 2], float& u0, float& u1) {
+                                                 const u64 (&yz)[HP / 2], float& u0, float& u1, float4* hp = nullptr,
+                                                 int64_t hstride = 0, int64_t hnode = 0) {
         if (plus0 && plus1) {
             const float xs[2] = {x0, x1};
             float out[2];
-            P::template forward_many<0, 2>(xs, yz, out);
+            P::template forward_many<0, 2>(xs, yz, out, hp, hstride, hnode);
             u0 = out[0];
             u1 = out[1];
         } else {
-            u0 = eval(plus0, x0, y, z);
-            u1 = eval(plus1, x1, y, z);
+            u0 = eval_stash(plus0, x0, y, z, hp, hstride);
+            u1 = eval_stash(plus1, x1, y, z, hp ? hp + hnode : nullptr, hstride);
         }
+    }
+    __device__ __forceinline__ static float eval_stash(bool plus, float x, float y, float z, float4* hp, int64_t hstride) {
+        if (plus) {
+            u64 a[LP][HP / 2];
+            const float u = P::template forward<0>(x, y, z, a);
+            if (hp) P::stash_store(hp, hstride, a[LP - 1]);
+            return u;
+        }
+        float a[LM][HM];
+        return M::template forward<P::NP>(x, y, z, a);
     }
     __device__ __forceinline__ static void grad(bool plus, float x, float y, float z, float g, Acc& acc) {
         if (plus) {
@@ -610,6 +646,7 @@ struct NodeView {
     float* U;
     const float* G;
     const float* R;              // may be null (no loss accumulation)
+    float4* Hst;                 // activation stash [HPQ][rep_nodes] 16-byte chunks, or null (recompute)
     float inv_n;
     float* partials;
     int row0;
@@ -624,6 +661,7 @@ static NodeView view_of(const nbm_shared_step_t& s) {
     v.lo = 0; v.hi = (int64_t)s.ex * s.ey * s.ez;
     v.rep_nodes = v.hi;
     v.side = s.side; v.U = s.U; v.G = s.G; v.R = s.R;
+    v.Hst = reinterpret_cast<float4*>(s.Hst);
     v.inv_n = s.inv_n_points; v.partials = s.partials; v.row0 = 0;
     v.row_stride = 0; v.loss_col = 0;
     return v;
@@ -660,10 +698,11 @@ __device__ __forceinline__ void fwd_task(const NodeView& v, const int plane, con
             }
         }
         float ua, ub;
+        float4* hst = (!GENERAL && v.Hst) ? v.Hst + e_cur : nullptr;
         if (has_b) {
-            NET::eval2(pa, pb, xa, xb, y, z, yz, ua, ub);
+            NET::eval2(pa, pb, xa, xb, y, z, yz, ua, ub, hst, v.rep_nodes, plane);
         } else {
-            ua = NET::eval(pa, xa, y, z);
+            ua = NET::eval_stash(pa, xa, y, z, hst, v.rep_nodes);
             ub = 0.0f;
         }
         if (!GENERAL || (e_cur >= v.lo && e_cur < v.hi)) U[e_cur] = ua;
@@ -672,7 +711,7 @@ __device__ __forceinline__ void fwd_task(const NodeView& v, const int plane, con
 }
 
 template <class NET, bool GENERAL>
-__global__ void __launch_bounds__(kThreads, 3) fwd_nodes_kernel(NodeView v, Tasks T) {
+__global__ void __launch_bounds__(kThreads) fwd_nodes_kernel(NodeView v, Tasks T) {
     const int rep = blockIdx.y;
     const float* xe = v.xe + (size_t)rep * v.ex;
     const float* ye = v.ye + (size_t)rep * v.ey;
@@ -926,6 +965,12 @@ __device__ __forceinline__ Faces4 load_faces4(const nbm_shared_step_t& s, int64_
 }
 #define NBM_DIAG(F, c) ((((((F).cxm.c + (F).cxp.c) + (F).cym.c) + (F).cyp.c) + (F).czm.c) + (F).czp.c)
 
+// d/du of the nonlinear part of a row: a N_m'(u) + b N_p'(u), in one fixed operation order (shared by the adjoint
+// kernels so that their results agree bitwise)
+__device__ __forceinline__ float nl_dfac(const nbm_shared_step_t& s, float a, float b, float u0) {
+    return fmaf(a, nl_deriv(s.nonlinear_m, s.nl_coef_m, u0), __fmul_rn(b, nl_deriv(s.nonlinear_p, s.nl_coef_p, u0)));
+}
+
 // rows of the 4 consecutive cells m..m+3 of plane ix (1 <= ix <= ex-2)
 __device__ __forceinline__ void residual_faces4_body(const nbm_shared_step_t& s, const int plane, const int m, const int ix) {
     const int64_t sx = plane, sy = s.ez;
@@ -1005,10 +1050,10 @@ __device__ __forceinline__ void adjoint_faces4_body(const nbm_shared_step_t& s, 
 #undef NBM_ADJ
     if (s.nl) {
         float4 u0 = ld4(s.U + e), a = ld4(s.nl + e), b = ld4(s.nl + ne + e);
-        g.x += (a.x * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.x) + b.x * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.x)) * r0.x;
-        g.y += (a.y * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.y) + b.y * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.y)) * r0.y;
-        g.z += (a.z * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.z) + b.z * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.z)) * r0.z;
-        g.w += (a.w * nl_deriv(s.nonlinear_m, s.nl_coef_m, u0.w) + b.w * nl_deriv(s.nonlinear_p, s.nl_coef_p, u0.w)) * r0.w;
+        g.x = fmaf(nl_dfac(s, a.x, b.x, u0.x), r0.x, g.x);
+        g.y = fmaf(nl_dfac(s, a.y, b.y, u0.y), r0.y, g.y);
+        g.z = fmaf(nl_dfac(s, a.z, b.z, u0.z), r0.z, g.z);
+        g.w = fmaf(nl_dfac(s, a.w, b.w, u0.w), r0.w, g.w);
     }
     *reinterpret_cast<float4*>(s.G + e) = g;
 }
@@ -1147,12 +1192,14 @@ __device__ __forceinline__ void block_reduce_store(typename NET::Acc& acc, float
 // the bias of the first layer live in shared memory and are touched once per task.
 constexpr int kGradThreads = 384;
 
+constexpr int kStashStages = 3;   // cp.async ring of the activation stash: nodes ix, ix+1, ix+2
 template <class NET>
-constexpr int grad_smem_bytes() {
-    return (3 * NET::HPW * kGradThreads + (kGradThreads / 32) * (NET::NP + 1)) * (int)sizeof(float);
+constexpr int grad_smem_bytes(bool stash = false) {
+    return (3 * NET::HPW * kGradThreads + (kGradThreads / 32) * (NET::NP + 1)) * (int)sizeof(float) +
+           (stash ? kStashStages * NET::P::HPQ * kGradThreads * 16 + 16 : 0);
 }
 
-template <class NET, bool GENERAL>
+template <class NET, bool GENERAL, bool STASH = false>
 __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, Tasks T) {
     using P = typename NET::P;
     using M = typename NET::M;
@@ -1160,6 +1207,12 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
     extern __shared__ __align__(16) float dsm[];
     float* hs = dsm + threadIdx.x;                      // [3H] hoisted sums of this thread, stride kGradThreads
     float* red = dsm + 3 * H * kGradThreads;            // [warps][NP + 1]
+    // activation stash ring: [stage][thread][HPQ] 16-byte chunks filled by this thread's own cp.async copies, two nodes
+    // ahead of the compute (no register is held by a load in flight, DRAM latency is off the critical path)
+    constexpr int HPQ = P::HPQ;
+    const uint32_t hsm_a = STASH ? (((uint32_t)__cvta_generic_to_shared(red + (kGradThreads / 32) * (NP + 1)) + 15u) & ~15u) +
+                                       16u * HPQ * threadIdx.x : 0u;
+    constexpr uint32_t kStageB = HPQ * kGradThreads * 16u;
 #pragma unroll
     for (int i = 0; i < 3 * H; ++i) hs[i * kGradThreads] = 0.0f;
     typename P::AccS acc;
@@ -1196,6 +1249,24 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
         bool in_n = valid && (!GENERAL || (e >= v.lo && e < v.hi));
         float g_n = in_n ? __ldg(gp) : 0.0f, r_n = (rp && valid) ? __ldg(rp) : 0.0f, x_n = __ldg(xp);
         uint8_t sd_n = __ldg(sp);
+        const float4* hnext = STASH ? v.Hst + e : nullptr;   // next node to prefetch from the stash
+        uint32_t st_w = 0, st_r = 0;                      // ring stage written next / read next
+        auto stash_prefetch = [&]() {
+            int64_t hs16 = v.rep_nodes;
+            asm volatile("" : "+l"(hs16));    // opaque: one running pointer + stride instead of HPQ hoisted pointers
+#pragma unroll
+            for (int q = 0; q < HPQ; ++q)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hsm_a + st_w * kStageB + 16u * q),
+                             "l"(hnext + q * hs16) : "memory");
+            hnext += T.plane;
+            st_w = st_w + 1 == kStashStages ? 0u : st_w + 1;
+        };
+        if (STASH) {
+            stash_prefetch();
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (x0 + 1 < x1) stash_prefetch();
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         for (int ix = x0; ix < x1; ++ix) {
             const float g = g_n * v.inv_n, r = r_n, x = x_n;
             const bool plus = (sd_n & 1) != 0;
@@ -1217,7 +1288,22 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
             }
             loss = fmaf(0.5f * r, r, loss);
             const bool do_p = plus && g != 0.0f;
-            if (__any_sync(0xffffffffu, do_p)) P::grad_split(x, yz, do_p ? g : 0.0f, acc, par);
+            u64 aLast[HP2];
+            if (STASH) {
+                if (ix + 2 < x1) stash_prefetch();
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 2;" ::: "memory");     // this node's copies have landed
+#pragma unroll
+                for (int q = 0; q < HPQ; ++q) {
+                    float4 c;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w)
+                                 : "r"(hsm_a + st_r * kStageB + 16u * q));
+                    aLast[2 * q] = pk(c.x, c.y);
+                    if (2 * q + 1 < HP2) aLast[2 * q + 1] = pk(c.z, c.w);
+                }
+                st_r = st_r + 1 == kStashStages ? 0u : st_r + 1;
+            }
+            if (__any_sync(0xffffffffu, do_p)) P::template grad_split<STASH>(x, yz, do_p ? g : 0.0f, acc, par, aLast);
             if (!plus && g != 0.0f) {
                 float a[NET::LMD][NET::HMW];
                 M::template forward<P::NP>(x, y, z, a);
@@ -1259,18 +1345,18 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
     }
 }
 
-template <class NET, bool GENERAL>
+template <class NET, bool GENERAL, bool STASH = false>
 static cudaError_t launch_node_grad(dim3 grid, const NodeView& v, const Tasks& T, cudaStream_t st) {
     static unsigned long long configured = 0ull;   // per instantiation AND per device (one process may drive several)
-    constexpr int bytes = grad_smem_bytes<NET>();
+    constexpr int bytes = grad_smem_bytes<NET>(STASH);
     int dev = 0;
     cudaGetDevice(&dev);
     if (!((configured >> (dev & 63)) & 1ull)) {
-        cudaError_t e = cudaFuncSetAttribute(node_grad_kernel<NET, GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        cudaError_t e = cudaFuncSetAttribute(node_grad_kernel<NET, GENERAL, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         configured |= 1ull << (dev & 63);
     }
-    node_grad_kernel<NET, GENERAL><<<grid, kGradThreads, bytes, st>>>(v, T);
+    node_grad_kernel<NET, GENERAL, STASH><<<grid, kGradThreads, bytes, st>>>(v, T);
     return cudaSuccess;
 }
 
@@ -2414,7 +2500,10 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
             nv.row_stride = pc_stride;
             nv.loss_col = NET::NP + n_pc;
         }
-        cudaError_t e = launch_node_grad<NET, false>(dim3(gridC), nv, Tg, st);
+        // (a call without the forward stage reads the stash of the last forward, as it reads that forward's U)
+        const bool stash = nv.Hst != nullptr;
+        cudaError_t e = stash ? launch_node_grad<NET, false, true>(dim3(gridC), nv, Tg, st)
+                              : launch_node_grad<NET, false, false>(dim3(gridC), nv, Tg, st);
         if (e != cudaSuccess) return cuda_check(e, "node_grad attribute");
     }
     if (stages & NBM_STAGE_REDUCE)

@@ -360,7 +360,7 @@ class SharedPlan:
     def __init__(self, lvl: LevelSet, tr_gstate, xa: int, xb: int, fns, net: NetShape,
                  nonlinear_m: Nonlinear, nonlinear_p: Nonlinear, n_mean: Optional[int] = None, device=None,
                  faces: Optional[bool] = None, fused: Optional[bool] = None, precond: Optional[PrecondShape] = None,
-                 deterministic: bool = False, stencil_tma: Optional[bool] = None):
+                 deterministic: bool = False, stencil_tma: Optional[bool] = None, stash: Optional[bool] = None):
         """`faces`: store one coefficient per cell FACE + 1/diag (16 B/node) instead of the 7 row weights
         (28 B/node); irregular rows move into the list.  Default: on (lattice rows are padded to 16-byte multiples).
         `fused`: evaluate the dense adjoint stencil inside the gradient kernel from TMA-staged row tables
@@ -369,6 +369,10 @@ class SharedPlan:
         shared ring couples the 12 warps of a CTA to the slowest one).
         `stencil_tma`: residual rows and adjoint stencil of the faces table as ONE kernel whose x planes arrive as 3-D
         TMA boxes (halo included) in a shared-memory ring (`csrc/nbm_stencil_tma.cuh`).  Default: on where it applies.
+        `stash`: keep the last hidden layer of every plus-side node from the forward kernel (48 bytes per lattice node
+        for hidden_p = 10) so that the gradient kernel does not recompute it.  Default OFF: measured on B200 at 256^3
+        the gradient kernel gains 21 us (343 -> 323) but the forward kernel loses 38 us to the 830 MB of stores
+        (172 -> 210); see DESIGN.md.
         `deterministic`: gather the adjoint of the lists (irregular rows, extrapolation) through their transposed
         incidence instead of scattering it with fp32 atomics: the whole step becomes bitwise reproducible, for
         ~5 us more per step at 256^3 (the atomics are faster than the doubly indirect gathers)."""
@@ -600,6 +604,10 @@ class SharedPlan:
                 s.ge_ptr, s.ge_ent = cabi.ptr(self.ge_ptr), cabi.ptr(self.ge_ent)
                 s.list_nodes, s.n_list = cabi.ptr(self.list_nodes), self.n_list
                 s.g_ptr, s.g_ent = cabi.ptr(self.g_ptr), cabi.ptr(self.g_ent)
+            # activation stash of the forward kernel
+            self.stash = (os.environ.get("NBM_STASH", "0") != "0") if stash is None else bool(stash)
+            self.Hst = torch.zeros(4 * ((net.hidden_p // 2 + 1) // 2) * ne, dtype=torch.float32, device=dev) if self.stash else None
+            s.Hst = cabi.ptr(self.Hst)
             # dense stencil stage: one TMA-fed kernel for residual rows + adjoint (default) or the two separate kernels
             self.stencil_tma = (os.environ.get("NBM_STENCIL_TMA", "1") != "0") if stencil_tma is None else bool(stencil_tma)
             s.stencil_tma = 0 if self.stencil_tma else -1

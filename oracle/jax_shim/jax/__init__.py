@@ -12,10 +12,12 @@ from . import numpy  # noqa: F401
 from . import lax  # noqa: F401
 from . import tree_util  # noqa: F401
 from . import lib  # noqa: F401
+from . import nn  # noqa: F401
 from ._src.api import vmap, jit, grad, value_and_grad, pmap  # noqa: F401
 from .numpy import config  # noqa: F401
 
 tree_map = tree_util.tree_map
+Array = numpy.ndarray     # annotation only (nn/preconditioner.py:23)
 
 
 def local_device_count():

@@ -29,14 +29,14 @@ jax, jnp = mg.jax, mg.jnp
 EPS = 1e-5
 
 
-def reference_loss_fn(problem, n_tr, n_lvl, interp, point_idx, zoom):
+def reference_loss_fn(problem, n_tr, n_lvl, interp, point_idx, zoom, precond=False):
     """loss(flat params) through the reference's Discretization (x64 mode), cf. make_golden.run_case"""
     dtype = np.float64
     jax.config.update("jax_enable_x64", True)
     lo, hi = problem.box
     init_mesh_fn, _ = mg.mesh.construct(3)
     ax = lambda n, a: jnp.linspace(lo[a], hi[a], n, dtype=jnp.float32)
-    tr = init_mesh_fn(ax(n_tr, 0), ax(n_tr, 1), ax(n_tr, 2))
+    tr_d = [ax(n_tr, a)[1] - ax(n_tr, a)[0] for a in range(3)]
     lv = init_mesh_fn(ax(n_lvl, 0), ax(n_lvl, 1), ax(n_lvl, 2))
     phi_grid = mg.tnp.vmap(problem.phi_fn)(torch.from_numpy(np.asarray(lv.R, dtype=np.float32))).numpy()
     if interp == "trilinear":
@@ -49,16 +49,20 @@ def reference_loss_fn(problem, n_tr, n_lvl, interp, point_idx, zoom):
                                b(problem.mu_p_fn), b(problem.k_m_fn), b(problem.k_p_fn), b(problem.f_m_fn),
                                b(problem.f_p_fn), b(problem.alpha_fn), b(problem.beta_fn),
                                mg.nonlinear_callable(problem.nonlinear_op_m), mg.nonlinear_callable(problem.nonlinear_op_p))
-    D = mg.Hooked(lv, None, fns, precondition=1, algorithm=0)
+    D = (mg.HookedPrecond if precond else mg.Hooked)(lv, None, fns, precondition=1, algorithm=0)
+    if precond:
+        D.set_precond(*mg.PRECOND)
     shape = mg.O.NetShape()
-    d = [dtype(np.float32(v) * np.float32(0.5 ** zoom)) for v in (tr.dx, tr.dy, tr.dz)]
-    pts = np.asarray(tr.R)[point_idx].astype(dtype)
+    d = [dtype(np.float32(v) * np.float32(0.5 ** zoom)) for v in tr_d]
+    pts = mg.grid_points(lo, hi, n_tr, point_idx).astype(dtype)
 
     def loss(flat):
-        D.set_net(jnp.Arr(np.asarray(flat, dtype=dtype)), shape)
+        flat = np.asarray(flat, dtype=dtype)
+        D.set_net(jnp.Arr(flat[:shape.n_params]), shape)
+        tree = {"preconditioner": mg.precond_tree(flat[shape.n_params:], mg.PRECOND[0])} if precond else None
         acc = 0.0
         for p in pts:
-            lr = np.asarray(D.compute_Ax_and_b_fn(None, jnp.Arr(p), *d)).reshape(2)
+            lr = np.asarray(D.compute_Ax_and_b_fn(tree, jnp.Arr(p), *d)).reshape(2)
             acc += 0.5 * (lr[0] - lr[1]) ** 2          # optax.l2_loss (trainer.py:899-901)
         return acc / len(pts)                           # jnp.mean over the batch
 
@@ -68,7 +72,10 @@ def reference_loss_fn(problem, n_tr, n_lvl, interp, point_idx, zoom):
 CASES = [("sphere_tri_z0", "sphere", "trilinear"), ("star_tri_z0", "star", "trilinear"),
          ("sphere_tri_z1", "sphere", "trilinear"),      # zoom level 1: cell size = spacing / 2
          ("sphere_quad_z0", "sphere", "quadratic"),     # non-oscillatory quadratic level-set interpolant
-         ("sphere_reaction_tri_z0", "sphere_reaction", "trilinear")]   # k != 0, N(u) = c sinh(u)
+         ("sphere_reaction_tri_z0", "sphere_reaction", "trilinear"),   # k != 0, N(u) = c sinh(u)
+         ("sphere_precond_tri_z0", "sphere", "trilinear"),             # learned preconditioner: theta = [network | preconditioner]
+         ("stars_tri_z0", "stars", "trilinear"), ("dragon_quad_z0", "dragon_like", "quadratic"),
+         ("pb_tri_z0", "poisson_boltzmann", "trilinear")]
 
 
 def main():
@@ -80,15 +87,21 @@ def main():
         z = np.load(os.path.join(outdir, f"{name}.npz"))
         P = mg.problems.PROBLEMS[pname]()
         idx, n_tr, n_lvl, zoom = z["point_idx"], int(z["n_tr"]), int(z["n_lvl"]), int(z["zoom"])
-        loss, shape = reference_loss_fn(P, n_tr, n_lvl, interp, idx, zoom)
+        precond = "f64_pc_params" in z.files
+        loss, shape = reference_loss_fn(P, n_tr, n_lvl, interp, idx, zoom, precond=precond)
         theta = mg.O.init_params(shape, seed=7, dtype=torch.float64).numpy()
+        if precond:
+            theta = np.concatenate((theta, mg.precond_flat(np.float64)))
         rng = np.random.default_rng(11)
         n = theta.size
         dirs = []
         for _ in range(5):                                  # dense random directions
             v = rng.standard_normal(n)
             dirs.append(v / np.linalg.norm(v))
-        for i in list(rng.choice(shape.n_p, 4, replace=False)) + list(shape.n_p + rng.choice(n - shape.n_p, 2, replace=False)):
+        coords = list(rng.choice(shape.n_p, 4, replace=False)) + list(shape.n_p + rng.choice(shape.n_params - shape.n_p, 2, replace=False))
+        if precond:     # + single coordinates of the preconditioner (first-layer kernel, deeper layers)
+            coords += list(shape.n_params + rng.choice(26 * 8, 3, replace=False)) + list(shape.n_params + 26 * 8 + rng.choice(n - shape.n_params - 26 * 8, 3, replace=False))
+        for i in coords:
             e = np.zeros(n)                                 # single coordinates of both heads
             e[i] = 1.0
             dirs.append(e)

@@ -11,8 +11,8 @@ from test_gpu_shared import DEV, TOL_LOSS, TOL_ROW, build, fns_of
 pytestmark = pytest.mark.gpu
 
 
-def general(problem, n_train, n_lvl, zoom, interp="trilinear", precond=None):
-    tr, lv, phi_grid, oprob = util.make_case(problem, n_train, n_lvl, interp, torch.float64)
+def general(problem, n_train, n_lvl, zoom, interp="trilinear", precond=None, phi_grid=None):
+    tr, lv, phi_grid, oprob = util.make_case(problem, n_train, n_lvl, interp, torch.float64, phi_grid=phi_grid)
     lvl = nplan.LevelSet(lv, phi_grid, interp=interp, perturb_eps=1e-10, device=DEV)
     shape = nplan.NetShape()
     d = [float(v) * 0.5 ** zoom for v in (tr.dx, tr.dy, tr.dz)]
@@ -354,27 +354,29 @@ import numpy as np
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
                 if not os.path.basename(p).startswith("grad_"))
-CASE_PROBLEM = {"sphere_tri_z0": ("sphere", "trilinear"), "sphere_tri_z1": ("sphere", "trilinear"),
-                "star_tri_z0": ("star", "trilinear"), "sphere_quad_z0": ("sphere", "quadratic"),
-                "sphere_reaction_tri_z0": ("sphere_reaction", "trilinear")}
+CASE_PROBLEM = util.GOLDEN_CASES
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_cuda_rows_match_reference_golden(path):
     """CUDA rows and cut-cell fractions at the golden points against what the REFERENCE'S OWN CODE
-    produced for the same inputs (x64 run).  Rows 1e-5; fractions 5e-5 = the reference's own
-    float32-vs-x64 spread (tests/test_oracle_pinning.py::test_reference_noise_floor)."""
+    produced for the same inputs (x64 run).  Rows 1e-5; fractions 1e-4 = the reference's own
+    float32 measure noise (tests/test_oracle_pinning.py::test_reference_noise_floor, TOL_FRAC_REF)."""
     name = os.path.basename(path)[:-4]
     pname, interp = CASE_PROBLEM[name]
     z = np.load(path)
+    if "f64_pc_params" in z.files:
+        pytest.skip("rows scaled by the learned preconditioner are not kept by the kernels (R <- P^2 r); the pinned "
+                    "oracle covers this fixture (test_oracle_pinning) and the kernels are checked against the oracle")
     P = problems.PROBLEMS[pname]()
     zoom, idx = int(z["zoom"]), torch.from_numpy(z["point_idx"]).long()
     params = torch.from_numpy(z["f32_params"]).float()
     gold = torch.from_numpy(z["f64_lhs_rhs"])
     coeffs = torch.from_numpy(z["f64_coeffs"])
     d = z["f64_d"]
+    pg = z["f32_phi_grid"]      # the fixture's own level-set samples
     if zoom == 0:
-        tr, lv, lvl, oprob, pl, shape = build(P, int(z["n_tr"]), int(z["n_lvl"]), interp)
+        tr, lv, lvl, oprob, pl, shape = build(P, int(z["n_tr"]), int(z["n_lvl"]), interp, phi_grid=pg)
         with torch.cuda.device(DEV):
             nplan.upload_params(shape, params.to(DEV))
             pl.loss_grad_launch()
@@ -385,7 +387,7 @@ def test_cuda_rows_match_reference_golden(path):
         cidx = pl.point_view(pl.sites.cidx).cpu()[idx]
         frac = pl.sites.frac.view(-1, 14).cpu()
     else:
-        tr, oprob, level, shape, dd = general(P, int(z["n_tr"]), int(z["n_lvl"]), zoom, interp)
+        tr, oprob, level, shape, dd = general(P, int(z["n_tr"]), int(z["n_lvl"]), zoom, interp, phi_grid=pg)
         pp = nplan.PointsPlan(level, 0, tr.num_points(), keep_rows=True)
         with torch.cuda.device(DEV):
             nplan.upload_params(shape, params.to(DEV))
@@ -398,9 +400,9 @@ def test_cuda_rows_match_reference_golden(path):
         cidx = level.sites.cidx[:n].cpu()[idx]
         frac = level.sites.frac.view(-1, 14).cpu()
     assert torch.equal(flag_k.double(), torch.from_numpy(z["f64_flag"]))
-    assert util.rel_inf(lhs_k, gold[:, 0]) < TOL_ROW
-    assert util.rel_inf(rhs_k, gold[:, 1]) < TOL_ROW
     cr = flag_k == 0
+    util.assert_rows_match(lhs_k, gold[:, 0], cr, TOL_ROW)
+    util.assert_rows_match(rhs_k, gold[:, 1], cr, TOL_ROW)
     if cr.any():
         f = frac[cidx[cr].long()].double()
         vol, area = d.prod(), d[1] * d[2]

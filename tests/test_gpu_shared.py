@@ -32,14 +32,15 @@ def fns_of(problem):
                              problem.nonlinear_op_m, problem.nonlinear_op_p)
 
 
-def build(problem, n_train, n_lvl, interp="trilinear", net=None, xa=0, xb=None, faces=None, fused=None, stencil_tma=None):
-    tr, lv, phi_grid, oprob = util.make_case(problem, n_train, n_lvl, interp, torch.float64, net=net)
+def build(problem, n_train, n_lvl, interp="trilinear", net=None, xa=0, xb=None, faces=None, fused=None, stencil_tma=None,
+          phi_grid=None, stash=None):
+    tr, lv, phi_grid, oprob = util.make_case(problem, n_train, n_lvl, interp, torch.float64, net=net, phi_grid=phi_grid)
     lvl = nplan.LevelSet(lv, phi_grid, interp=interp, perturb_eps=1e-10, device=DEV)
     shape = nplan.NetShape(oprob.shape.Lp, oprob.shape.Hp, oprob.shape.Lm, oprob.shape.Hm)
     pl = nplan.SharedPlan(lvl, tr, xa, xb if xb is not None else tr.shape()[0], fns_of(problem), shape,
                           nplan.Nonlinear.coerce(problem.nonlinear_op_m),
                           nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=DEV, faces=faces, fused=fused,
-                          stencil_tma=stencil_tma)
+                          stencil_tma=stencil_tma, stash=stash)
     return tr, lv, lvl, oprob, pl, shape
 
 
@@ -301,3 +302,25 @@ def test_stencil_tma_is_bitwise_the_two_stencil_kernels(name, n, nl, xa, xb):
     assert util.rel_inf(la.cpu(), lb.cpu()) < 2e-6, util.rel_inf(la.cpu(), lb.cpu())
     assert util.rel_inf(la2.cpu(), la.cpu()) < 2e-6
     assert abs(float(la[-1]) - float(lb[-1])) <= 1e-6 * abs(float(lb[-1]))
+
+
+# The forward kernel keeps the last hidden layer of every plus-side node (activation stash) and the gradient kernel reads
+# it back instead of recomputing it: same [grad, loss] as the recomputing kernel up to the rounding of two tanh variants
+# (shared-reciprocal in the forward kernel, per-element reciprocal in the recompute), for every compiled head shape.
+@pytest.mark.parametrize("name,n,shape_args", [("sphere", 16, None), ("star", 20, None), ("sphere_reaction", 16, None),
+                                               ("sphere", 12, (2, 10, 1, 3)), ("sphere", 12, (1, 10, 1, 1)),
+                                               ("sphere", 12, (3, 10, 1, 1))])
+def test_activation_stash_equals_recompute(name, n, shape_args):
+    P = problems.PROBLEMS[name]()
+    net = O.NetShape(*shape_args) if shape_args else None
+    tr, lv, lvl, oprob, pa, shape = build(P, n, 32, net=net, stash=True)
+    _, _, _, _, pb, _ = build(P, n, 32, net=net, stash=False)
+    assert pa.Hst is not None and pb.Hst is None
+    params = O.init_params(oprob.shape, seed=13, dtype=torch.float64).float().to(DEV)
+    with torch.cuda.device(DEV):
+        nplan.upload_params(shape, params)
+        la = pa.loss_grad_launch().clone()
+        lb = pb.loss_grad_launch().clone()
+        torch.cuda.synchronize()
+        assert float(pa.Hst.abs().max()) > 0 and float(pa.Hst.abs().max()) <= 1.0    # tanh outputs were stored
+    assert util.rel_inf(la.cpu(), lb.cpu()) < 5e-6, util.rel_inf(la.cpu(), lb.cpu())

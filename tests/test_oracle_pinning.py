@@ -18,9 +18,7 @@ from oracle import nbm_oracle as O
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
                 if not os.path.basename(p).startswith("grad_"))
-CASE_PROBLEM = {"sphere_tri_z0": ("sphere", "trilinear"), "sphere_tri_z1": ("sphere", "trilinear"),
-                "star_tri_z0": ("star", "trilinear"), "sphere_quad_z0": ("sphere", "quadratic"),
-                "sphere_reaction_tri_z0": ("sphere_reaction", "trilinear")}
+CASE_PROBLEM = util.GOLDEN_CASES
 
 
 def test_reference_kat_sphere_area_and_volume():
@@ -60,9 +58,11 @@ def test_geometry_invariants():
 # The reference measures cut pieces with sqrt|det(E E^T)| on vertex arrays it casts to float32 EVEN in
 # x64 mode (`jnp.array([...], dtype=f32)`, geometric_integrations_per_point.py:81-89, 148-178): for sliver
 # pieces that Gram form loses half the digits, and the reference's own float32 and x64 runs differ by up to
-# 3.0e-5 of the cell measure (sphere_tri_z0; see test_reference_noise_floor).  Fractions are therefore
-# pinned at 5e-5, everything downstream (rows) at 1e-5.
-TOL_FRAC_REF = 5e-5
+# 3.0e-5 of the cell measure on the ~20-cell fixtures (see test_reference_noise_floor); on the 220-cell fixtures the exact
+# float64 oracle and the reference's x64 run differ by 6.2e-5 (volumes) and the float32 pair by 8.0e-5 (mu A / d).
+# Fractions are therefore pinned at 1e-4; rows of uncrossed cells at 1e-5; rows of crossed cells carry their fractions'
+# noise (rhs = f^- V^- + f^+ V^+ + ...) and are pinned at 1e-4 of the largest crossed-cell row.
+TOL_FRAC_REF = 1e-4
 
 
 def test_reference_noise_floor():
@@ -73,7 +73,7 @@ def test_reference_noise_floor():
         a, b = z["f32_coeffs"].astype(np.float64), z["f64_coeffs"]
         worst = max(worst, np.abs(a[:, 12:14] - b[:, 12:14]).max() / d.prod(),
                     np.abs(a[:, 14:] - b[:, 14:]).max() / (d[1] * d[2]))
-    assert 1e-5 < worst < TOL_FRAC_REF   # the reference does not meet 1e-5 against itself
+    assert 1e-5 < worst < TOL_FRAC_REF, worst   # the reference does not meet 1e-5 against itself
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -88,12 +88,21 @@ def test_oracle_matches_reference_sources(path, tag, dtype, tol):
     pname, interp = CASE_PROBLEM[name]
     z = np.load(path)
     P = problems.PROBLEMS[pname]()
-    tr, lv, phi_grid, op = util.make_case(P, int(z["n_tr"]), int(z["n_lvl"]), interp, dtype)
-    assert np.array_equal(phi_grid.numpy(), z[f"{tag}_phi_grid"])
+    # the level set is the fixture's own sample array (what the reference run interpolated); the problem's analytic
+    # callable must reproduce it up to libm rounding
+    tr, lv, phi_grid, op = util.make_case(P, int(z["n_tr"]), int(z["n_lvl"]), interp, dtype, phi_grid=z[f"{tag}_phi_grid"])
+    if int(z["n_lvl"]) <= 32:
+        regen = util.make_case(P, int(z["n_tr"]), int(z["n_lvl"]), interp, dtype)[2]
+        assert np.allclose(regen.numpy(), z[f"{tag}_phi_grid"], rtol=0, atol=1e-5)
     pts = torch.from_numpy(z[f"{tag}_points"]).to(dtype)
     d = [torch.tensor(float(v), dtype=dtype) for v in z[f"{tag}_d"]]
     params = torch.from_numpy(z[f"{tag}_params"]).to(dtype)
     g = lambda k: torch.from_numpy(z[f"{tag}_{k}"]).to(torch.float64)
+    has_pc = f"{tag}_pc_params" in z.files
+    if has_pc:   # learned preconditioner: flat vector = [network | preconditioner], lpbe.yaml's widths
+        op.precond = O.PrecondShape((8, 4), 1.0)
+        pc = torch.from_numpy(z[f"{tag}_pc_params"]).to(dtype)
+        params = torch.cat((params, pc))
 
     flag = O.is_cell_crossed(pts, *d, op.phi_fn)
     assert torch.equal(flag.double(), g("flag"))
@@ -108,6 +117,11 @@ def test_oracle_matches_reference_sources(path, tag, dtype, tol):
     fin = ~torch.isnan(gb)
     if fin.any() and float(gb[fin].abs().max()) > 0:
         assert util.rel_inf(bg[fin], gb[fin]) < TOL_FRAC_REF
+    if has_pc:
+        # P = 0.5 + s * sigmoid(MLP(coeffs_)) from the reference's own flax module on the reference's own coeffs_
+        Pc = O.precond_eval(pc, op.precond, torch.from_numpy(z[f"{tag}_coeffs"]).to(dtype))
+        assert float(g("precond").max() - g("precond").min()) > 1e-3     # it varies between cells
+        assert util.rel_inf(Pc, g("precond")) < (1e-12 if dtype == torch.float64 else 1e-6)
     um, up = O.u_mp_at_sites(params, pts, *d, op)
     assert util.rel_inf(torch.stack((um, up), 1), g("u_mp")) < tol
     rc = O.regression_coeffs(pts, *d, op)
@@ -117,10 +131,24 @@ def test_oracle_matches_reference_sources(path, tag, dtype, tol):
     ref = g("zeta_gamma")
     crossed = flag == 0     # only crossed sites ever use them (discretization.py:518)
     if crossed.any():
-        assert util.rel_inf(mine[crossed], ref[crossed]) < 1e-3   # pinv in float32: conditioning of X^T W X
+        # float64: measured 1.5e-7 .. 8.4e-7 at h >= 0.03; the oracle evaluates the level-set interpolant in float32
+        # (as the reference's float32 mode does) while the reference's x64 run evaluates it in float64, and the weights
+        # see phi through its central differences over 2h: at the Poisson-Boltzmann spacing (h = 0.02, |phi| ~ 1)
+        # that is 2e-5.  float32: pinv's conditioning of X^T W X
+        tol_zg = (1e-5 if float(d[0]) >= 0.03 else 5e-5) if dtype == torch.float64 else 1e-3
+        assert util.rel_inf(mine[crossed], ref[crossed]) < tol_zg, util.rel_inf(mine[crossed], ref[crossed])
     lhs, rhs = O.compute_Ax_and_b(params, pts, *d, op)
-    assert util.rel_inf(lhs, g("lhs_rhs")[:, 0]) < tol
-    assert util.rel_inf(rhs, g("lhs_rhs")[:, 1]) < tol
+    # all rows against the problem's O(1) scale (Dirichlet rows), as in round 1 ...
+    for k, mine_k in ((0, lhs), (1, rhs)):
+        ref_k = g("lhs_rhs")[:, k]
+        assert float((mine_k.double() - ref_k).abs().max()) < tol * max(float(ref_k.abs().max()), 1.0)
+    # ... and per class against the class's own scale (problems with zero boundary data have no O(1) row)
+    un = ~crossed
+    assert util.rel_inf(lhs[un], g("lhs_rhs")[un, 0]) < tol
+    assert util.rel_inf(rhs[un], g("lhs_rhs")[un, 1]) < tol
+    if crossed.any():
+        assert util.rel_inf(lhs[crossed], g("lhs_rhs")[crossed, 0]) < max(tol, TOL_FRAC_REF)
+        assert util.rel_inf(rhs[crossed], g("lhs_rhs")[crossed, 1]) < max(tol, TOL_FRAC_REF)
 
 
 GRAD_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "grad_*.npz")))
@@ -137,8 +165,11 @@ def test_oracle_loss_and_gradient_match_the_reference_sources(path):
     z = np.load(path)
     dt = torch.float64
     P = problems.PROBLEMS[pname]()
-    tr, lv, phi_grid, op = util.make_case(P, int(z["n_tr"]), int(z["n_lvl"]), interp, dt)
-    pts = tr.R.to(dt)[torch.from_numpy(z["point_idx"]).long()]
+    zr = np.load(os.path.join(os.path.dirname(path), name + ".npz"))
+    tr, lv, phi_grid, op = util.make_case(P, int(z["n_tr"]), int(z["n_lvl"]), interp, dt, phi_grid=zr["f64_phi_grid"])
+    pts = torch.from_numpy(zr["f64_points"]).to(dt)
+    if "f64_pc_params" in zr.files:     # theta = [network | preconditioner]
+        op.precond = O.PrecondShape((8, 4), 1.0)
     f = torch.tensor(0.5 ** int(z["zoom"]), dtype=torch.float32)
     d = [(v * f).to(dt) for v in (tr.dx, tr.dy, tr.dz)]
     params = torch.from_numpy(z["params"]).to(dt)
