@@ -460,8 +460,11 @@ def main():
     # launches per step: constant-bank upload (memcpy node), fwd_nodes, residual, adjoint, node_grad, finalize
     # (+ 2 list kernels each for crossed sites / irregular rows); on several GPUs the peer all-reduce kernel in addition
     dense_launches = 3 if pl.stencil_tma_active else 4      # fwd_nodes, (residual + adjoint | stencil_tma), node_grad
-    launches_per_step = ((2 if world > 1 else 1) + dense_launches + (1 if pl.sites.n > 0 else 0) * 2
-                         + (1 if pl.n_irr > 0 else 0) * 2)
+    if pl.overlap_lists:     # extrap, extrap adjoint | irregular rows fwd + bwd | merge
+        list_launches = (2 if pl.sites.n > 0 else 0) + (1 if pl.n_irr > 0 else 0) + 1
+    else:
+        list_launches = (1 if pl.sites.n > 0 else 0) * 2 + (1 if pl.n_irr > 0 else 0) * 2
+    launches_per_step = (2 if world > 1 else 1) + dense_launches + list_launches
 
     # ---------------- value: device-resident inputs -------------------------------------------
     sampler = ClockSampler(local)          # NVML initialised here, outside the timed window
@@ -616,6 +619,8 @@ def main():
                            "adjoint": ("fused into the gradient kernel (TMA ring)" if pl.fused else
                                        ("residual rows + adjoint stencil in one kernel fed by 3-D TMA boxes (T never leaves the SM)"
                                         if pl.stencil_tma_active else "separate stencil pass")),
+                           "lists": ("side stream beside the TMA stencil, merged into G by one kernel" if pl.overlap_lists
+                                     else "in line after the dense stencil"),
                            "cuda_graph": used_graph,
                            "allreduce": ("peer-memory kernel fused with the partial reduction" if comm is not None
                                          else ("nccl" if world > 1 else "none")),

@@ -300,6 +300,17 @@ typedef struct {
      * recomputing that layer (for the default 3-10-10-1 head: 100 of the 140 forward FMAs and half of the tanh
      * evaluations of its forward part). */
     float* Hst;
+    /* List chain beside the dense stencil (optional; NULL = the list kernels run in line after the dense stencil).
+     * With G2 [ex*ey*ez, zero on first use; the step re-zeroes what it touched], Rq [n_irr] and list_nodes / n_list
+     * (every lattice node that can receive a contribution of the lists: the 27-cube of every crossed site and the 7
+     * stencil sites of every irregular row, ascending; g_ptr must be NULL) the whole step with the TMA stencil runs as
+     *   stream:       fwd_nodes -> stencil_tma ------------------------------> merge_lists -> node_grad
+     *   side stream:           \-> extrap -> irregular rows fwd + bwd -> extrap adjoint -/
+     * The side chain needs only U: it keeps the residuals of the irregular rows in Rq and scatters its part of
+     * d loss/d U into G2 with fp32 atomics; merge_lists then adds G2 into G and stores Rq into R.  The side stream
+     * and its two events are library-owned (one set per device); the fork/join is CUDA-graph capturable, and all
+     * work is ordered after what `stream` held on entry and before what is enqueued on `stream` afterwards. */
+    float* G2; float* Rq;
 } nbm_shared_step_t;
 
 /* number of preconditioner parameters for hidden widths (d1, d2) */

@@ -479,7 +479,9 @@ static int launch_t(const nbm_shared_step_t& s, int sms, cudaStream_t st) {
           cache.dims[2] == s.ez)) {
         int smem_max = 0;
         cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        Geom g = choose_geom(s.ex, s.ey, s.ez, sms, n_tables<KV, NL>(), (size_t)smem_max);
+        // 8 KB of the SM's shared memory stay free: the list kernels of the side stream (no shared memory of their own,
+        // 1 KB system reservation per CTA) must be able to co-reside with a stencil CTA
+        Geom g = choose_geom(s.ex, s.ey, s.ez, sms, n_tables<KV, NL>(), (size_t)smem_max - 8192);
         if (g.gy == 0) {
             set_error("stencil_tma: no tile shape fits");
             return NBM_ERR_UNSUPPORTED;

@@ -12,6 +12,7 @@
 // constant-bank operand (no load, no register).
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include "nbm_common.cuh"
 
 namespace nbm {
@@ -623,7 +624,13 @@ __device__ __forceinline__ float nl_deriv(int kind, float coef, float u) {
 // ---------------------------------------------------------------------------------------------
 struct Tasks {
     int plane, mblocks, xchunk, nxch, total;
+    int split;   // ranges of (strip, x plane) pairs per CTA of the two network kernels (balanced runs), >= 1
 };
+// ranges per CTA: up to 4 (regions of cheap minus-side nodes spread over more CTAs) while a range keeps >= 64 planes
+static int run_split(int64_t plane_iterations, int ctas) {
+    const int64_t per_cta = plane_iterations / (ctas > 0 ? ctas : 1);
+    return (int)(per_cta >= 256 ? 4 : (per_cta >= 128 ? 2 : 1));
+}
 __host__ __device__ inline Tasks make_tasks(int ex, int ey, int ez, int xchunk, int threads = kThreads) {
     Tasks t;
     t.plane = ey * ez;
@@ -631,6 +638,7 @@ __host__ __device__ inline Tasks make_tasks(int ex, int ey, int ez, int xchunk, 
     t.xchunk = xchunk;
     t.nxch = (ex + xchunk - 1) / xchunk;
     t.total = t.mblocks * t.nxch;
+    t.split = 1;
     return t;
 }
 
@@ -669,7 +677,7 @@ static NodeView view_of(const nbm_shared_step_t& s) {
 
 // A: U[e] = u(node e)   (evaluate_solution_fn, trainer.py:836-844)
 // one thread's part of a task: cell `m` of the flattened (y,z) plane, x planes [x0, x1)
-template <class NET, bool GENERAL>
+template <class NET, bool GENERAL, bool STASH>
 __device__ __forceinline__ void fwd_task(const NodeView& v, const int plane, const float* __restrict__ xe,
                                          const float* __restrict__ ye, const float* __restrict__ ze,
                                          const uint8_t* __restrict__ side, float* __restrict__ U, const int m, const int x0,
@@ -698,7 +706,7 @@ __device__ __forceinline__ void fwd_task(const NodeView& v, const int plane, con
             }
         }
         float ua, ub;
-        float4* hst = (!GENERAL && v.Hst) ? v.Hst + e_cur : nullptr;
+        float4* hst = STASH ? v.Hst + e_cur : nullptr;   // compile-time null: the default path carries no stash code
         if (has_b) {
             NET::eval2(pa, pb, xa, xb, y, z, yz, ua, ub, hst, v.rep_nodes, plane);
         } else {
@@ -710,18 +718,29 @@ __device__ __forceinline__ void fwd_task(const NodeView& v, const int plane, con
     }
 }
 
-template <class NET, bool GENERAL>
-__global__ void __launch_bounds__(kThreads) fwd_nodes_kernel(NodeView v, Tasks T) {
+template <class NET, bool GENERAL, bool STASH = false>
+__global__ void __launch_bounds__(kThreads, 3) fwd_nodes_kernel(NodeView v, Tasks T) {
     const int rep = blockIdx.y;
     const float* xe = v.xe + (size_t)rep * v.ex;
     const float* ye = v.ye + (size_t)rep * v.ey;
     const float* ze = v.ze + (size_t)rep * v.ez;
     const uint8_t* side = v.side + rep * v.rep_nodes;
     float* U = v.U + rep * v.rep_nodes;
-    for (int task = blockIdx.x; task < T.total; task += gridDim.x) {
-        const int mb = task % T.mblocks, xc = task / T.mblocks;
-        const int x0 = v.x_begin + xc * T.xchunk, x1 = min(v.x_end, x0 + T.xchunk);
-        fwd_task<NET, GENERAL>(v, T.plane, xe, ye, ze, side, U, mb * kThreads + (int)threadIdx.x, x0, x1);
+    // balanced contiguous runs: the (strip, x plane) pairs in strip-major order are cut into gridDim.x equal ranges, so
+    // every CTA does the same number of plane iterations (+-1) and a thread keeps its (y, z) for a long x march
+    // (T.split ranges per CTA, dealt round-robin)
+    const int nx = v.x_end - v.x_begin;
+    const int64_t total = (int64_t)T.mblocks * nx;
+    const int64_t nranges = (int64_t)gridDim.x * T.split;
+    for (int64_t rg = blockIdx.x; rg < nranges; rg += gridDim.x) {
+        const int64_t hi = total * (rg + 1) / nranges;
+        for (int64_t p = total * rg / nranges; p < hi;) {
+            const int mb = (int)(p / nx), xo = (int)(p - (int64_t)mb * nx);
+            const int len = (int)min((int64_t)(nx - xo), hi - p);
+            fwd_task<NET, GENERAL, STASH>(v, T.plane, xe, ye, ze, side, U, mb * kThreads + (int)threadIdx.x, v.x_begin + xo,
+                                          v.x_begin + xo + len);
+            p += len;
+        }
     }
 }
 
@@ -1148,7 +1167,7 @@ __global__ void irregular_bwd_kernel(nbm_shared_step_t s, bool nl_center) {
 }
 
 // C0b: adjoint of the extrapolation: G[node_c + off_q] += B[c][q] gE[c]
-__global__ void extrap_bwd_kernel(nbm_shared_step_t s) {
+__global__ void extrap_bwd_kernel(nbm_shared_step_t s, float* __restrict__ Gt) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t c = t / 27;
     int q = (int)(t - c * 27);
@@ -1157,7 +1176,78 @@ __global__ void extrap_bwd_kernel(nbm_shared_step_t s) {
     if (g == 0.0f) return;
     int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
     int a = q % 3 - 1, b = (q / 3) % 3 - 1, cc = q / 9 - 1;
-    atomicAdd(s.G + s.c_node[c] + a * sx + b * sy + cc, s.B[c * 28 + q] * g);
+    atomicAdd(Gt + s.c_node[c] + a * sx + b * sy + cc, s.B[c * 28 + q] * g);
+}
+
+// ---- the list chain beside the dense stencil (nbm_shared_step_t.G2 / Rq; faces table) -----------------------------
+// An irregular row forward AND backward in one thread: the row needs only U and E, its residual stays in the compact
+// array Rq (the dense kernel owns R while this runs), its adjoint goes into gE and into the side buffer G2.
+__global__ void irregular_fb_kernel(nbm_shared_step_t s) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= s.n_irr) return;
+    const int64_t e = s.irr_point[q];
+    const int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
+    const int64_t off[7] = {0, -sx, sx, -sy, sy, -1, 1};
+    int32_t c[7];
+    float wE[7], wU[7], u[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        c[k] = s.irr_c[q * 7 + k];
+        wE[k] = s.irr_wE[q * 7 + k];
+        wU[k] = s.irr_wU[q * 7 + k];
+        u[k] = s.U[e + off[k]];
+    }
+    // same operation order as irregular_fwd_kernel
+    float r = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+        if (c[k] >= 0) r = fmaf(wE[k], s.E[c[k]], r);
+    const uint8_t nlr = s.irr_nl[q];
+    float Ec = 0.0f, nlw = 0.0f;
+    if (nlr) {
+        Ec = s.E[c[0]];
+        nlw = s.irr_nlw[q];
+        r = fmaf(nlw, nlr == 1 ? nl_apply(s.nonlinear_m, s.nl_coef_m, Ec) : nl_apply(s.nonlinear_p, s.nl_coef_p, Ec), r);
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) r = fmaf(wU[k], u[k], r);
+    float nla = 0.0f, nlb = 0.0f;
+    if (s.nl) {
+        const int64_t ne = sx * s.ex;
+        nla = s.nl[e];
+        nlb = s.nl[ne + e];
+        r = fmaf(nla, nl_apply(s.nonlinear_m, s.nl_coef_m, u[0]), r);
+        r = fmaf(nlb, nl_apply(s.nonlinear_p, s.nl_coef_p, u[0]), r);
+    }
+    r -= s.irr_rhs[q];
+    s.Rq[q] = r;
+    // adjoint (irregular_bwd_kernel with nl_center = true)
+    if (s.nl)
+        atomicAdd(s.G2 + e, (nla * nl_deriv(s.nonlinear_m, s.nl_coef_m, u[0]) + nlb * nl_deriv(s.nonlinear_p, s.nl_coef_p, u[0])) * r);
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+        if (c[k] >= 0) atomicAdd(s.gE + c[k], wE[k] * r);
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+        if (wU[k] != 0.0f) atomicAdd(s.G2 + e + off[k], wU[k] * r);
+    if (nlr) {
+        const float d = nlr == 1 ? nl_deriv(s.nonlinear_m, s.nl_coef_m, Ec) : nl_deriv(s.nonlinear_p, s.nl_coef_p, Ec);
+        atomicAdd(s.gE + c[0], nlw * d * r);
+    }
+}
+
+// join of the list chain: G += G2 on the nodes the lists can reach (G2 re-zeroed), R <- Rq on the irregular rows
+__global__ void merge_lists_kernel(nbm_shared_step_t s) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < s.n_list) {
+        const int64_t n = s.list_nodes[i];
+        const float g2 = s.G2[n];
+        if (g2 != 0.0f) {
+            s.G[n] += g2;
+            s.G2[n] = 0.0f;
+        }
+    }
+    if (i < s.n_irr) s.R[s.irr_point[i]] = s.Rq[i];
 }
 
 // block-level reduction of per-thread accumulators into partials[blockIdx.x][0..NP] (loss last)
@@ -1229,8 +1319,22 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
     const uint8_t* side = v.side + rep * v.rep_nodes;
     const float* G = v.G + rep * v.rep_nodes;
     const float* R = v.R;  // only the shared path (one replica) accumulates the loss here
-    for (int task = blockIdx.x; task < T.total; task += gridDim.x) {
-        const int mb = task % T.mblocks, xc = task / T.mblocks;
+    // balanced contiguous runs of (strip, x plane) pairs, strip-major (see fwd_nodes_kernel)
+    const int nx = v.x_end - v.x_begin;
+    const int64_t total = (int64_t)T.mblocks * nx;
+    const int64_t nranges = (int64_t)gridDim.x * T.split;
+    int64_t rg = blockIdx.x, pr = total * rg / nranges, run_hi = total * (rg + 1) / nranges;
+    for (;;) {
+        if (pr >= run_hi) {        // next range of this CTA
+            rg += gridDim.x;
+            if (rg >= nranges) break;
+            pr = total * rg / nranges;
+            run_hi = total * (rg + 1) / nranges;
+            continue;
+        }
+        const int mb = (int)(pr / nx), xo = (int)(pr - (int64_t)mb * nx);
+        const int run_len = (int)min((int64_t)(nx - xo), run_hi - pr);
+        pr += run_len;
         const int m_raw = mb * kGradThreads + threadIdx.x;
         const bool valid = m_raw < T.plane;             // lanes past the plane stay in the warp (shuffles) with g = 0
         const int m = valid ? m_raw : T.plane - 1;
@@ -1238,7 +1342,7 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
         const float y = __ldg(ye + iy), z = __ldg(ze + iz);
         u64 yz[HP2];
         P::template first_layer_yz<0>(y, z, yz);
-        const int x0 = v.x_begin + xc * T.xchunk, x1 = min(v.x_end, x0 + T.xchunk);
+        const int x0 = v.x_begin + xo, x1 = x0 + run_len;
         // software pipeline: the loads of plane ix+1 are in flight while plane ix is computed; running pointers, one
         // add per array and plane
         int64_t e = (int64_t)x0 * T.plane + m;
@@ -2366,6 +2470,31 @@ static int sm_count() {
     return g_sm_count;
 }
 
+// library-owned side stream + fork/join events of the list chain, one set per device (created on first use)
+struct SideLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideLane* side_lane() {
+    static SideLane lanes[64];
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SideLane& l = lanes[dev & 63];
+    std::lock_guard<std::mutex> lock(mu);
+    if (!l.stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // (hi = numerically lowest = highest priority)
+        if (cudaStreamCreateWithPriority(&l.stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) {
+            l.stream = nullptr;
+            return nullptr;
+        }
+    }
+    return &l;
+}
+
 constexpr int kPartialRows = 148 * 9;  // shared path: <= 148 rows; general path: 7 replicas x 148 + rows + extrap rows
 
 template <class NET>
@@ -2390,13 +2519,14 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
         int mblocks = (s.ey * s.ez + kGradThreads - 1) / kGradThreads;
         while (xchunk_g > 2 && (int64_t)mblocks * ((s.ex + xchunk_g - 1) / xchunk_g) < 2 * (int64_t)sms) xchunk_g >>= 1;
     }
-    const Tasks Tg = make_tasks(s.ex, s.ey, s.ez, xchunk_g, kGradThreads);
+    Tasks Tg = make_tasks(s.ex, s.ey, s.ez, xchunk_g, kGradThreads);
     const bool pc = s.coef26 != nullptr;
     const int n_pc = pc ? PrecondNet<8, 4>::NP : 0;
     const int pc_stride = NET::NP + n_pc + 1;
     const int gridP = pc ? min(s.n_pc_rows, 3 * sms) : 0;
-    int gridC = min(Tg.total, min(kPartialRows, sms));
+    int gridC = (int)min((int64_t)Tg.mblocks * s.ex, (int64_t)min(kPartialRows, sms));
     if (gridC > s.n_partial_rows - gridP) gridC = s.n_partial_rows - gridP;
+    Tg.split = run_split((int64_t)Tg.mblocks * s.ex, gridC);
     // K_B: residual rows + adjoint stencil of the faces table as one TMA-fed kernel whenever both stages are wanted and
     // nothing sits between them (the preconditioner rescales R; the r1 fused gradient kernel wants S)
     const int dense2 = NBM_STAGE_RESIDUAL | NBM_STAGE_ADJOINT;
@@ -2405,12 +2535,35 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     // timing modifiers: run only the dense kernels / only the list kernels of the selected stages
     const bool lists_on = !(stages & NBM_STAGE_NO_LISTS), dense_on = !(stages & NBM_STAGE_NO_DENSE);
     if (dense_on && (stages & NBM_STAGE_FWD)) {
-        int gridA = min(T.total, sms * 8);
-        fwd_nodes_kernel<NET, false><<<gridA, kThreads, 0, st>>>(view_of(s), T);
+        static const int fwd_cta_per_sm = getenv("NBM_FWD_CTAS") ? atoi(getenv("NBM_FWD_CTAS")) : 6;   // 3 resident: 2 even waves
+        int gridA = (int)min((int64_t)T.mblocks * s.ex, (int64_t)sms * fwd_cta_per_sm);
+        if (s.Hst) fwd_nodes_kernel<NET, false, true><<<gridA, kThreads, 0, st>>>(view_of(s), T);
+        else fwd_nodes_kernel<NET, false, false><<<gridA, kThreads, 0, st>>>(view_of(s), T);
     }
-    if ((stages & NBM_STAGE_EXTRAP) && lists_on && s.n_crossed > 0)
+    // the list chain beside the dense stencil (see nbm_shared_step_t.G2): whole-step launches only
+    const int chain = NBM_STAGE_EXTRAP | dense2;
+    const bool overlap = fusedA && lists_on && dense_on && ((stages & chain) == chain) && s.G2 && s.Rq && s.list_nodes &&
+                         !s.g_ptr && (s.n_irr > 0 || s.n_crossed > 0) && (s.n_irr == 0 || s.n_list > 0);
+    if (overlap) {
+        SideLane* lane = side_lane();
+        if (!lane) return cuda_check(cudaGetLastError(), "side stream of the list chain");
+        cudaEventRecord(lane->fork, st);
+        cudaStreamWaitEvent(lane->stream, lane->fork, 0);
+        if (s.n_crossed > 0) extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, lane->stream>>>(s);
+        if (s.n_irr > 0) irregular_fb_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, lane->stream>>>(s);
+        if (s.n_crossed > 0)
+            extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, lane->stream>>>(s, s.G2);
+        cudaEventRecord(lane->join, lane->stream);
+        int rc = stencil_tma::launch(s, sms, st);
+        if (rc) return rc;
+        cudaStreamWaitEvent(st, lane->join, 0);
+        const int64_t nm = s.n_list > s.n_irr ? s.n_list : s.n_irr;
+        merge_lists_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(s);
+    }
+    if (!overlap && (stages & NBM_STAGE_EXTRAP) && lists_on && s.n_crossed > 0)
         extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
-    if (fusedA) {
+    if (overlap) {
+    } else if (fusedA) {
         if (dense_on) {
             int rc = stencil_tma::launch(s, sms, st);
             if (rc) return rc;
@@ -2457,7 +2610,7 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
         }
     }
     const bool fused = s.faces && s.S && !s.nl && !pc;
-    if (stages & NBM_STAGE_ADJOINT) {
+    if ((stages & NBM_STAGE_ADJOINT) && !overlap) {
         if (fusedA || !dense_on) {
             // (dense adjoint already done inside K_B / not wanted)
         } else if (fused) {
@@ -2481,7 +2634,7 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
             if (s.n_list > 0) gather_G_kernel<<<(unsigned)((s.n_list + 127) / 128), 128, 0, st>>>(s);
         } else {
             if (s.n_irr > 0) irregular_bwd_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, st>>>(s, fusedA);
-            if (s.n_crossed > 0) extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, st>>>(s);
+            if (s.n_crossed > 0) extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, st>>>(s, s.G);
         }
     }
     if ((stages & NBM_STAGE_GRAD) && fused) {
@@ -2733,9 +2886,9 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
         while (xchunk > 2 && (int64_t)mblocks * ((nxp + xchunk - 1) / xchunk) * 7 < 2 * (int64_t)sms) xchunk >>= 1;
     }
     Tasks T = make_tasks(v.x_end - v.x_begin, s.ny, s.nz, xchunk);
-    const int gridF = min(T.total, sms * 2);
+    const int gridF = (int)min((int64_t)T.mblocks * (v.x_end - v.x_begin), (int64_t)sms * 2);
     const Tasks Tg = make_tasks(v.x_end - v.x_begin, s.ny, s.nz, xchunk, kGradThreads);
-    const int gridG = min(Tg.total, max(1, sms / 4));        // x 7 replicas: ~2 waves of the 1-CTA/SM backward kernel
+    const int gridG = (int)min((int64_t)Tg.mblocks * (v.x_end - v.x_begin), (int64_t)max(1, sms / 4));        // x 7 replicas: ~2 waves of the 1-CTA/SM backward kernel
     const int gridR = (int)min((int64_t)sms * 2, (nb + kThreads - 1) / kThreads);
     int gridE = 0;
     if (s.n_crossed > 0) gridE = (int)min((int64_t)sms, (s.n_crossed * 32 + kThreads - 1) / kThreads);
@@ -2846,6 +2999,10 @@ int nbm_loss_grad_shared_f32(const nbm_shared_step_t* s, nbm_stream_t stream) {
         NBM_REQUIRE(s->g_ent && s->list_nodes && s->n_list >= 0, "null list-node tables");
         NBM_REQUIRE(s->n_crossed == 0 || (s->ge_ptr && s->ge_ent), "null crossed-site incidence");
         NBM_REQUIRE(!s->S, "the gathered list adjoint and the fused adjoint (S) are alternatives");
+    }
+    if (s->G2 || s->Rq) {
+        NBM_REQUIRE(s->G2 && s->Rq && s->list_nodes && s->n_list >= 0 && !s->g_ptr,
+                    "the list chain beside the stencil needs G2, Rq and list_nodes (and no gathered adjoint)");
     }
     if (s->coef26) {
         NBM_REQUIRE(s->pc_params, "null preconditioner parameters");

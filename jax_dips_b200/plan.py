@@ -360,7 +360,8 @@ class SharedPlan:
     def __init__(self, lvl: LevelSet, tr_gstate, xa: int, xb: int, fns, net: NetShape,
                  nonlinear_m: Nonlinear, nonlinear_p: Nonlinear, n_mean: Optional[int] = None, device=None,
                  faces: Optional[bool] = None, fused: Optional[bool] = None, precond: Optional[PrecondShape] = None,
-                 deterministic: bool = False, stencil_tma: Optional[bool] = None, stash: Optional[bool] = None):
+                 deterministic: bool = False, stencil_tma: Optional[bool] = None, stash: Optional[bool] = None,
+                 overlap_lists: Optional[bool] = None):
         """`faces`: store one coefficient per cell FACE + 1/diag (16 B/node) instead of the 7 row weights
         (28 B/node); irregular rows move into the list.  Default: on (lattice rows are padded to 16-byte multiples).
         `fused`: evaluate the dense adjoint stencil inside the gradient kernel from TMA-staged row tables
@@ -373,6 +374,9 @@ class SharedPlan:
         for hidden_p = 10) so that the gradient kernel does not recompute it.  Default OFF: measured on B200 at 256^3
         the gradient kernel gains 21 us (343 -> 323) but the forward kernel loses 38 us to the 830 MB of stores
         (172 -> 210); see DESIGN.md.
+        `overlap_lists`: run the list kernels (crossed sites, irregular rows) on a side stream BESIDE the TMA stencil
+        kernel instead of after it (they need only U); their adjoint lands in a side buffer that a small merge kernel
+        adds to G.  Default: on whenever the TMA stencil is active and `deterministic` is off.
         `deterministic`: gather the adjoint of the lists (irregular rows, extrapolation) through their transposed
         incidence instead of scattering it with fp32 atomics: the whole step becomes bitwise reproducible, for
         ~5 us more per step at 256^3 (the atomics are faster than the doubly indirect gathers)."""
@@ -614,6 +618,27 @@ class SharedPlan:
             # (mirrors the library's own test, nbm_step.cu launch_shared)
             self.stencil_tma_active = bool(self.stencil_tma and self.faces and precond is None and not self.fused
                                            and ez % 4 == 0 and not (use_nl and self.g_ptr is not None))
+            # list chain beside the dense stencil: side buffer G2, compact residuals Rq, the nodes the lists can reach
+            want = (os.environ.get("NBM_OVERLAP_LISTS", "1") != "0") if overlap_lists is None else bool(overlap_lists)
+            self.overlap_lists = bool(want and self.stencil_tma_active and self.g_ptr is None and (cs.n > 0 or n_irr > 0))
+            self.G2 = self.Rq = None
+            if self.overlap_lists:
+                sxy, sy = ey * ez, ez
+                tg = []
+                if cs.n > 0:
+                    v27 = torch.arange(27, device=dev)
+                    o27 = (v27 % 3 - 1) * sxy + ((v27 // 3) % 3 - 1) * sy + (v27 // 9 - 1)
+                    tg.append((cs.idx[:cs.n, None] + o27[None, :]).reshape(-1))
+                if n_irr > 0:
+                    o7 = torch.tensor([0, -sxy, sxy, -sy, sy, -1, 1], dtype=torch.int64, device=dev)
+                    tg.append((self.irr_point[:n_irr, None] + o7[None, :]).reshape(-1))
+                self.list_nodes = torch.unique(torch.cat(tg)).contiguous()
+                assert int(self.list_nodes.min()) >= 0 and int(self.list_nodes.max()) < ne
+                self.n_list = int(self.list_nodes.numel())
+                self.G2 = torch.zeros(ne, dtype=torch.float32, device=dev)
+                self.Rq = torch.zeros(max(n_irr, 1), dtype=torch.float32, device=dev)
+                s.list_nodes, s.n_list = cabi.ptr(self.list_nodes), self.n_list
+                s.G2, s.Rq = cabi.ptr(self.G2), cabi.ptr(self.Rq)
             if precond is not None:
                 s.coef26 = cabi.ptr(self.coef26)
                 s.pc_d1, s.pc_d2, s.pc_scale = precond.widths[0], precond.widths[1], precond.scale

@@ -352,6 +352,7 @@ import os
 
 import numpy as np
 
+TOL_FRAC_REF = 1e-4   # = tests/test_oracle_pinning.py: the reference's own float32 measure noise on 220-cell sets is 6.2e-5
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
                 if not os.path.basename(p).startswith("grad_"))
 CASE_PROBLEM = util.GOLDEN_CASES
@@ -406,8 +407,9 @@ def test_cuda_rows_match_reference_golden(path):
     if cr.any():
         f = frac[cidx[cr].long()].double()
         vol, area = d.prod(), d[1] * d[2]
-        assert float((f[:, 12:14] - coeffs[cr][:, 12:14]).abs().max()) / vol < 5e-5
-        assert float((f[:, 0:12] - coeffs[cr][:, 14:26]).abs().max()) / area < 5e-5
+        ev = float((f[:, 12:14] - coeffs[cr][:, 12:14]).abs().max()) / vol
+        ea = float((f[:, 0:12] - coeffs[cr][:, 14:26]).abs().max()) / area
+        assert ev < TOL_FRAC_REF and ea < TOL_FRAC_REF, (ev, ea)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -33,14 +33,14 @@ def fns_of(problem):
 
 
 def build(problem, n_train, n_lvl, interp="trilinear", net=None, xa=0, xb=None, faces=None, fused=None, stencil_tma=None,
-          phi_grid=None, stash=None):
+          phi_grid=None, stash=None, overlap_lists=None):
     tr, lv, phi_grid, oprob = util.make_case(problem, n_train, n_lvl, interp, torch.float64, net=net, phi_grid=phi_grid)
     lvl = nplan.LevelSet(lv, phi_grid, interp=interp, perturb_eps=1e-10, device=DEV)
     shape = nplan.NetShape(oprob.shape.Lp, oprob.shape.Hp, oprob.shape.Lm, oprob.shape.Hm)
     pl = nplan.SharedPlan(lvl, tr, xa, xb if xb is not None else tr.shape()[0], fns_of(problem), shape,
                           nplan.Nonlinear.coerce(problem.nonlinear_op_m),
                           nplan.Nonlinear.coerce(problem.nonlinear_op_p), device=DEV, faces=faces, fused=fused,
-                          stencil_tma=stencil_tma, stash=stash)
+                          stencil_tma=stencil_tma, stash=stash, overlap_lists=overlap_lists)
     return tr, lv, lvl, oprob, pl, shape
 
 
@@ -302,6 +302,50 @@ def test_stencil_tma_is_bitwise_the_two_stencil_kernels(name, n, nl, xa, xb):
     assert util.rel_inf(la.cpu(), lb.cpu()) < 2e-6, util.rel_inf(la.cpu(), lb.cpu())
     assert util.rel_inf(la2.cpu(), la.cpu()) < 2e-6
     assert abs(float(la[-1]) - float(lb[-1])) <= 1e-6 * abs(float(lb[-1]))
+
+
+# The list kernels (crossed sites, irregular rows) run on a side stream beside the TMA stencil and leave their adjoint in
+# a side buffer that a merge kernel adds to G: same rows bitwise, same G / [grad, loss] up to the order of the fp32
+# atomics, the side buffer is left clean, and a CUDA graph of the step replays the fork/join.
+@pytest.mark.parametrize("name,n,nl,xa,xb", [
+    ("sphere", 16, 32, 0, None), ("star", 32, 32, 0, None), ("sphere", 24, 24, 5, 17),
+    ("sphere_reaction", 16, 32, 0, None), ("sphere", 64, 64, 0, None), ("sphere", 24, 24, 0, 4)])
+def test_list_chain_beside_the_stencil_equals_the_serial_chain(name, n, nl, xa, xb):
+    P = problems.PROBLEMS[name]()
+    tr, lv, lvl, oprob, pa, shape = build(P, n, nl, xa=xa, xb=xb, faces=True, stencil_tma=True, overlap_lists=True)
+    _, _, _, _, pb, _ = build(P, n, nl, xa=xa, xb=xb, faces=True, stencil_tma=True, overlap_lists=False)
+    if pa.sites.n == 0 and pa.n_irr == 0:
+        assert not pa.overlap_lists      # a slab without interface has no list chain
+        return
+    assert pa.overlap_lists and not pb.overlap_lists and pa.G2 is not None and pb.G2 is None
+    params = O.init_params(oprob.shape, seed=17, dtype=torch.float64).float().to(DEV)
+    with torch.cuda.device(DEV):
+        nplan.upload_params(shape, params)
+        la = pa.loss_grad_launch().clone()
+        lb = pb.loss_grad_launch().clone()
+        torch.cuda.synchronize()
+        assert torch.equal(pa.U, pb.U)
+        assert torch.equal(pa.R, pb.R)
+        assert torch.equal(pa.E, pb.E)
+        assert util.rel_inf(pa.gE.cpu(), pb.gE.cpu()) < 2e-6
+        assert util.rel_inf(pa.G.cpu(), pb.G.cpu()) < 2e-6
+        assert int((pa.G2 != 0).sum()) == 0
+        assert util.rel_inf(la.cpu(), lb.cpu()) < 2e-6, util.rel_inf(la.cpu(), lb.cpu())
+        # replayed as a CUDA graph (what the trainer does): the fork / join onto the library's side stream is captured
+        side = torch.cuda.Stream(device=DEV)
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            pa.loss_grad_launch()
+            with torch.cuda.graph(graph, stream=side):
+                pa.loss_grad_launch()
+        torch.cuda.current_stream().wait_stream(side)
+        for _ in range(3):
+            pa.loss_grad.zero_()
+            graph.replay()
+        torch.cuda.synchronize()
+        assert util.rel_inf(pa.loss_grad.cpu(), lb.cpu()) < 2e-6
+        assert int((pa.G2 != 0).sum()) == 0
 
 
 # The forward kernel keeps the last hidden layer of every plus-side node (activation stash) and the gradient kernel reads

@@ -20,13 +20,13 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r1b"
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
-STEP = ["prep_params_kernel", "fwd_nodes_kernel", "extrap_kernel", "residual", "irregular_fwd_kernel", "adjoint",
+STEP = ["prep_params_kernel", "fwd_nodes_kernel", "extrap_kernel", "residual", "stencil_tma", "step_", "irregular_fwd_kernel", "adjoint",
         "irregular_bwd_kernel", "extrap_bwd_kernel", "node_grad", "precond_kernel", "reduce_partials_kernel",
         "apply_update_kernel", "finalize_step_kernel"]
 
 
 def short(name):
-    n = name.replace("void ", "").replace("nbm::", "")
+    n = name.replace("void ", "").replace("nbm::", "").replace("stencil_tma::", "")
     return n.split("(")[0].split("<")[0]
 
 
