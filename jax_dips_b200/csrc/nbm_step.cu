@@ -650,6 +650,7 @@ struct NodeView {
     int x_begin, x_end;          // planes walked
     int64_t lo, hi;              // only nodes lo <= e < hi (index inside a replica) are touched
     int64_t rep_nodes;           // replica stride of side / U / G
+    int nrep;                    // replicas walked (1: shared path, 7: general path); ranges run across replicas
     const uint8_t* side;
     float* U;
     const float* G;
@@ -668,6 +669,7 @@ static NodeView view_of(const nbm_shared_step_t& s) {
     v.x_begin = 0; v.x_end = s.ex;
     v.lo = 0; v.hi = (int64_t)s.ex * s.ey * s.ez;
     v.rep_nodes = v.hi;
+    v.nrep = 1;
     v.side = s.side; v.U = s.U; v.G = s.G; v.R = s.R;
     v.Hst = reinterpret_cast<float4*>(s.Hst);
     v.inv_n = s.inv_n_points; v.partials = s.partials; v.row0 = 0;
@@ -720,25 +722,22 @@ __device__ __forceinline__ void fwd_task(const NodeView& v, const int plane, con
 
 template <class NET, bool GENERAL, bool STASH = false>
 __global__ void __launch_bounds__(kThreads, 3) fwd_nodes_kernel(NodeView v, Tasks T) {
-    const int rep = blockIdx.y;
-    const float* xe = v.xe + (size_t)rep * v.ex;
-    const float* ye = v.ye + (size_t)rep * v.ey;
-    const float* ze = v.ze + (size_t)rep * v.ez;
-    const uint8_t* side = v.side + rep * v.rep_nodes;
-    float* U = v.U + rep * v.rep_nodes;
-    // balanced contiguous runs: the (strip, x plane) pairs in strip-major order are cut into gridDim.x equal ranges, so
-    // every CTA does the same number of plane iterations (+-1) and a thread keeps its (y, z) for a long x march
-    // (T.split ranges per CTA, dealt round-robin)
+    // balanced contiguous runs: the (replica, strip, x plane) triples in that order are cut into gridDim.x * T.split equal
+    // ranges dealt round-robin, so every CTA does the same number of plane iterations (+-1) and a thread keeps its
+    // (y, z) for a long x march
     const int nx = v.x_end - v.x_begin;
-    const int64_t total = (int64_t)T.mblocks * nx;
+    const int64_t per_rep = (int64_t)T.mblocks * nx, total = per_rep * v.nrep;
     const int64_t nranges = (int64_t)gridDim.x * T.split;
     for (int64_t rg = blockIdx.x; rg < nranges; rg += gridDim.x) {
         const int64_t hi = total * (rg + 1) / nranges;
         for (int64_t p = total * rg / nranges; p < hi;) {
-            const int mb = (int)(p / nx), xo = (int)(p - (int64_t)mb * nx);
+            const int rep = (int)(p / per_rep);
+            const int64_t q = p - rep * per_rep;
+            const int mb = (int)(q / nx), xo = (int)(q - (int64_t)mb * nx);
             const int len = (int)min((int64_t)(nx - xo), hi - p);
-            fwd_task<NET, GENERAL, STASH>(v, T.plane, xe, ye, ze, side, U, mb * kThreads + (int)threadIdx.x, v.x_begin + xo,
-                                          v.x_begin + xo + len);
+            fwd_task<NET, GENERAL, STASH>(v, T.plane, v.xe + (size_t)rep * v.ex, v.ye + (size_t)rep * v.ey,
+                                          v.ze + (size_t)rep * v.ez, v.side + rep * v.rep_nodes, v.U + rep * v.rep_nodes,
+                                          mb * kThreads + (int)threadIdx.x, v.x_begin + xo, v.x_begin + xo + len);
             p += len;
         }
     }
@@ -1312,16 +1311,10 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
     for (int i = 0; i < M::NP; ++i) accm[i] = 0.0f;
     float loss = 0.0f;
     const bool par = (threadIdx.x & 1) != 0;
-    const int rep = blockIdx.y;
-    const float* xe = v.xe + (size_t)rep * v.ex;
-    const float* ye = v.ye + (size_t)rep * v.ey;
-    const float* ze = v.ze + (size_t)rep * v.ez;
-    const uint8_t* side = v.side + rep * v.rep_nodes;
-    const float* G = v.G + rep * v.rep_nodes;
     const float* R = v.R;  // only the shared path (one replica) accumulates the loss here
-    // balanced contiguous runs of (strip, x plane) pairs, strip-major (see fwd_nodes_kernel)
+    // balanced contiguous runs of (replica, strip, x plane) triples (see fwd_nodes_kernel)
     const int nx = v.x_end - v.x_begin;
-    const int64_t total = (int64_t)T.mblocks * nx;
+    const int64_t per_rep = (int64_t)T.mblocks * nx, total = per_rep * v.nrep;
     const int64_t nranges = (int64_t)gridDim.x * T.split;
     int64_t rg = blockIdx.x, pr = total * rg / nranges, run_hi = total * (rg + 1) / nranges;
     for (;;) {
@@ -1332,9 +1325,16 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
             run_hi = total * (rg + 1) / nranges;
             continue;
         }
-        const int mb = (int)(pr / nx), xo = (int)(pr - (int64_t)mb * nx);
+        const int rep = (int)(pr / per_rep);
+        const int64_t qr = pr - rep * per_rep;
+        const int mb = (int)(qr / nx), xo = (int)(qr - (int64_t)mb * nx);
         const int run_len = (int)min((int64_t)(nx - xo), run_hi - pr);
         pr += run_len;
+        const float* xe = v.xe + (size_t)rep * v.ex;
+        const float* ye = v.ye + (size_t)rep * v.ey;
+        const float* ze = v.ze + (size_t)rep * v.ez;
+        const uint8_t* side = v.side + rep * v.rep_nodes;
+        const float* G = v.G + rep * v.rep_nodes;
         const int m_raw = mb * kGradThreads + threadIdx.x;
         const bool valid = m_raw < T.plane;             // lanes past the plane stay in the warp (shuffles) with g = 0
         const int m = valid ? m_raw : T.plane - 1;
@@ -1440,7 +1440,7 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
     }
     __syncthreads();
     const int stride = v.row_stride ? v.row_stride : NP + 1, loss_col = v.row_stride ? v.loss_col : NP;
-    float* partials = v.partials + (size_t)(v.row0 + rep * gridDim.x) * stride;
+    float* partials = v.partials + (size_t)v.row0 * stride;
     for (int i = threadIdx.x; i < NP + 1; i += kGradThreads) {
         float val = 0.0f;
 #pragma unroll
@@ -2535,8 +2535,14 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     // timing modifiers: run only the dense kernels / only the list kernels of the selected stages
     const bool lists_on = !(stages & NBM_STAGE_NO_LISTS), dense_on = !(stages & NBM_STAGE_NO_DENSE);
     if (dense_on && (stages & NBM_STAGE_FWD)) {
-        static const int fwd_cta_per_sm = getenv("NBM_FWD_CTAS") ? atoi(getenv("NBM_FWD_CTAS")) : 6;   // 3 resident: 2 even waves
-        int gridA = (int)min((int64_t)T.mblocks * s.ex, (int64_t)sms * fwd_cta_per_sm);
+        // 3 CTAs are resident per SM.  Large lattices: 12 CTAs per SM (4 even waves; measured 153.6 us at 256^3 against
+        // 154.6 with 6 and 160.9 with 3: minus-side regions make CTAs uneven).  Small ones: fewer, so that a CTA keeps
+        // >= 24 plane iterations per range start, down to one wave.
+        static const int fwd_env = getenv("NBM_FWD_CTAS") ? atoi(getenv("NBM_FWD_CTAS")) : 0;
+        const int64_t iters = (int64_t)T.mblocks * s.ex;
+        int per_sm = fwd_env > 0 ? fwd_env : 12;
+        while (!fwd_env && per_sm > 3 && iters / ((int64_t)sms * per_sm) < 24) per_sm -= 3;
+        int gridA = (int)min(iters, (int64_t)sms * per_sm);
         if (s.Hst) fwd_nodes_kernel<NET, false, true><<<gridA, kThreads, 0, st>>>(view_of(s), T);
         else fwd_nodes_kernel<NET, false, false><<<gridA, kThreads, 0, st>>>(view_of(s), T);
     }
@@ -2877,6 +2883,7 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     v.x_end = (int)((s.p1 + plane - 1) / plane);
     v.lo = s.p0; v.hi = s.p1;
     v.rep_nodes = a.n_points;
+    v.nrep = 7;
     v.side = s.side; v.U = s.U7; v.G = s.G7; v.R = nullptr;
     v.inv_n = s.inv_n_points; v.partials = s.partials;
     int xchunk = 16;
@@ -2886,9 +2893,15 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
         while (xchunk > 2 && (int64_t)mblocks * ((nxp + xchunk - 1) / xchunk) * 7 < 2 * (int64_t)sms) xchunk >>= 1;
     }
     Tasks T = make_tasks(v.x_end - v.x_begin, s.ny, s.nz, xchunk);
-    const int gridF = (int)min((int64_t)T.mblocks * (v.x_end - v.x_begin), (int64_t)sms * 2);
-    const Tasks Tg = make_tasks(v.x_end - v.x_begin, s.ny, s.nz, xchunk, kGradThreads);
-    const int gridG = (int)min((int64_t)Tg.mblocks * (v.x_end - v.x_begin), (int64_t)max(1, sms / 4));        // x 7 replicas: ~2 waves of the 1-CTA/SM backward kernel
+    const int64_t itersF = (int64_t)T.mblocks * (v.x_end - v.x_begin) * 7;
+    int perF = 12;      // forward CTAs per SM (3 resident), fewer while a range would hold < 24 plane iterations
+    while (perF > 3 && itersF / ((int64_t)sms * perF) < 24) perF -= 3;
+    const int gridF = (int)min(itersF, (int64_t)sms * perF);
+    Tasks Tg = make_tasks(v.x_end - v.x_begin, s.ny, s.nz, xchunk, kGradThreads);
+    // one gradient CTA per SM: the 7 replicas are one range set, every CTA gets the same share (one even wave)
+    const int64_t itersG = (int64_t)Tg.mblocks * (v.x_end - v.x_begin) * 7;
+    const int gridG = (int)min(itersG, (int64_t)sms);
+    Tg.split = run_split(itersG, gridG);
     const int gridR = (int)min((int64_t)sms * 2, (nb + kThreads - 1) / kThreads);
     int gridE = 0;
     if (s.n_crossed > 0) gridE = (int)min((int64_t)sms, (s.n_crossed * 32 + kThreads - 1) / kThreads);
@@ -2896,7 +2909,7 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     const int n_pc = pc ? PrecondNet<8, 4>::NP : 0;
     const int stride = NET::NP + n_pc + 1;
     const int gridP = pc ? min(s.n_pc_rows, 3 * sms) : 0;
-    const int rows_needed = 7 * gridG + gridR + gridE + gridP;
+    const int rows_needed = gridG + gridR + gridE + gridP;
     if (rows_needed > s.n_partial_rows) {
         set_error("partials buffer has %d rows, %d needed", s.n_partial_rows, rows_needed);
         return NBM_ERR_WORKSPACE;
@@ -2907,22 +2920,22 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     if (s.n_crossed > 0)
         points_extrap_kernel<NET><<<(unsigned)min((int64_t)sms * 4, (s.n_crossed * 32 + kThreads - 1) / kThreads),
                                     kThreads, 0, st>>>(a);
-    fwd_nodes_kernel<NET, true><<<dim3(gridF, 7), kThreads, 0, st>>>(v, T);
+    fwd_nodes_kernel<NET, true><<<gridF, kThreads, 0, st>>>(v, T);
     if (pc)
         precond_fwd_kernel<8, 4><<<(unsigned)min((int64_t)sms * 8, (nb + kThreads - 1) / kThreads), kThreads, 0, st>>>(
             s.coef26 + s.p0, a.n_points, nb, s.pc_params, s.pc_scale, s.Pc + s.p0);
-    points_rows_kernel<<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, 7 * gridG, stride);
+    points_rows_kernel<<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, gridG, stride);
     if (pc)   // loss + d loss/d theta_P from the raw residuals kept in `rows`
         precond_kernel<8, 4><<<gridP, kThreads, 0, st>>>(s.coef26 + s.p0, a.n_points, s.rows + s.p0, nullptr, nb, s.pc_params,
                                                          s.pc_scale, s.inv_n_points,
-                                                         s.partials + (size_t)(7 * gridG + gridR + gridE) * stride, stride,
+                                                         s.partials + (size_t)(gridG + gridR + gridE) * stride, stride,
                                                          NET::NP, NET::NP + n_pc);
     v.row0 = 0; v.row_stride = pc ? stride : 0; v.loss_col = NET::NP + n_pc;
     {
-        cudaError_t e = launch_node_grad<NET, true>(dim3(gridG, 7), v, Tg, st);
+        cudaError_t e = launch_node_grad<NET, true>(dim3(gridG), v, Tg, st);
         if (e != cudaSuccess) return cuda_check(e, "node_grad attribute");
     }
-    if (gridE > 0) points_extrap_bwd_kernel<NET><<<gridE, kThreads, 0, st>>>(a, 7 * gridG + gridR, stride);
+    if (gridE > 0) points_extrap_bwd_kernel<NET><<<gridE, kThreads, 0, st>>>(a, gridG + gridR, stride);
     reduce_partials_kernel<<<(stride * 32 + 127) / 128, 128, 0, st>>>(s.partials, rows_needed, stride, s.loss_grad);
     return cuda_check(cudaGetLastError(), "points step launch");
 }

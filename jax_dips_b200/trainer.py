@@ -179,13 +179,13 @@ class Trainer:
         self.batch_size, self.num_epochs, self.multi_gpu = batch_size, num_epochs, multi_gpu
         self.checkpoint_dir, self.checkpoint_interval = checkpoint_dir, checkpoint_interval
         self.results_dir, self.loss_plot_name, self.print_rate = results_dir, loss_plot_name, print_rate
-        # the reference stores this factor and never reads it outside the private, unused `__update`
-        # (trainer.py:791-816): the public `update` / `update_multi_gpu` ignore it.  Anything but 1 would silently
-        # train differently from what the caller asked for, so say so.
+        # the reference stores this factor and reads it only in the private `__update` (trainer.py:791-816), which none
+        # of its training loops call: `update` / `update_multi_gpu` ignore it.  Same here: the loops ignore it (and say
+        # so), `update_region_scaled` is that private step for callers who want it.
         self.mgrad_over_pgrad_scalefactor = mgrad_over_pgrad_scalefactor
         if mgrad_over_pgrad_scalefactor != 1:
-            logger.warning("mgrad_over_pgrad_scalefactor=%s is accepted for API compatibility but, as in the reference "
-                           "(only its unused `__update` reads it, trainer.py:791-816), it does not enter the update",
+            logger.warning("mgrad_over_pgrad_scalefactor=%s does not enter the training loops (as in the reference, whose "
+                           "loops never call `__update`, trainer.py:791-816); use Trainer.update_region_scaled for that step",
                            mgrad_over_pgrad_scalefactor)
         self.restart_checkpoint_dir = restart_checkpoint_dir
         self.use_cuda_graph = use_cuda_graph
@@ -376,6 +376,24 @@ class Trainer:
                                            self.n_params + 1, cabi.ptr(lg), cabi.ptr(self.params),
                                            cabi.ptr(self.opt_state), cabi.ptr(self.opt_count), cabi.ptr(loss_hist),
                                            cabi.stream_ptr()), "nbm_finalize_step_f32")
+
+    def update_region_scaled(self, plan, loss_hist: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The reference's private `__update` (trainer.py:791-816): the gradient of the minus-domain network
+        (`mlp_m_fn` parameters) is multiplied by `mgrad_over_pgrad_scalefactor`, the plus-domain gradient is taken as
+        is, one optimizer update is applied to both, and the returned loss is m_loss + p_loss (the same loss evaluated
+        twice, i.e. 2 x loss).  One value_and_grad here: both of the reference's passes differentiate the same
+        function.  Returns the device scalar; no training loop calls this (none does in the reference either)."""
+        L = cabi.lib()
+        with torch.cuda.device(self.device):
+            upload_params(self.net, self.params)
+            lg = plan.loss_grad_launch()
+            n_p = self.net.n_p      # flat layout: [p-head | m-head | preconditioner]
+            lg[n_p:self.net.n_params] *= float(self.mgrad_over_pgrad_scalefactor)
+            lg[-1] *= 2.0
+            cabi.check(L.nbm_apply_update_f32(C.byref(self._optimizer_struct()), cabi.ptr(lg), cabi.ptr(self.params),
+                                              cabi.ptr(self.opt_state), cabi.ptr(self.opt_count), cabi.ptr(loss_hist),
+                                              cabi.stream_ptr()), "nbm_apply_update_f32")
+            return lg[-1]
 
     def _begin_training(self) -> None:
         """stage the current parameters (plain / pre-scaled / transposed copies) for the first step of a loop"""

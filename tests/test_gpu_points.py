@@ -286,6 +286,40 @@ def test_analytic_level_set_through_the_trainer():
     assert util.rel_inf(state.grad_normal_solution.cpu()[fin], gn_o[fin]) < 1e-4
 
 
+def test_region_scaled_update_is_the_references_private_update():
+    """Trainer.update_region_scaled = the reference's `__update` (trainer.py:791-816): minus-network gradient times
+    mgrad_over_pgrad_scalefactor, one optimizer update, loss = m_loss + p_loss."""
+    P = problems.sphere()
+    n_tr, n_lvl, factor = 8, 24, 10.0
+    tr, lv, phi_grid, oprob = util.make_case(P, n_tr, n_lvl, "trilinear", torch.float64)
+    p0 = O.init_params(oprob.shape, seed=42, dtype=torch.float64)
+    od = {"optimizer_name": "custom", "learning_rate": 1e-2, "sched": {"scheduler_name": "exponential", "decay_rate": 0.975}}
+    lo, hi = P.box
+    g = [mesh.linspace_grid(lo, hi, [n] * 3) for n in (n_lvl, n_tr, 8)]
+    init_fn = ntrainer.setup(*P.setup_args())
+    sim_state, solve_fn = init_fn(lvl_gstate=g[0], tr_gstate=g[1], eval_gstate=g[2], num_epochs=4, batch_size=512,
+                                  mgrad_over_pgrad_scalefactor=factor, checkpoint_dir=None, optimizer_dict=od,
+                                  init_params=p0.float(), device=DEV, print_rate=0, phi_interp="trilinear")
+    solve_fn(sim_state)
+    T = solve_fn.trainer
+    plan = T.plan_for(0, 0, n_tr ** 3)
+    T.params.copy_(p0.float())      # back to the initial state: the loops above do not use the factor
+    T.opt_state.zero_()
+    T.opt_count.zero_()
+    d = [tr.dx.double(), tr.dy.double(), tr.dz.double()]
+    opt = O.OptaxCustom(p0.numel(), learning_rate=1e-2, decay_rate=0.975, dtype=torch.float64)
+    p_o = p0.clone()
+    n_p = T.net.n_p
+    for _ in range(3):
+        loss_o, grad_o = O.loss_and_grad(p_o, tr.R.double(), *d, oprob)
+        grad_o = grad_o.clone()
+        grad_o[n_p:] *= factor
+        p_o = p_o + opt.update(grad_o)
+        loss_k = T.update_region_scaled(plan)
+        assert abs(float(loss_k) - 2.0 * float(loss_o)) < 1e-4 * abs(2.0 * float(loss_o))
+    assert util.rel_inf(T.params.cpu(), p_o) < 1e-4
+
+
 def test_ragged_batches_keep_their_real_points():
     """512 points in batches of 200 (200 + 200 + 112; the reference would pad the last one with 88 random points from
     jax PRNGKey(0), data_management.py:70-76): unaligned batches run on the per-point path at every zoom level."""
