@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
                     help="N > 1: strong = the named grid (256^3) sharded over the N GPUs (default, BASELINE.json's shape); "
                          "weak = --grid x-planes per GPU (the box is stretched in x)")
+    ap.add_argument("--balance", type=int, default=1,
+                    help="N > 1, strong scaling: 1 = cost-weighted x-slab boundaries (plan.balanced_slabs), 0 = equal slabs "
+                         "(the reference's partition); the summed [grad, loss] is the same either way")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps when the working set fits in it")
     ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling measurement at N > 1")
     ap.add_argument("--zoom", type=int, default=0, help=">0: time the general per-point path at cell size = spacing/2^zoom")
@@ -270,7 +273,12 @@ def main():
                                 fused=None if args.fused < 0 else bool(args.fused), precond=precond,
                                 stencil_tma=None if args.stencil_tma < 0 else bool(args.stencil_tma))
 
-    pl = make_plan(tr, xa, xb)
+    n_nominal = per * Ny * Nz           # every rank's mean runs over the nominal per-device batch (psum of means)
+    slabs = None
+    if world > 1 and args.scaling == "strong" and args.balance and not emu:
+        slabs = nplan.balanced_slabs(lvl, tr, world, device=dev)
+        xa, xb = slabs[rank]
+    pl = make_plan(tr, xa, xb, n_mean=n_nominal)
     torch.cuda.synchronize()
     t_setup = time.time() - t_setup
 
@@ -354,8 +362,9 @@ def main():
             else:        # parameters handed in by the host every step (the e2e leg): prep kernel + copy
                 nplan.upload_params(net, params)
             partials, rows = None, 0
-            if comm is not None:
-                p.loss_grad_launch(comm=comm)
+            if comm is not None:   # exchange + optax chain + staging: one kernel
+                p.loss_grad_launch(comm=comm, finalize=(ostruct, net_struct, params, opt_state, opt_count, None))
+                return
             elif world > 1:
                 p.loss_grad_launch()
                 dist.all_reduce(self.lg, op=dist.ReduceOp.SUM)
@@ -444,7 +453,7 @@ def main():
                   "what": "fused peer all-reduce output vs dist.all_reduce(SUM) of the per-rank [grad, loss]; "
                           "rel = max|a-b| / max|b|"}
         if rank == 0 and args.scaling == "strong":
-            whole = make_plan(tr, 0, Nx, n_mean=pl.n_points)
+            whole = make_plan(tr, 0, Nx, n_mean=n_nominal)
             cabi.check(L.nbm_upload_staged_params(cabi.stream_ptr()), "nbm_upload_staged_params")
             w = whole.loss_grad_launch().clone()
             torch.cuda.synchronize()
@@ -464,7 +473,7 @@ def main():
         list_launches = (2 if pl.sites.n > 0 else 0) + (1 if pl.n_irr > 0 else 0) + 1
     else:
         list_launches = (1 if pl.sites.n > 0 else 0) * 2 + (1 if pl.n_irr > 0 else 0) * 2
-    launches_per_step = (2 if world > 1 else 1) + dense_launches + list_launches
+    launches_per_step = (2 if (world > 1 and comm is None) else 1) + dense_launches + list_launches
 
     # ---------------- value: device-resident inputs -------------------------------------------
     sampler = ClockSampler(local)          # NVML initialised here, outside the timed window
@@ -529,8 +538,8 @@ def main():
             tt += h0.elapsed_time(h1) / 5
         allt = [torch.zeros(3, device=dev) for _ in range(world)]
         dist.all_gather(allt, torch.tensor([tt, float(pl.sites.n), float(pl.n_irr)], device=dev))
-        per_rank = [{"rank": r, "ms_eager_no_exchange": float(a[0]), "crossed_sites": int(a[1]), "irregular_rows": int(a[2])}
-                    for r, a in enumerate(allt)]
+        per_rank = [{"rank": r, "ms_eager_no_exchange": float(a[0]), "crossed_sites": int(a[1]), "irregular_rows": int(a[2]),
+                     "planes": (slabs[r][1] - slabs[r][0]) if slabs else per} for r, a in enumerate(allt)]
     if rank == 0:
         # measured FP32 FMA peak (MEASURED_PEAKS.json holds no FP32 figure)
         scratch = torch.zeros(4, device=dev)
@@ -608,7 +617,8 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{args.workload}: train grid {Nx}x{Ny}x{Nz} ({n_points_total} points, "
-                                       f"x-slabs of {per} planes per GPU), level set on {args.lvl}^3 lvl grid "
+                                       f"x-slabs of {per} planes per GPU" +
+                                       (f", cost-balanced to {[b - a for a, b in slabs]}" if slabs else "") + "), level set on {args.lvl}^3 lvl grid "
                                        f"({args.interp}), MLP p 3-10-10-1 | m 3-1-1 tanh, optimizer custom(adam), "
                                        "one batch per GPU",
                            "l2": (f"row tables + work arrays ({table_mb:.0f} MB per GPU) exceed the 126 MB L2; no flush needed"

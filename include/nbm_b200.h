@@ -437,6 +437,14 @@ int nbm_comm_free(void* local_block);
  * out[np1] receives the sum over ranks.  np1 <= 1024. */
 int nbm_reduce_allreduce_f32(const float* partials, int rows, int np1, int rank, int world,
                              void* const* blocks_host, int32_t* step_dev, float* out, nbm_stream_t stream);
+/* The whole tail of a multi-GPU optimizer step as ONE kernel (update_multi_gpu, trainer.py:824-834: psum of grads
+ * and loss, optimizer.update, apply_updates): nbm_reduce_allreduce_f32 followed by the tail of nbm_finalize_step_f32
+ * (optax chain, staged parameter copies for the next step) without a kernel boundary between them.  loss_grad[np1]
+ * receives the sum over ranks; np1 = opt->n_params + 1. */
+int nbm_reduce_allreduce_finalize_f32(const nbm_optimizer_t* opt, const nbm_net_t* net, const float* partials, int rows,
+                                      int np1, int rank, int world, void* const* blocks_host, int32_t* step_dev,
+                                      float* loss_grad, float* params, float* state, int32_t* count, float* loss_hist,
+                                      nbm_stream_t stream);
 /* nonzero once a peer wait timed out on this device's block (host read of the block's error word) */
 int nbm_comm_error(void* local_block);
 

@@ -130,6 +130,8 @@ SYMBOLS = {
     "nbm_comm_free": (C.c_int, [C.c_void_p]),
     "nbm_comm_error": (C.c_int, [C.c_void_p]),
     "nbm_reduce_allreduce_f32": (C.c_int, [c_fp, C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_void_p), c_fp, c_fp, c_fp]),
+    "nbm_reduce_allreduce_finalize_f32": (C.c_int, [_P(Optimizer), _P(Net), c_fp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                    _P(C.c_void_p), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "nbm_apply_update_f32": (C.c_int, [_P(Optimizer), c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "nbm_finalize_step_f32": (C.c_int, [_P(Optimizer), _P(Net), c_fp, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "nbm_upload_staged_params": (C.c_int, [c_fp]),

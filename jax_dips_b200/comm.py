@@ -62,6 +62,16 @@ class PeerComm:
                                                        cabi.stream_ptr()), "nbm_reduce_allreduce_f32")
         return out
 
+    def reduce_allreduce_finalize(self, partials, rows, np1, out, fin) -> torch.Tensor:
+        """exchange + optax chain + parameter staging as one kernel; fin = (optimizer struct, net struct, params,
+        opt_state, opt_count, loss_hist or None)"""
+        o, net, params, state, count, hist = fin
+        cabi.check(cabi.lib().nbm_reduce_allreduce_finalize_f32(
+            C.byref(o), C.byref(net), cabi.ptr(partials), rows, np1, self.rank, self.world, self.blocks,
+            cabi.ptr(self.step), cabi.ptr(out), cabi.ptr(params), cabi.ptr(state), cabi.ptr(count), cabi.ptr(hist),
+            cabi.stream_ptr()), "nbm_reduce_allreduce_finalize_f32")
+        return out
+
     def error(self) -> int:
         return int(cabi.lib().nbm_comm_error(self.local))
 
@@ -91,6 +101,15 @@ class LocalPeerComm:
             cabi.check(cabi.lib().nbm_reduce_allreduce_f32(cabi.ptr(partials), rows, np1, self.rank, p.world, p.blocks,
                                                            cabi.ptr(p.steps[self.rank]), cabi.ptr(out),
                                                            cabi.stream_ptr()), "nbm_reduce_allreduce_f32")
+            return out
+
+        def reduce_allreduce_finalize(self, partials, rows, np1, out, fin):
+            p = self.parent
+            o, net, params, state, count, hist = fin
+            cabi.check(cabi.lib().nbm_reduce_allreduce_finalize_f32(
+                C.byref(o), C.byref(net), cabi.ptr(partials), rows, np1, self.rank, p.world, p.blocks,
+                cabi.ptr(p.steps[self.rank]), cabi.ptr(out), cabi.ptr(params), cabi.ptr(state), cabi.ptr(count),
+                cabi.ptr(hist), cabi.stream_ptr()), "nbm_reduce_allreduce_finalize_f32")
             return out
 
     def __init__(self, devices):

@@ -2407,7 +2407,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // `timeout_ns` == 0: wait for the peers without a bound (what NCCL does).  Otherwise a rank that has waited that long
 // sets the block's error word and poisons ITS output with NaN - never a plausible-looking partial sum; the host turns
 // the error word into an exception (Trainer._check_comm, bench.py).
-__global__ void __launch_bounds__(1024) reduce_allreduce_kernel(const float* __restrict__ partials, int rows, int np1,
+__device__ __forceinline__ void reduce_allreduce_body(const float* __restrict__ partials, int rows, int np1,
                                                                 int rank, int world, CommPeers peers,
                                                                 int32_t* __restrict__ step_dev, float* __restrict__ out,
                                                                 unsigned long long timeout_ns) {
@@ -2457,6 +2457,27 @@ __global__ void __launch_bounds__(1024) reduce_allreduce_kernel(const float* __r
     }
     __syncthreads();
     if (t == 0) *step_dev = (int32_t)(step + 1);
+}
+
+__global__ void __launch_bounds__(1024) reduce_allreduce_kernel(const float* __restrict__ partials, int rows, int np1,
+                                                                int rank, int world, CommPeers peers,
+                                                                int32_t* __restrict__ step_dev, float* __restrict__ out,
+                                                                unsigned long long timeout_ns) {
+    reduce_allreduce_body(partials, rows, np1, rank, world, peers, step_dev, out, timeout_ns);
+}
+
+// K4 on several GPUs as ONE kernel: partial rows -> exchange over peer memory -> optax chain -> staged parameter copies
+// (reduce_allreduce_kernel followed by finalize_step_kernel's tail: one launch and one kernel boundary less per step)
+__global__ void __launch_bounds__(1024) reduce_allreduce_finalize_kernel(
+    const float* __restrict__ partials, int rows, int np1, int rank, int world, CommPeers peers, int32_t* __restrict__ step_dev,
+    float* __restrict__ loss_grad, unsigned long long timeout_ns, nbm_optimizer_t o, nbm_net_t net, int n_net,
+    float* __restrict__ params, float* __restrict__ state, int32_t* __restrict__ count, float* __restrict__ loss_hist,
+    float* __restrict__ stage) {
+    reduce_allreduce_body(partials, rows, np1, rank, world, peers, step_dev, loss_grad, timeout_ns);
+    __syncthreads();
+    optax_update(o, loss_grad, params, state, count, loss_hist);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_net; i += blockDim.x) stage_param(net, i, params[i], stage);
 }
 
 static int g_sm_count = 0;
@@ -3152,6 +3173,35 @@ int nbm_reduce_allreduce_f32(const float* partials, int rows, int np1, int rank,
     reduce_allreduce_kernel<<<1, threads, sizeof(float) * (size_t)ngrp * np1, as_stream(stream)>>>(
         partials, rows, np1, rank, world, peers, step_dev, out, g_comm_timeout_ns);
     NBM_LAUNCH_CHECK("reduce_allreduce");
+    return NBM_OK;
+}
+
+int nbm_reduce_allreduce_finalize_f32(const nbm_optimizer_t* opt, const nbm_net_t* net, const float* partials, int rows,
+                                      int np1, int rank, int world, void* const* blocks_host, int32_t* step_dev,
+                                      float* loss_grad, float* params, float* state, int32_t* count, float* loss_hist,
+                                      nbm_stream_t stream) {
+    NBM_REQUIRE(opt && net && partials && blocks_host && step_dev && loss_grad && params && state && count, "null pointer");
+    NBM_REQUIRE(opt->n_params > 0 && opt->n_params <= NBM_MAXP, "bad parameter count");
+    if (opt->optimizer < 0 || opt->optimizer > 2 || opt->scheduler < 0 || opt->scheduler > 1) {
+        set_error("unknown optimizer id %d", opt->optimizer);
+        return NBM_ERR_UNSUPPORTED;
+    }
+    const int n_net = nbm_net_num_params(net);
+    NBM_REQUIRE(n_net > 0 && n_net <= opt->n_params, "the optimizer must cover at least the network's parameters");
+    NBM_REQUIRE(rows > 0 && np1 == opt->n_params + 1 && np1 <= 1024, "partial rows must be n_params + 1 <= 1024 floats wide");
+    NBM_REQUIRE(world >= 1 && world <= NBM_COMM_MAX_RANKS && rank >= 0 && rank < world, "bad rank/world");
+    CommPeers peers;
+    for (int r = 0; r < NBM_COMM_MAX_RANKS; ++r) peers.b[r] = r < world ? reinterpret_cast<CommBlock*>(blocks_host[r]) : nullptr;
+    for (int r = 0; r < world; ++r) NBM_REQUIRE(peers.b[r], "null peer block");
+    float* stage = nullptr;
+    int rc = cuda_check(cudaGetSymbolAddress((void**)&stage, g_stage), "staging buffer");
+    if (rc) return rc;
+    const int threads = 1024;
+    const int ngrp = threads / np1 > 0 ? threads / np1 : 1;
+    reduce_allreduce_finalize_kernel<<<1, threads, sizeof(float) * (size_t)ngrp * np1, as_stream(stream)>>>(
+        partials, rows, np1, rank, world, peers, step_dev, loss_grad, g_comm_timeout_ns, *opt, *net, n_net, params, state, count,
+        loss_hist, stage);
+    NBM_LAUNCH_CHECK("reduce_allreduce_finalize");
     return NBM_OK;
 }
 

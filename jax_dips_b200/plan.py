@@ -661,7 +661,7 @@ class SharedPlan:
             for name in ("tri", "tri_area", "pos", "proj", "Cm", "Cp"):
                 pass  # kept: tests read them back; they are O(crossed sites)
 
-    def loss_grad_launch(self, out: Optional[torch.Tensor] = None, comm=None) -> torch.Tensor:
+    def loss_grad_launch(self, out: Optional[torch.Tensor] = None, comm=None, finalize=None) -> torch.Tensor:
         """Enqueue loss and d loss/d params for this plan's rows (parameters must have been uploaded
         with `upload_params`).  Returns the device buffer [grad(P), loss].  With `comm` (a PeerComm) the
         final partial-row reduction is fused with the all-reduce over the ranks (SUM, psum semantics)."""
@@ -678,7 +678,10 @@ class SharedPlan:
                        "nbm_loss_grad_shared_f32")
         finally:
             self.step.stages = 0
-        comm.reduce_allreduce(self.partials, self.step.n_partial_rows, self.n_total + 1, target)
+        if finalize is not None:   # exchange + optax chain + staging of the next step's parameters in one kernel
+            comm.reduce_allreduce_finalize(self.partials, self.step.n_partial_rows, self.n_total + 1, target, finalize)
+        else:
+            comm.reduce_allreduce(self.partials, self.step.n_partial_rows, self.n_total + 1, target)
         return target
 
     def bind_params(self, params: torch.Tensor) -> None:
@@ -703,6 +706,48 @@ class SharedPlan:
         """lattice-layout array -> (n_points,) in the reference's point order"""
         ex, ey, ez = self.dims
         return t.view(ex, ey, ez)[self.HX:ex - self.HX, self.HY:ey - self.HY, self.HZ:ez - self.hz_hi].reshape(-1)
+
+
+def balanced_slabs(lvl, tr_gstate, world: int, device=None, list_weight: Optional[float] = None):
+    """Cost-weighted x-slab boundaries for `world` devices: [(xa, xb)] contiguous, covering every x plane.
+
+    The reference gives every device the same number of planes (data_management.py:121-130).  A plane that holds
+    interface costs more than one that does not (crossed sites and irregular rows run through the list kernels), so with
+    equal slabs the interface-holding ranks set the pace.  The per-plane cost here is Ny*Nz + list_weight * (number of
+    nodes of the plane with a 6-neighbour on the other side of the level set), evaluated with the plan's own level set;
+    boundaries sit at the quantiles of its prefix sum.  Any contiguous partition gives the same [grad, loss] when every
+    device normalises by the nominal N / world (`SharedPlan(n_mean=...)`): psum of per-device means with a common
+    denominator is a sum over all points (trainer.py:829-830)."""
+    Nx, Ny, Nz = tr_gstate.shape()
+    if world <= 1:
+        return [(0, Nx)]
+    if list_weight is None:
+        list_weight = float(os.environ.get("NBM_BALANCE_W", "10"))
+    dev = torch.device(device if device is not None else lvl.device)
+    ys, zs = tr_gstate.y.to(dev), tr_gstate.z.to(dev)
+    Y, Z = torch.meshgrid(ys, zs, indexing="ij")
+    Y, Z = Y.reshape(-1), Z.reshape(-1)
+    sign = torch.empty((Nx, Ny, Nz), dtype=torch.bool, device=dev)
+    for i in range(Nx):
+        pts = torch.stack((torch.full_like(Y, float(tr_gstate.x[i])), Y, Z), dim=1)
+        sign[i] = (lvl(pts) >= 0).view(Ny, Nz)
+    ch = torch.zeros((Nx, Ny, Nz), dtype=torch.bool, device=dev)
+    for ax in range(3):
+        a = sign.narrow(ax, 0, sign.shape[ax] - 1) != sign.narrow(ax, 1, sign.shape[ax] - 1)
+        ch.narrow(ax, 0, sign.shape[ax] - 1).logical_or_(a)
+        ch.narrow(ax, 1, sign.shape[ax] - 1).logical_or_(a)
+    cost = (Ny * Nz + list_weight * ch.view(Nx, -1).sum(dim=1).double()).cpu()
+    cum = torch.cumsum(cost, 0)
+    total = float(cum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        # first plane index whose inclusion reaches r/world of the total cost; every slab keeps at least one plane
+        k = int(torch.searchsorted(cum, torch.tensor(total * r / world, dtype=cum.dtype)).item()) + 1
+        k = max(k, cuts[-1] + 1)
+        k = min(k, Nx - (world - r))
+        cuts.append(k)
+    cuts.append(Nx)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
 def upload_params(net: NetShape, params: torch.Tensor) -> None:
@@ -884,10 +929,12 @@ class EmptyPlan:
     def bind_params(self, params: torch.Tensor) -> None:
         pass
 
-    def loss_grad_launch(self, out: Optional[torch.Tensor] = None, comm=None) -> torch.Tensor:
+    def loss_grad_launch(self, out: Optional[torch.Tensor] = None, comm=None, finalize=None) -> torch.Tensor:
         target = out if out is not None else self.loss_grad
         if comm is None:
             target.zero_()
+        elif finalize is not None:
+            comm.reduce_allreduce_finalize(self._partials, 1, self.n_total + 1, target, finalize)
         else:
             comm.reduce_allreduce(self._partials, 1, self.n_total + 1, target)
         return target

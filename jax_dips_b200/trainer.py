@@ -293,8 +293,10 @@ class Trainer:
     # ------------------------------------------------------------------------------------------
     # plans: one per (zoom level, batch range); built lazily, kept in HBM
     # ------------------------------------------------------------------------------------------
-    def plan_for(self, zoom: int, p0: int, p1: int):
-        key = (zoom, p0, p1)
+    def plan_for(self, zoom: int, p0: int, p1: int, n_mean: Optional[int] = None):
+        """`n_mean`: number of points the mean of the loss runs over when it is not the batch's own size (cost-balanced
+        slabs of the multi-GPU loops: every device divides by the nominal per-device batch size)"""
+        key = (zoom, p0, p1, n_mean)
         if key in self._plans:
             return self._plans[key]
         Nx, Ny, Nz = self.tr_gstate.shape()
@@ -304,13 +306,35 @@ class Trainer:
                 pl = EmptyPlan(self.n_params, self.device)
             elif zoom == 0 and p0 % plane == 0 and p1 % plane == 0:
                 pl = SharedPlan(self.lvl, self.tr_gstate, p0 // plane, p1 // plane, self.sim_state_fn, self.net,
-                                self.nonlinear_m, self.nonlinear_p, device=self.device, precond=self.precond)
+                                self.nonlinear_m, self.nonlinear_p, device=self.device, precond=self.precond,
+                                n_mean=n_mean)
                 pl.bind_params(self.params)
             else:
+                if n_mean is not None:
+                    raise ValueError("n_mean is a property of whole-plane batches on the shared path")
                 pl = PointsPlan(self.general_level(zoom), p0, p1)
                 pl.bind_params(self.params)
         self._plans[key] = pl
         return pl
+
+    def _device_ranges(self, DD, world: int):
+        """per device the list of (p0, p1, n_mean) batches.  The reference's partition (contiguous equal blocks,
+        data_management.py:121-130) unless every device holds ONE batch of whole x planes and no preconditioner is
+        trained: then the slab boundaries are cost-weighted (`plan.balanced_slabs`; NBM_BALANCE_SLABS=0 keeps equal
+        slabs) and every device divides by the nominal batch size, which leaves the summed [grad, loss] unchanged."""
+        plane = self.tr_gstate.shape()[1] * self.tr_gstate.shape()[2]
+        ref = [[(p0, p1, None) for (p0, p1) in DD.ranges(r)] for r in range(world)]
+        one_batch = all(len(rr) == 1 and rr[0][1] > rr[0][0] and rr[0][0] % plane == 0 and rr[0][1] % plane == 0 for rr in ref)
+        whole = sum(rr[0][1] - rr[0][0] for rr in ref) == self.tr_gstate.num_points() if one_batch else False
+        if (world > 1 and one_batch and whole and self.precond is None
+                and os.environ.get("NBM_BALANCE_SLABS", "1") != "0"):
+            from .plan import balanced_slabs
+            n_nom = ref[0][0][1] - ref[0][0][0]
+            if all(rr[0][1] - rr[0][0] == n_nom for rr in ref):
+                with torch.cuda.device(self.device):
+                    slabs = balanced_slabs(self.lvl, self.tr_gstate, world, device=self.device)
+                return [[(xa * plane, xb * plane, n_nom)] for (xa, xb) in slabs]
+        return ref
 
     def general_level(self, zoom: int) -> GeneralLevel:
         if zoom not in self._levels:
@@ -354,12 +378,16 @@ class Trainer:
         net = self.net.struct()
         partials, rows = None, 0
         d = _dist() if allreduce else None
+        # (peer exchange: partial rows -> psum over NVLink peer memory -> optax chain -> staging is ONE kernel)
+        fin = (self._optimizer_struct(), net, self.params, self.opt_state, self.opt_count, loss_hist)
         if local_comm is not None:
-            lg = plan.loss_grad_launch(comm=local_comm)
+            plan.loss_grad_launch(comm=local_comm, finalize=fin)
+            return
         elif d is not None and d.get_world_size() > 1:
             comm = self._peer_comm() if (self.allreduce_kind == "peer" and isinstance(plan, (SharedPlan, EmptyPlan))) else None
             if comm is not None:
-                lg = plan.loss_grad_launch(comm=comm)    # reduction fused with the psum over NVLink peer memory
+                plan.loss_grad_launch(comm=comm, finalize=fin)
+                return
             else:
                 lg = plan.loss_grad_launch()
                 d.all_reduce(lg, op=d.ReduceOp.SUM)      # psum of grads and loss (:829-830)
@@ -559,12 +587,13 @@ class Trainer:
         DD = data_management.DatasetDict(num_points=self.tr_gstate.num_points(), batch_size=world * self.batch_size,
                                          num_gpus=world)
         self._warn_if_padded(DD)
-        ranges = DD.ranges(rank)
+        all_ranges = self._device_ranges(DD, world)
+        ranges = all_ranges[rank]
         nb = len(ranges)
         # every rank must pick the same exchange for the same batch: the fused peer kernel serves whole-plane batches
         # (shared path) only
         plane = self.tr_gstate.shape()[1] * self.tr_gstate.shape()[2]
-        if not all(p0 % plane == 0 and p1 % plane == 0 for r in range(world) for (p0, p1) in DD.ranges(r) if p1 > p0):
+        if not all(p0 % plane == 0 and p1 % plane == 0 for rr in all_ranges for (p0, p1, _) in rr if p1 > p0):
             self.allreduce_kind = "nccl"
         loss_epochs, epoch_store = [], []
         t0 = time.time()
@@ -572,7 +601,7 @@ class Trainer:
         with torch.cuda.device(self.device):
             # every plan of an epoch is built BEFORE the first exchange (set-up cost differs a lot between ranks: the
             # interface may lie in a few slabs only), then the ranks meet at a barrier
-            plans = [self.plan_for(0, p0, p1) for (p0, p1) in ranges]
+            plans = [self.plan_for(0, p0, p1, n_mean) for (p0, p1, n_mean) in ranges]
             if d is not None and world > 1:
                 if self.allreduce_kind == "peer":
                     self._peer_comm()
@@ -654,7 +683,8 @@ class Trainer:
                 t.opt_state.copy_(self.opt_state.to(t.device))
                 t.opt_count.copy_(self.opt_count.to(t.device))
         comm = LocalPeerComm([t.device for t in reps])
-        nb = len(DD.ranges(0))
+        dev_ranges = self._device_ranges(DD, n_dev)
+        nb = len(dev_ranges[0])
         n_steps = (self.num_epochs - self.epoch_start) * nb
         base = int(self.opt_count.item())
         hists, plans, graphs = [], [], []
@@ -662,7 +692,7 @@ class Trainer:
             with torch.cuda.device(t.device):
                 t._begin_training()
                 hists.append(torch.zeros(n_steps + 1, dtype=torch.float32, device=t.device))
-                plans.append([t.plan_for(0, p0, p1) for (p0, p1) in DD.ranges(r)])
+                plans.append([t.plan_for(0, p0, p1, n_mean) for (p0, p1, n_mean) in dev_ranges[r]])
                 torch.cuda.synchronize(t.device)
         per_step = [] if base != 0 else None
 

@@ -279,3 +279,26 @@ def test_cabi_argument_validation_without_a_gpu():
     assert L.nbm_upload_params(C.byref(net), None, None) == 1
     with pytest.raises(cabi.NbmError):
         cabi.check(L.nbm_assemble_f32(None, None), "nbm_assemble_f32")
+
+
+def test_balanced_slabs_cover_the_grid_and_relieve_interface_planes():
+    """plan.balanced_slabs: contiguous cover of every x plane, at least one plane per device, and fewer planes for the
+    devices whose slab holds the interface (sphere of radius 0.5 in [-1, 1]^3: the middle half of the x range)."""
+    from jax_dips_b200 import plan as nplan
+    tr = mesh.linspace_grid((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0), [32, 16, 16])
+    phi = lambda pts: pts.norm(dim=1) - 0.5
+    assert nplan.balanced_slabs(phi, tr, 1, device="cpu") == [(0, 32)]
+    for world in (2, 4, 8):
+        slabs = nplan.balanced_slabs(phi, tr, world, device="cpu", list_weight=10.0)
+        assert slabs[0][0] == 0 and slabs[-1][1] == 32 and len(slabs) == world
+        assert all(slabs[r][1] == slabs[r + 1][0] for r in range(world - 1))
+        assert all(b > a for a, b in slabs)
+    s8 = nplan.balanced_slabs(phi, tr, 8, device="cpu", list_weight=10.0)
+    n = [b - a for a, b in s8]
+    assert n[0] > n[3] and n[7] > n[4], n          # interface-free end slabs take more planes
+    # without a list weight the planes all cost the same: the reference's equal blocks
+    assert nplan.balanced_slabs(phi, tr, 4, device="cpu", list_weight=0.0) == [(0, 8), (8, 16), (16, 24), (24, 32)]
+    # more devices than interface-free planes still leaves one plane each
+    tiny = mesh.linspace_grid((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0), [8, 8, 8])
+    s = nplan.balanced_slabs(phi, tiny, 8, device="cpu")
+    assert [b - a for a, b in s] == [1] * 8
