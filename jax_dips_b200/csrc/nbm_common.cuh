@@ -28,6 +28,33 @@ int cuda_check(cudaError_t e, const char* what);
 static inline cudaStream_t as_stream(nbm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched with `launch_pdl` may have its CTAs placed while the previous
+// kernel of the stream is still draining; it must call pdl_wait() before it touches global memory (the wait returns
+// when the previous kernel has completed and its writes are visible).  pdl_trigger() lets the NEXT kernel start that
+// early placement.  Without a programmatic edge both are no-ops.  The launch attribute is opt-in (NBM_PDL=1): it measured no gain, see pdl_enabled().
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // a14: phi from the ghosted lvl grid.  Follows interpolate.py:946-956 (cell index with the
 // `i<=1 -> 2` clamp, so the first interior cell extrapolates from its neighbour), :1001-1009
 // (trilinear) and :485-565 (non-oscillatory quadratic correction, un-normalised second

@@ -127,6 +127,8 @@ stencil_tma_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Ge
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_trigger();
+    pdl_wait();      // (programmatic launch: U of the forward kernel is complete from here on)
     __syncthreads();
 
     if (tid >= kConsumers) {
@@ -515,8 +517,9 @@ static int launch_t(const nbm_shared_step_t& s, int sms, cudaStream_t st) {
         configured |= 1ull << (dev & 63);
     }
     const int grid = g.ny_t * g.nz_t * g.nxc;
-    stencil_tma_kernel<KV, NL><<<grid, g.n_main + g.n_halo + 32, smem_bytes<KV, NL>(g), st>>>(cache.maps, g, s);
-    return 0;
+    cudaError_t le = launch_pdl(stencil_tma_kernel<KV, NL>, dim3(grid), dim3(g.n_main + g.n_halo + 32), smem_bytes<KV, NL>(g), st,
+                                cache.maps, g, s);
+    return le == cudaSuccess ? 0 : cuda_check(le, "stencil_tma launch");
 }
 
 // applicable: faces table, 16-byte lattice rows and array bases

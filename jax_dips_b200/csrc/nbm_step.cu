@@ -722,6 +722,7 @@ __device__ __forceinline__ void fwd_task(const NodeView& v, const int plane, con
 
 template <class NET, bool GENERAL, bool STASH = false>
 __global__ void __launch_bounds__(kThreads, 3) fwd_nodes_kernel(NodeView v, Tasks T) {
+    pdl_trigger();
     // balanced contiguous runs: the (replica, strip, x plane) triples in that order are cut into gridDim.x * T.split equal
     // ranges dealt round-robin, so every CTA does the same number of plane iterations (+-1) and a thread keeps its
     // (y, z) for a long x march
@@ -746,6 +747,7 @@ __global__ void __launch_bounds__(kThreads, 3) fwd_nodes_kernel(NodeView v, Task
 // A2: E[c] = sum_q B[c][q] U[node_c + off_q] + B[c][27]   (discretization.py:464-513); clears gE
 // (thread per crossed site; a warp-per-site variant with a shuffle reduction measured 14.9 us against 8.4 us)
 __global__ void extrap_kernel(nbm_shared_step_t s) {
+    pdl_trigger();
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= s.n_crossed) return;
     int64_t e = s.c_node[c];
@@ -1167,6 +1169,7 @@ __global__ void irregular_bwd_kernel(nbm_shared_step_t s, bool nl_center) {
 
 // C0b: adjoint of the extrapolation: G[node_c + off_q] += B[c][q] gE[c]
 __global__ void extrap_bwd_kernel(nbm_shared_step_t s, float* __restrict__ Gt) {
+    pdl_wait();
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t c = t / 27;
     int q = (int)(t - c * 27);
@@ -1182,6 +1185,8 @@ __global__ void extrap_bwd_kernel(nbm_shared_step_t s, float* __restrict__ Gt) {
 // An irregular row forward AND backward in one thread: the row needs only U and E, its residual stays in the compact
 // array Rq (the dense kernel owns R while this runs), its adjoint goes into gE and into the side buffer G2.
 __global__ void irregular_fb_kernel(nbm_shared_step_t s) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= s.n_irr) return;
     const int64_t e = s.irr_point[q];
@@ -1237,6 +1242,7 @@ __global__ void irregular_fb_kernel(nbm_shared_step_t s) {
 
 // join of the list chain: G += G2 on the nodes the lists can reach (G2 re-zeroed), R <- Rq on the irregular rows
 __global__ void merge_lists_kernel(nbm_shared_step_t s) {
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < s.n_list) {
         const int64_t n = s.list_nodes[i];
@@ -1312,6 +1318,8 @@ __global__ void __launch_bounds__(kGradThreads, 1) node_grad_kernel(NodeView v, 
     float loss = 0.0f;
     const bool par = (threadIdx.x & 1) != 0;
     const float* R = v.R;  // only the shared path (one replica) accumulates the loss here
+    pdl_trigger();
+    pdl_wait();            // (programmatic launch: G, R of the previous kernel are complete from here on)
     // balanced contiguous runs of (replica, strip, x plane) triples (see fwd_nodes_kernel)
     const int nx = v.x_end - v.x_begin;
     const int64_t per_rep = (int64_t)T.mblocks * nx, total = per_rep * v.nrep;
@@ -1460,8 +1468,7 @@ static cudaError_t launch_node_grad(dim3 grid, const NodeView& v, const Tasks& T
         if (e != cudaSuccess) return e;
         configured |= 1ull << (dev & 63);
     }
-    node_grad_kernel<NET, GENERAL, STASH><<<grid, kGradThreads, bytes, st>>>(v, T);
-    return cudaSuccess;
+    return launch_pdl(node_grad_kernel<NET, GENERAL, STASH>, grid, dim3(kGradThreads), (size_t)bytes, st, v, T);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2298,6 +2305,7 @@ __global__ void __launch_bounds__(1024) finalize_step_kernel(nbm_optimizer_t o, 
                                                              float* __restrict__ loss_hist, float* __restrict__ stage) {
     extern __shared__ float sred[];   // [ngrp][np1]
     const int t = threadIdx.x;
+    pdl_wait();
     if (partials) {
         const int ngrp = max(1, (int)blockDim.x / np1);
         const int grp = t / np1, col = t - grp * np1;
@@ -2413,6 +2421,7 @@ __device__ __forceinline__ void reduce_allreduce_body(const float* __restrict__ 
                                                                 unsigned long long timeout_ns) {
     extern __shared__ float sred[];   // [ngrp][np1]
     const int t = threadIdx.x;
+    pdl_wait();
     const unsigned int step = (unsigned int)*step_dev;
     const int par = step & 1;
     CommBlock* mine = peers.b[rank];
@@ -2491,6 +2500,14 @@ static int sm_count() {
     return g_sm_count;
 }
 
+bool pdl_enabled() {
+    // opt-in (NBM_PDL=1).  Measured on B200 with the step as a CUDA graph: 256^3 625.7 us with, 622.8 without;
+    // 128^3 119.7 / 120.6; 64^3 47.3 / 47.7 - the graph's kernel-to-kernel edges are already that cheap, and CTAs of
+    // the next kernel placed during the last wave of the previous one take its resources.
+    static const bool on = getenv("NBM_PDL") && getenv("NBM_PDL")[0] == '1';
+    return on;
+}
+
 // library-owned side stream + fork/join events of the list chain, one set per device (created on first use)
 struct SideLane {
     cudaStream_t stream = nullptr;
@@ -2506,7 +2523,8 @@ static SideLane* side_lane() {
     if (!l.stream) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);   // (hi = numerically lowest = highest priority)
-        if (cudaStreamCreateWithPriority(&l.stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        const char* pe = getenv("NBM_SIDE_PRIO");     // timing experiments: "low" = lowest priority
+        if (cudaStreamCreateWithPriority(&l.stream, cudaStreamNonBlocking, (pe && pe[0] == 'l') ? lo : hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming) != cudaSuccess) {
             l.stream = nullptr;
@@ -2574,18 +2592,22 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     if (overlap) {
         SideLane* lane = side_lane();
         if (!lane) return cuda_check(cudaGetLastError(), "side stream of the list chain");
+        static const int dbg_skip = getenv("NBM_OV_SKIP") ? atoi(getenv("NBM_OV_SKIP")) : 0;   // timing experiments only
         cudaEventRecord(lane->fork, st);
         cudaStreamWaitEvent(lane->stream, lane->fork, 0);
+        if (!(dbg_skip & 1)) {
         if (s.n_crossed > 0) extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, lane->stream>>>(s);
-        if (s.n_irr > 0) irregular_fb_kernel<<<(unsigned)((s.n_irr + 127) / 128), 128, 0, lane->stream>>>(s);
+        if (s.n_irr > 0)
+            launch_pdl(irregular_fb_kernel, dim3((unsigned)((s.n_irr + 127) / 128)), dim3(128), 0, lane->stream, s);
         if (s.n_crossed > 0)
-            extrap_bwd_kernel<<<(unsigned)((s.n_crossed * 27 + 127) / 128), 128, 0, lane->stream>>>(s, s.G2);
+            launch_pdl(extrap_bwd_kernel, dim3((unsigned)((s.n_crossed * 27 + 127) / 128)), dim3(128), 0, lane->stream, s, s.G2);
+        }
         cudaEventRecord(lane->join, lane->stream);
         int rc = stencil_tma::launch(s, sms, st);
         if (rc) return rc;
         cudaStreamWaitEvent(st, lane->join, 0);
         const int64_t nm = s.n_list > s.n_irr ? s.n_list : s.n_irr;
-        merge_lists_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(s);
+        if (!(dbg_skip & 2)) merge_lists_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(s);
     }
     if (!overlap && (stages & NBM_STAGE_EXTRAP) && lists_on && s.n_crossed > 0)
         extrap_kernel<<<(unsigned)((s.n_crossed + 127) / 128), 128, 0, st>>>(s);
@@ -3170,8 +3192,9 @@ int nbm_reduce_allreduce_f32(const float* partials, int rows, int np1, int rank,
     const int threads = 1024;   // np1 <= 1025 columns... one column per thread in the last phase needs np1 <= 1024
     NBM_REQUIRE(np1 <= 1024, "np1 must be <= 1024");
     const int ngrp = threads / np1 > 0 ? threads / np1 : 1;
-    reduce_allreduce_kernel<<<1, threads, sizeof(float) * (size_t)ngrp * np1, as_stream(stream)>>>(
-        partials, rows, np1, rank, world, peers, step_dev, out, g_comm_timeout_ns);
+    cudaError_t le = launch_pdl(reduce_allreduce_kernel, dim3(1), dim3(threads), sizeof(float) * (size_t)ngrp * np1, as_stream(stream),
+                                partials, rows, np1, rank, world, peers, step_dev, out, g_comm_timeout_ns);
+    if (le != cudaSuccess) return cuda_check(le, "reduce_allreduce launch");
     NBM_LAUNCH_CHECK("reduce_allreduce");
     return NBM_OK;
 }
@@ -3198,9 +3221,10 @@ int nbm_reduce_allreduce_finalize_f32(const nbm_optimizer_t* opt, const nbm_net_
     if (rc) return rc;
     const int threads = 1024;
     const int ngrp = threads / np1 > 0 ? threads / np1 : 1;
-    reduce_allreduce_finalize_kernel<<<1, threads, sizeof(float) * (size_t)ngrp * np1, as_stream(stream)>>>(
-        partials, rows, np1, rank, world, peers, step_dev, loss_grad, g_comm_timeout_ns, *opt, *net, n_net, params, state, count,
-        loss_hist, stage);
+    cudaError_t le = launch_pdl(reduce_allreduce_finalize_kernel, dim3(1), dim3(threads), sizeof(float) * (size_t)ngrp * np1,
+                                as_stream(stream), partials, rows, np1, rank, world, peers, step_dev, loss_grad, g_comm_timeout_ns,
+                                *opt, *net, n_net, params, state, count, loss_hist, stage);
+    if (le != cudaSuccess) return cuda_check(le, "reduce_allreduce_finalize launch");
     NBM_LAUNCH_CHECK("reduce_allreduce_finalize");
     return NBM_OK;
 }
@@ -3237,8 +3261,10 @@ int nbm_finalize_step_f32(const nbm_optimizer_t* opt, const nbm_net_t* net, cons
     if (rc) return rc;
     const int threads = 1024;
     const int ngrp = partials ? (threads / row_stride > 0 ? threads / row_stride : 1) : 0;
-    finalize_step_kernel<<<1, threads, sizeof(float) * (size_t)ngrp * (partials ? row_stride : 0), st>>>(
-        *opt, *net, n_net, partials, rows, row_stride, loss_grad, params, state, count, loss_hist, stage);
+    cudaError_t le = launch_pdl(finalize_step_kernel, dim3(1), dim3(threads),
+                                sizeof(float) * (size_t)ngrp * (partials ? row_stride : 0), st, *opt, *net, n_net, partials, rows,
+                                row_stride, loss_grad, params, state, count, loss_hist, stage);
+    if (le != cudaSuccess) return cuda_check(le, "finalize_step launch");
     NBM_LAUNCH_CHECK("finalize_step");
     return NBM_OK;
 }
