@@ -36,10 +36,10 @@ F_GRAD = 0.93e3       # FLOP per lattice node for the dominant kernel (forward r
 B_STEP_FACES = 52.0
 B_STEP_ROWS = 76.0
 B_STEP_TMA = 36.0        # fused residual + adjoint: U, 3 face coefficients, 1/diag, rhs read once; R and G written
-# DRAM bytes (read + write) of one node_grad launch at 256^3, `ncu --set full` (profiles/r1_ncu_summary.md)
-NODE_GRAD_TRAFFIC_256 = 160527360
+# DRAM bytes (read + write) of one node_grad launch at 256^3, `ncu --set full` (profiles/r2s_ncu_summary.md)
+NODE_GRAD_TRAFFIC_256 = 160883968
 NODE_GRAD_TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one node_grad launch at sphere 256^3, "
-                            "`ncu --set full` capture profiles/r1d_ncu_full_raw.csv (not re-measured in this run)")
+                            "`ncu --set full` capture profiles/r2s_ncu_full_raw.csv (not re-measured in this run)")
 FP32_NOMINAL = 74.5                  # TFLOP/s: 148 SM x 128 lanes x 2 x 1.965 GHz
 
 
@@ -356,6 +356,16 @@ def main():
             return graph
 
         def _step(self, staged):
+            if staged:
+                return self._step_device(True)
+            # the e2e leg: the host owns the parameters.  Pinned host -> device, the step, [grad, loss] and the updated
+            # parameters device -> pinned host; captured, the three copies are memcpy nodes of the step's graph
+            params.copy_(h_params, non_blocking=True)
+            self._step_device(False)
+            h_out.copy_(self.lg, non_blocking=True)
+            h_params.copy_(params, non_blocking=True)   # the host keeps the parameters: next step's input
+
+        def _step_device(self, staged):
             p = self.p
             if staged:   # device-resident training: the previous step staged the parameter copies
                 cabi.check(L.nbm_upload_staged_params(cabi.stream_ptr()), "nbm_upload_staged_params")
@@ -423,6 +433,10 @@ def main():
     if table_mb <= 1.25 * L2_MB and not args.no_flush:
         flush_buf = torch.empty(int(2 * L2_MB * 1e6) // 4, dtype=torch.float32, device=dev)
 
+    # pinned host buffers of the e2e leg (allocated before any capture: the graph's memcpy nodes hold their addresses)
+    h_params = params.detach().cpu().pin_memory()
+    h_out = torch.empty(P + 1).pin_memory()
+
     reset_state()
     st = Stepper(pl)
     used_graph = st.graph_dev is not None
@@ -488,14 +502,10 @@ def main():
     # constant-bank upload + all kernels), then [grad, loss] and the updated parameters back to pinned host memory and a
     # stream synchronize (what a host framework that owns the parameters sees).  The grids and row tables are
     # per-level state, resident like the reference's jit constants.
-    h_params = params.detach().cpu().pin_memory()
-    h_out = torch.empty(P + 1).pin_memory()
+    h_params.copy_(params)
 
     def e2e_step():
-        params.copy_(h_params, non_blocking=True)
-        st.step_host_params()
-        h_out.copy_(lg, non_blocking=True)
-        h_params.copy_(params, non_blocking=True)   # the host keeps the parameters: next step's input
+        st.step_host_params()          # H2D + step + 2 x D2H (one graph launch when the step is captured)
         torch.cuda.current_stream().synchronize()
 
     ms_e2e = st.time(e2e_step, args.steps, 2)
@@ -503,7 +513,7 @@ def main():
            "h2d_bytes_per_step": int(h_params.numel() * 4),
            "d2h_bytes_per_step": int((P + 1) * 4 + P * 4),
            "what": "parameter vector H2D from pinned memory, step through the C ABI, [grad, loss] and updated "
-                   "parameters D2H, stream sync, every step"}
+                   "parameters D2H, stream sync, every step (the copies are memcpy nodes of the step's CUDA graph)"}
 
     # ---------------- secondary: weak scaling (the same per-GPU slab at every N) ---------------
     weak = None

@@ -2569,8 +2569,12 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     // K_B: residual rows + adjoint stencil of the faces table as one TMA-fed kernel whenever both stages are wanted and
     // nothing sits between them (the preconditioner rescales R; the r1 fused gradient kernel wants S)
     const int dense2 = NBM_STAGE_RESIDUAL | NBM_STAGE_ADJOINT;
-    const bool fusedA = s.stencil_tma >= 0 && s.faces && !pc && !s.S && !(s.nl && s.g_ptr) && ((stages & dense2) == dense2) &&
+    // (not with a nonlinear operator: sinh / cosh per cell on the one-barrier-per-plane critical path of the TMA kernel
+    // measured 510 us at Poisson-Boltzmann 256^3 against 127 + 131 us for the two separate kernels)
+    const bool fusedA = s.stencil_tma >= 0 && s.faces && !pc && !s.S && !s.nl && ((stages & dense2) == dense2) &&
                         stencil_tma::applicable(s);
+    // the two separate face-table kernels can take the list chain beside them just as well
+    const bool sepA = !fusedA && s.faces && !pc && !s.S && ((stages & dense2) == dense2);
     // timing modifiers: run only the dense kernels / only the list kernels of the selected stages
     const bool lists_on = !(stages & NBM_STAGE_NO_LISTS), dense_on = !(stages & NBM_STAGE_NO_DENSE);
     if (dense_on && (stages & NBM_STAGE_FWD)) {
@@ -2587,7 +2591,7 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
     }
     // the list chain beside the dense stencil (see nbm_shared_step_t.G2): whole-step launches only
     const int chain = NBM_STAGE_EXTRAP | dense2;
-    const bool overlap = fusedA && lists_on && dense_on && ((stages & chain) == chain) && s.G2 && s.Rq && s.list_nodes &&
+    const bool overlap = (fusedA || sepA) && lists_on && dense_on && ((stages & chain) == chain) && s.G2 && s.Rq && s.list_nodes &&
                          !s.g_ptr && (s.n_irr > 0 || s.n_crossed > 0) && (s.n_irr == 0 || s.n_list > 0);
     if (overlap) {
         SideLane* lane = side_lane();
@@ -2603,8 +2607,14 @@ static int launch_shared(const nbm_shared_step_t& s, cudaStream_t st) {
             launch_pdl(extrap_bwd_kernel, dim3((unsigned)((s.n_crossed * 27 + 127) / 128)), dim3(128), 0, lane->stream, s, s.G2);
         }
         cudaEventRecord(lane->join, lane->stream);
-        int rc = stencil_tma::launch(s, sms, st);
-        if (rc) return rc;
+        if (fusedA) {
+            int rc = stencil_tma::launch(s, sms, st);
+            if (rc) return rc;
+        } else {   // (irregular rows keep R = 0 until the merge: their nonlinear centre term is irregular_fb's)
+            const unsigned gx = (unsigned)((s.ey * s.ez / 4 + kThreads - 1) / kThreads);
+            residual_faces4_kernel<<<dim3(gx, s.ex - 2), kThreads, 0, st>>>(s);
+            adjoint_faces4_kernel<<<dim3(gx, s.ex), kThreads, 0, st>>>(s);
+        }
         cudaStreamWaitEvent(st, lane->join, 0);
         const int64_t nm = s.n_list > s.n_irr ? s.n_list : s.n_irr;
         if (!(dbg_skip & 2)) merge_lists_kernel<<<(unsigned)((nm + 255) / 256), 256, 0, st>>>(s);

@@ -376,7 +376,7 @@ class SharedPlan:
         (172 -> 210); see DESIGN.md.
         `overlap_lists`: run the list kernels (crossed sites, irregular rows) on a side stream BESIDE the TMA stencil
         kernel instead of after it (they need only U); their adjoint lands in a side buffer that a small merge kernel
-        adds to G.  Default: on whenever the TMA stencil is active and `deterministic` is off.
+        adds to G.  Default: on with the faces table (TMA stencil or the two separate kernels) when `deterministic` is off.
         `deterministic`: gather the adjoint of the lists (irregular rows, extrapolation) through their transposed
         incidence instead of scattering it with fp32 atomics: the whole step becomes bitwise reproducible, for
         ~5 us more per step at 256^3 (the atomics are faster than the doubly indirect gathers)."""
@@ -617,10 +617,11 @@ class SharedPlan:
             s.stencil_tma = 0 if self.stencil_tma else -1
             # (mirrors the library's own test, nbm_step.cu launch_shared)
             self.stencil_tma_active = bool(self.stencil_tma and self.faces and precond is None and not self.fused
-                                           and ez % 4 == 0 and not (use_nl and self.g_ptr is not None))
+                                           and ez % 4 == 0 and not use_nl)
             # list chain beside the dense stencil: side buffer G2, compact residuals Rq, the nodes the lists can reach
             want = (os.environ.get("NBM_OVERLAP_LISTS", "1") != "0") if overlap_lists is None else bool(overlap_lists)
-            self.overlap_lists = bool(want and self.stencil_tma_active and self.g_ptr is None and (cs.n > 0 or n_irr > 0))
+            self.overlap_lists = bool(want and self.faces and precond is None and not self.fused and self.g_ptr is None
+                                      and (cs.n > 0 or n_irr > 0))
             self.G2 = self.Rq = None
             if self.overlap_lists:
                 sxy, sy = ey * ez, ez

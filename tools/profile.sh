@@ -11,7 +11,7 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c
     > gpurun_out/ncu_bench_${TAG}.log 2>&1
 # skip the set-up and warm-up launches: capture the dense step kernels of a late step
 timeout 500 ncu --set full --import-source on --clock-control none \
-    -k 'regex:(fwd_nodes_kernel|residual_faces4_kernel|adjoint_faces4_kernel|stencil_tma_kernel|node_grad_kernel|step_)' --launch-skip 9 -c 3 \
+    -k 'regex:(fwd_nodes_kernel|stencil_tma_kernel|node_grad_kernel|merge_lists_kernel|irregular_fb_kernel|finalize_step_kernel)' --launch-skip 12 -c 6 \
     -f -o gpurun_out/prof_${TAG} python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-graph $EXTRA \
     > gpurun_out/ncu_full_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_full_${TAG}.log | cut -c1-300

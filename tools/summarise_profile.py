@@ -20,7 +20,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r1b"
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
-STEP = ["prep_params_kernel", "fwd_nodes_kernel", "extrap_kernel", "residual", "stencil_tma", "step_", "irregular_fwd_kernel", "adjoint",
+STEP = ["prep_params_kernel", "fwd_nodes_kernel", "extrap_kernel", "residual", "stencil_tma", "merge_lists", "irregular_fb", "irregular_fwd_kernel", "adjoint",
         "irregular_bwd_kernel", "extrap_bwd_kernel", "node_grad", "precond_kernel", "reduce_partials_kernel",
         "apply_update_kernel", "finalize_step_kernel"]
 
@@ -78,7 +78,7 @@ cols = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
 cols = [c for c in cols if c in ix]
-md = [f"# {tag} - `ncu --set full --clock-control none` of the four step kernels (sphere 256^3, "
+md = [f"# {tag} - `ncu --set full --clock-control none` of the step kernels (sphere 256^3, "
       f"{bench['roofline']['nodes_per_launch']} lattice nodes per launch)", "",
       f"Raw metrics: `{tag}_ncu_full_raw.csv`; per-instruction stall samples of node_grad: `{tag}_ncu_node_grad_source.csv`.",
       "", "| kernel | " + " | ".join(c.replace("__", ".").replace(".avg.pct_of_peak_sustained_active", " %").replace(
