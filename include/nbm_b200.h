@@ -370,6 +370,13 @@ typedef struct {
      * n_net + n_pc + 1 floats and n_pc_rows extra rows are needed after the 7*grid + rows + extrap rows */
     const float* coef26; const float* pc_params; float* Pc;
     int pc_d1, pc_d2; float pc_scale; int n_pc_rows;
+    /* Zoom level 1 with whole-plane batches (cell size = half the grid spacing, data_management.py:320-326): the stencil
+     * site p + d e_a of a point is the site p' - d e_a of its neighbour p' = p + 2 d e_a, so FOUR lattices - the nodes and the
+     * x-, y-, z-half-offset lattices - replace the 7 displaced ones (4 network evaluations per point instead of 7).  All four
+     * are stored with the padded dims (nx+1, ny+1, nz+1): xs4 [4][nx+1], ys4 [4][ny+1], zs4 [4][nz+1] (lattice l = 1, 2, 3
+     * carries x - dx, y - dy, z - dz in its own direction, its last entry the + side of the last point), side4 / U4 / G4
+     * [4][(nx+1)(ny+1)(nz+1)].  NULL = the 7-lattice path.  Needs p0, p1 multiples of ny*nz. */
+    const float* xs4; const float* ys4; const float* zs4; const uint8_t* side4; float* U4; float* G4;
 } nbm_points_step_t;
 
 /* General path (any cell size, any contiguous batch): 7 network evaluations per point (the reference

@@ -92,7 +92,8 @@ class PointsStep(C.Structure):
                 ("partials", c_fp), ("n_partial_rows", C.c_int), ("loss_grad", c_fp), ("rows", c_fp),
                 ("xs7", c_fp), ("ys7", c_fp), ("zs7", c_fp), ("U7", c_fp), ("G7", c_fp),
                 ("coef26", c_fp), ("pc_params", c_fp), ("Pc", c_fp), ("pc_d1", C.c_int), ("pc_d2", C.c_int),
-                ("pc_scale", c_f), ("n_pc_rows", C.c_int)]
+                ("pc_scale", c_f), ("n_pc_rows", C.c_int),
+                ("xs4", c_fp), ("ys4", c_fp), ("zs4", c_fp), ("side4", c_fp), ("U4", c_fp), ("G4", c_fp)]
 
 
 class Optimizer(C.Structure):

@@ -654,6 +654,7 @@ struct NodeView {
     const uint8_t* side;
     float* U;
     const float* G;
+    float* Gz;                   // general path on shared lattices: the forward kernel clears G of the nodes it visits
     const float* R;              // may be null (no loss accumulation)
     float4* Hst;                 // activation stash [HPQ][rep_nodes] 16-byte chunks, or null (recompute)
     float inv_n;
@@ -670,7 +671,7 @@ static NodeView view_of(const nbm_shared_step_t& s) {
     v.lo = 0; v.hi = (int64_t)s.ex * s.ey * s.ez;
     v.rep_nodes = v.hi;
     v.nrep = 1;
-    v.side = s.side; v.U = s.U; v.G = s.G; v.R = s.R;
+    v.side = s.side; v.U = s.U; v.G = s.G; v.R = s.R; v.Gz = nullptr;
     v.Hst = reinterpret_cast<float4*>(s.Hst);
     v.inv_n = s.inv_n_points; v.partials = s.partials; v.row0 = 0;
     v.row_stride = 0; v.loss_col = 0;
@@ -683,7 +684,7 @@ template <class NET, bool GENERAL, bool STASH>
 __device__ __forceinline__ void fwd_task(const NodeView& v, const int plane, const float* __restrict__ xe,
                                          const float* __restrict__ ye, const float* __restrict__ ze,
                                          const uint8_t* __restrict__ side, float* __restrict__ U, const int m, const int x0,
-                                         const int x1) {
+                                         const int x1, float* __restrict__ Gz = nullptr) {
     if (m >= plane) return;
     const int iy = m / v.ez, iz = m - iy * v.ez;
     const float y = __ldg(ye + iy), z = __ldg(ze + iz);
@@ -717,6 +718,10 @@ __device__ __forceinline__ void fwd_task(const NodeView& v, const int plane, con
         }
         if (!GENERAL || (e_cur >= v.lo && e_cur < v.hi)) U[e_cur] = ua;
         if (has_b && (!GENERAL || (e_cur + plane >= v.lo && e_cur + plane < v.hi))) U[e_cur + plane] = ub;
+        if (GENERAL && Gz) {
+            Gz[e_cur] = 0.0f;
+            if (has_b) Gz[e_cur + plane] = 0.0f;
+        }
     }
 }
 
@@ -738,7 +743,8 @@ __global__ void __launch_bounds__(kThreads, 3) fwd_nodes_kernel(NodeView v, Task
             const int len = (int)min((int64_t)(nx - xo), hi - p);
             fwd_task<NET, GENERAL, STASH>(v, T.plane, v.xe + (size_t)rep * v.ex, v.ye + (size_t)rep * v.ey,
                                           v.ze + (size_t)rep * v.ez, v.side + rep * v.rep_nodes, v.U + rep * v.rep_nodes,
-                                          mb * kThreads + (int)threadIdx.x, v.x_begin + xo, v.x_begin + xo + len);
+                                          mb * kThreads + (int)threadIdx.x, v.x_begin + xo, v.x_begin + xo + len,
+                                          (GENERAL && v.Gz) ? v.Gz + rep * v.rep_nodes : nullptr);
             p += len;
         }
     }
@@ -2802,19 +2808,34 @@ __global__ void __launch_bounds__(kThreads) points_extrap_kernel(PointsArgs a) {
 
 // Z1: rows of the batch, pointwise on the 7 site values U7[k][p] (written by fwd_nodes over the 7 displaced
 // lattices): residual, loss partial, and d loss / d u(site) into G7[k][p] for the per-site backward kernel
+// S4: the 7 site values come from the 4 shared lattices of zoom level 1 (nbm_points_step_t.U4), padded dims
+// (nx+1, ny+1, nz+1); a half-offset site belongs to two points, whose contributions meet in G4 by atomicAdd (the forward
+// kernel cleared it; two addends: the order cannot change the sum)
+template <bool S4>
 __global__ void __launch_bounds__(kThreads) points_rows_kernel(PointsArgs a, const float* __restrict__ U7,
                                                                float* __restrict__ G7, int row0, int np1) {
     const nbm_points_step_t& s = a.s;
     const int64_t N = a.n_points;
+    const int64_t sy4 = s.nz + 1, sx4 = (int64_t)(s.ny + 1) * sy4, ne4 = (int64_t)(s.nx + 1) * sx4;
     float loss = 0.0f;
     for (int64_t p = s.p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < s.p1;
          p += (int64_t)gridDim.x * blockDim.x) {
         float u[7], w[7];
         float r = -__ldg(s.rhs + p);
+        int64_t i4[7];
+        if (S4) {
+            const int64_t pl = (int64_t)s.ny * s.nz;
+            const int ix = (int)(p / pl), rem = (int)(p - (int64_t)ix * pl), iy = rem / s.nz, iz = rem - iy * s.nz;
+            const int64_t e4 = ix * sx4 + iy * sy4 + iz;
+            i4[0] = e4;
+            i4[1] = ne4 + e4;     i4[2] = ne4 + e4 + sx4;
+            i4[3] = 2 * ne4 + e4; i4[4] = 2 * ne4 + e4 + sy4;
+            i4[5] = 3 * ne4 + e4; i4[6] = 3 * ne4 + e4 + 1;
+        }
 #pragma unroll
         for (int q = 0; q < 7; ++q) {
             w[q] = __ldg(s.w + q * N + p);
-            u[q] = U7[q * N + p];
+            u[q] = S4 ? U7[i4[q]] : U7[q * N + p];
             r = fmaf(w[q], u[q], r);
         }
         float nlw0 = 0.0f, nlw1 = 0.0f;
@@ -2872,7 +2893,9 @@ __global__ void __launch_bounds__(kThreads) points_rows_kernel(PointsArgs a, con
             if (q == 0 && s.nl)
                 gq = fmaf(nlw0 * nl_deriv(s.nonlinear_m, s.nl_coef_m, u[0]) +
                               nlw1 * nl_deriv(s.nonlinear_p, s.nl_coef_p, u[0]), r, gq);
-            G7[q * N + p] = gq;
+            if (!S4) G7[q * N + p] = gq;
+            else if (q == 0) G7[i4[0]] = gq;
+            else atomicAdd(G7 + i4[q], gq);
         }
     }
     // loss partial: one row per CTA, gradient entries zero
@@ -2937,22 +2960,29 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     v.lo = s.p0; v.hi = s.p1;
     v.rep_nodes = a.n_points;
     v.nrep = 7;
-    v.side = s.side; v.U = s.U7; v.G = s.G7; v.R = nullptr;
+    v.side = s.side; v.U = s.U7; v.G = s.G7; v.R = nullptr; v.Gz = nullptr;
     v.inv_n = s.inv_n_points; v.partials = s.partials;
-    int xchunk = 16;
-    {
-        int mblocks = (plane + kThreads - 1) / kThreads;
-        int nxp = v.x_end - v.x_begin;
-        while (xchunk > 2 && (int64_t)mblocks * ((nxp + xchunk - 1) / xchunk) * 7 < 2 * (int64_t)sms) xchunk >>= 1;
+    // zoom level 1 on the 4 shared lattices (padded dims; the batch is whole x planes; one more plane for the x-half lattice)
+    const bool s4 = s.U4 != nullptr;
+    if (s4) {
+        v.xe = s.xs4; v.ye = s.ys4; v.ze = s.zs4;
+        v.ex = s.nx + 1; v.ey = s.ny + 1; v.ez = s.nz + 1;
+        v.x_end = v.x_begin + (int)(nb / plane) + 1;
+        v.rep_nodes = (int64_t)v.ex * v.ey * v.ez;
+        v.lo = 0; v.hi = v.rep_nodes;
+        v.nrep = 4;
+        v.side = s.side4; v.U = s.U4; v.G = s.G4; v.Gz = s.G4;
     }
-    Tasks T = make_tasks(v.x_end - v.x_begin, s.ny, s.nz, xchunk);
-    const int64_t itersF = (int64_t)T.mblocks * (v.x_end - v.x_begin) * 7;
+    const int nrep = v.nrep;
+    int xchunk = 16;
+    Tasks T = make_tasks(v.x_end - v.x_begin, v.ey, v.ez, xchunk);
+    const int64_t itersF = (int64_t)T.mblocks * (v.x_end - v.x_begin) * nrep;
     int perF = 12;      // forward CTAs per SM (3 resident), fewer while a range would hold < 24 plane iterations
     while (perF > 3 && itersF / ((int64_t)sms * perF) < 24) perF -= 3;
     const int gridF = (int)min(itersF, (int64_t)sms * perF);
-    Tasks Tg = make_tasks(v.x_end - v.x_begin, s.ny, s.nz, xchunk, kGradThreads);
-    // one gradient CTA per SM: the 7 replicas are one range set, every CTA gets the same share (one even wave)
-    const int64_t itersG = (int64_t)Tg.mblocks * (v.x_end - v.x_begin) * 7;
+    Tasks Tg = make_tasks(v.x_end - v.x_begin, v.ey, v.ez, xchunk, kGradThreads);
+    // one gradient CTA per SM: the replicas are one range set, every CTA gets the same share (one even wave)
+    const int64_t itersG = (int64_t)Tg.mblocks * (v.x_end - v.x_begin) * nrep;
     const int gridG = (int)min(itersG, (int64_t)sms);
     Tg.split = run_split(itersG, gridG);
     const int gridR = (int)min((int64_t)sms * 2, (nb + kThreads - 1) / kThreads);
@@ -2977,7 +3007,8 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     if (pc)
         precond_fwd_kernel<8, 4><<<(unsigned)min((int64_t)sms * 8, (nb + kThreads - 1) / kThreads), kThreads, 0, st>>>(
             s.coef26 + s.p0, a.n_points, nb, s.pc_params, s.pc_scale, s.Pc + s.p0);
-    points_rows_kernel<<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, gridG, stride);
+    if (s4) points_rows_kernel<true><<<gridR, kThreads, 0, st>>>(a, s.U4, s.G4, gridG, stride);
+    else points_rows_kernel<false><<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, gridG, stride);
     if (pc)   // loss + d loss/d theta_P from the raw residuals kept in `rows`
         precond_kernel<8, 4><<<gridP, kThreads, 0, st>>>(s.coef26 + s.p0, a.n_points, s.rows + s.p0, nullptr, nb, s.pc_params,
                                                          s.pc_scale, s.inv_n_points,
@@ -3100,6 +3131,11 @@ int nbm_loss_grad_points_f32(const nbm_points_step_t* s, nbm_stream_t stream) {
     NBM_REQUIRE(s->dx > 0 && s->dy > 0 && s->dz > 0, "cell size must be positive");
     NBM_REQUIRE(s->partials && s->loss_grad && s->n_partial_rows >= 2, "null work buffers");
     NBM_REQUIRE(s->U7 && s->G7 && s->xs7 && s->ys7 && s->zs7, "null site work buffers / displaced coordinate arrays");
+    if (s->U4 || s->G4 || s->xs4 || s->ys4 || s->zs4 || s->side4) {
+        NBM_REQUIRE(s->U4 && s->G4 && s->xs4 && s->ys4 && s->zs4 && s->side4, "the 4 shared lattices need all of xs4, ys4, zs4, side4, U4, G4");
+        const int64_t plane = (int64_t)s->ny * s->nz;
+        NBM_REQUIRE(s->p0 % plane == 0 && s->p1 % plane == 0, "the 4 shared lattices serve batches of whole x planes");
+    }
     NBM_REQUIRE(s->n_crossed == 0 || (s->c_site && s->c_pos && s->c_cube_side && s->B && s->E && s->gE),
                 "null crossed-site tables");
     NBM_REQUIRE(s->n_irr == 0 || (s->irr_wE && s->irr_c && s->irr_nl && s->irr_nlw), "null irregular-row tables");

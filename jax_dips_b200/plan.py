@@ -854,6 +854,35 @@ class GeneralLevel:
             self.zs7 = (self.zs[None, :] + sh[:, 2:3]).contiguous()
             self.U7 = torch.zeros(7 * N, dtype=torch.float32, device=dev)
             self.G7 = torch.zeros(7 * N, dtype=torch.float32, device=dev)
+            # Zoom level 1 (cell size = half the grid spacing): p + d e_a of a point is p' - d e_a of its neighbour, so the
+            # nodes + the x-, y-, z-half-offset lattices (4 network evaluations per point) replace the 7 displaced
+            # lattices for whole-plane batches (data_management.py:320-326).  Padded dims (Nx+1, Ny+1, Nz+1);
+            # lattice l carries "- d" in its own direction, its last entry is the "+ d" site of the last point.
+            g = (float(tr_gstate.dx), float(tr_gstate.dy), float(tr_gstate.dz))
+            half = all(abs(2.0 * self.d[a] - g[a]) <= 1e-6 * g[a] for a in range(3))
+            self.shared4 = bool(half and os.environ.get("NBM_ZOOM1_SHARED", "1") != "0")
+            if self.shared4:
+                def pad(base, minus=None, plus_last=None, step=0.0):
+                    a0 = base if minus is None else minus
+                    last = (base[-1:] + step) if plus_last is None else plus_last
+                    return torch.cat((a0, last))
+                xs0, ys0, zs0 = pad(self.xs, step=g[0]), pad(self.ys, step=g[1]), pad(self.zs, step=g[2])
+                self.xs4 = torch.stack((xs0, pad(self.xs, self.xs7[1], self.xs7[2][-1:]), xs0, xs0)).contiguous()
+                self.ys4 = torch.stack((ys0, ys0, pad(self.ys, self.ys7[3], self.ys7[4][-1:]), ys0)).contiguous()
+                self.zs4 = torch.stack((zs0, zs0, zs0, pad(self.zs, self.zs7[5], self.zs7[6][-1:]))).contiguous()
+                s7 = cs.side[:7 * N].view(7, Nx, Ny, Nz)
+                s4 = torch.zeros((4, Nx + 1, Ny + 1, Nz + 1), dtype=torch.uint8, device=dev)
+                s4[0, :Nx, :Ny, :Nz] = s7[0]
+                s4[1, :Nx, :Ny, :Nz] = s7[1]
+                s4[1, Nx, :Ny, :Nz] = s7[2][Nx - 1]
+                s4[2, :Nx, :Ny, :Nz] = s7[3]
+                s4[2, :Nx, Ny, :Nz] = s7[4][:, Ny - 1]
+                s4[3, :Nx, :Ny, :Nz] = s7[5]
+                s4[3, :Nx, :Ny, Nz] = s7[6][:, :, Nz - 1]
+                self.side4 = s4.reshape(-1).contiguous()
+                ne4 = (Nx + 1) * (Ny + 1) * (Nz + 1)
+                self.U4 = torch.zeros(4 * ne4, dtype=torch.float32, device=dev)
+                self.G4 = torch.zeros(4 * ne4, dtype=torch.float32, device=dev)
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             self.n_pc_rows = sms if precond is not None else 0
             rows = L.nbm_step_partial_rows() + self.n_pc_rows
@@ -895,6 +924,11 @@ class PointsPlan:
         s.rows = cabi.ptr(self.rows)
         s.xs7, s.ys7, s.zs7 = cabi.ptr(level.xs7), cabi.ptr(level.ys7), cabi.ptr(level.zs7)
         s.U7, s.G7 = cabi.ptr(level.U7), cabi.ptr(level.G7)
+        plane = level.shape[1] * level.shape[2]
+        self.shared4 = bool(getattr(level, "shared4", False) and self.p0 % plane == 0 and self.p1 % plane == 0)
+        if self.shared4:
+            s.xs4, s.ys4, s.zs4 = cabi.ptr(level.xs4), cabi.ptr(level.ys4), cabi.ptr(level.zs4)
+            s.side4, s.U4, s.G4 = cabi.ptr(level.side4), cabi.ptr(level.U4), cabi.ptr(level.G4)
         if level.precond is not None:
             s.coef26, s.Pc = cabi.ptr(level.coef26), cabi.ptr(level.Pc)
             s.pc_d1, s.pc_d2, s.pc_scale = level.precond.widths[0], level.precond.widths[1], level.precond.scale

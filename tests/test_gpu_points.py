@@ -49,6 +49,35 @@ def test_general_path_loss_and_gradient(name, zoom):
     assert util.rel_inf(lgb[:-1], grad_b) < TOL_LOSS
 
 
+@pytest.mark.parametrize("name", ["sphere", "star", "sphere_reaction"])
+def test_zoom_1_on_four_shared_lattices_equals_the_seven_displaced_ones(name, monkeypatch):
+    """zoom level 1: p + d e_a of a point is p' - d e_a of its neighbour, so 4 lattices (nodes + three half-offset ones)
+    carry every stencil site; same [grad, loss] as the 7-lattice formulation up to the 1-ulp difference between
+    fl(x_i + d) and fl(x_{i+1} - d), for the whole grid and for a batch of x planes; other batches keep 7 lattices."""
+    P = problems.PROBLEMS[name]()
+    tr, oprob, level4, shape, d = general(P, 12, 32, 1)
+    monkeypatch.setenv("NBM_ZOOM1_SHARED", "0")
+    _, _, level7, _, _ = general(P, 12, 32, 1)
+    assert level4.shared4 and not level7.shared4
+    _, _, level_z2, _, _ = general(P, 12, 32, 2)
+    assert not level_z2.shared4                      # no sharing below half the spacing
+    n, plane = tr.num_points(), 12 * 12
+    params = O.init_params(oprob.shape, seed=19).to(DEV)
+    with torch.cuda.device(DEV):
+        nplan.upload_params(shape, params)
+        for (a, b) in ((0, n), (3 * plane, 9 * plane), (11 * plane, 12 * plane)):
+            p4, p7 = nplan.PointsPlan(level4, a, b, keep_rows=True), nplan.PointsPlan(level7, a, b, keep_rows=True)
+            assert p4.shared4 and not p7.shared4
+            l4, l7 = p4.loss_grad_launch().clone(), p7.loss_grad_launch().clone()
+            l4b = p4.loss_grad_launch().clone()      # G4 is cleared by the forward kernel: repeated launches agree
+            torch.cuda.synchronize()
+            assert util.rel_inf(p4.rows.cpu()[a:b], p7.rows.cpu()[a:b]) < 1e-5
+            assert util.rel_inf(l4.cpu(), l7.cpu()) < 1e-5, util.rel_inf(l4.cpu(), l7.cpu())
+            assert torch.equal(l4, l4b)
+        ragged = nplan.PointsPlan(level4, 5, n - 7)
+        assert not ragged.shared4
+
+
 def test_general_and_shared_paths_agree_at_native_spacing():
     P = problems.star()
     tr, lv, lvl, oprob, shared, shape = build(P, 16, 32)
