@@ -628,6 +628,8 @@ struct Tasks {
 };
 // ranges per CTA: up to 4 (regions of cheap minus-side nodes spread over more CTAs) while a range keeps >= 64 planes
 static int run_split(int64_t plane_iterations, int ctas) {
+    static const int forced = getenv("NBM_GRAD_SPLIT") ? atoi(getenv("NBM_GRAD_SPLIT")) : 0;   // timing experiments
+    if (forced > 0) return forced;
     const int64_t per_cta = plane_iterations / (ctas > 0 ? ctas : 1);
     return (int)(per_cta >= 256 ? 4 : (per_cta >= 128 ? 2 : 1));
 }
