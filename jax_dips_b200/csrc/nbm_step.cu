@@ -1,12 +1,17 @@
 // Per-optimizer-step kernels (K3/K4) and the evaluation kernel (K5).
 //
 // Shared-evaluation path (cell size == grid spacing): the network is evaluated ONCE per node of
-// the rank-local lattice (fwd_nodes), crossed nodes get their far-side value from the 27-point
-// regression table (extrap), every row is a 7-point stencil on U (+ irregular corrections),
-// the adjoint stencil gathers d loss/d U per node, and one fused forward-recompute + backward
-// kernel (node_grad: 12 warps/SM, pair-split outer-product accumulators) turns it into per-CTA
-// partial sums of d loss/d theta held in registers.  Optional: the learned preconditioner kernels
-// between the residual and the adjoint stage; the TMA-staged fused adjoint + gradient kernel.
+// the rank-local lattice (fwd_nodes); the rows (7-point stencil on U) and the adjoint stencil
+// (d loss/d U per node) of the face table are ONE kernel fed by 3-D TMA boxes (nbm_stencil_tma.cuh);
+// crossed nodes get their far-side value from the 27-point regression table and irregular rows
+// their corrections in a chain of list kernels that runs on a side stream BESIDE that kernel
+// (extrap -> irregular_fb -> extrap_bwd, merged into G by merge_lists); one fused forward-recompute
+// + backward kernel (node_grad: 12 warps/SM, pair-split outer-product accumulators) turns G into
+// per-CTA partial sums of d loss/d theta held in registers; finalize_step (or, on several GPUs,
+// reduce_allreduce_finalize over NVLink peer memory) sums them and runs the optax chain.
+// Optional: the learned preconditioner kernels between separate residual and adjoint kernels.
+// General path (any cell size): the network kernels over 7 displaced lattices - 4 shared ones at
+// zoom level 1 -, a pointwise rows kernel, and the 27-cubes of crossed sites as 3x3x3 mini-lattices.
 //
 // The network parameters live in __constant__ memory so that every FFMA takes its weight as a
 // constant-bank operand (no load, no register).
