@@ -1298,7 +1298,10 @@ __device__ __forceinline__ void block_reduce_store(typename NET::Acc& acc, float
 //
 // 12 warps per SM (168 registers): the p-head accumulators are pair-split (MlpP::AccS), the y/z rows and
 // the bias of the first layer live in shared memory and are touched once per task.
-constexpr int kGradThreads = 384;
+#ifndef NBM_GRAD_THREADS
+#define NBM_GRAD_THREADS 384
+#endif
+constexpr int kGradThreads = NBM_GRAD_THREADS;
 
 constexpr int kStashStages = 3;   // cp.async ring of the activation stash: nodes ix, ix+1, ix+2
 template <class NET>
