@@ -206,6 +206,28 @@ __device__ __forceinline__ u64 tanh2_prescaled(u64 sp) {
     return ffma2(pk(m, -2.0f * m), A, pk(1.0f, 1.0f));
 }
 
+// FOUR tanh for the price of 5 MUFU (4 ex2 + ONE reciprocal of the product of the four (e + 1)): the forward kernel is
+// MUFU-bound (XU pipe 76 % busy with the pair version), this trades 5 MUFU per two pairs for 3 more multiplies.  Clamped
+// at 31: (2^31 + 1)^4 stays finite and 1 - 2/(2^31 + 1) already rounds to 1.  1/a_i = (product of the other three) / P
+// costs two roundings more than the pair version: abs error ~4e-7.
+__device__ __forceinline__ void tanh4_prescaled(u64 sp0, u64 sp1, u64& t0, u64& t1) {
+    const float s0 = fminf(lo32(sp0), 31.0f), s1 = fminf(hi32(sp0), 31.0f), s2 = fminf(lo32(sp1), 31.0f),
+                s3 = fminf(hi32(sp1), 31.0f);
+    float e0, e1, e2, e3, m;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(s0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(s1));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(s2));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(s3));
+    const u64 one2 = pk(1.0f, 1.0f);
+    const u64 A = fadd2(pk(e0, e1), one2), B = fadd2(pk(e2, e3), one2);   // (a0, a1), (a2, a3)
+    const float pA = lo32(A) * hi32(A), pB = lo32(B) * hi32(B);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(pA * pB));
+    const float rA = -2.0f * (m * pB), rB = -2.0f * (m * pA);               // -2 / (a0 a1), -2 / (a2 a3)
+    // t_i = 1 - 2 / a_i = 1 + r (the partner of a_i inside its pair)
+    t0 = ffma2(pk(rA, rA), pk(hi32(A), lo32(A)), one2);
+    t1 = ffma2(pk(rB, rB), pk(hi32(B), lo32(B)), one2);
+}
+
 // Variant for kernels with MUFU head-room (node_grad: XU pipe ~30 % busy): one reciprocal per element instead of a
 // shared one.  4 MUFU per pair instead of 3, but 6 instructions instead of 9 and no clamp: rcp(inf) = 0 gives t = 1.
 __device__ __forceinline__ u64 tanh2_prescaled_4mufu(u64 sp) {
@@ -295,8 +317,12 @@ struct MlpP {
 #pragma unroll
         for (int j = 0; j < HP; ++j) {
             const u64 wx = cpair(S + 2 * j);
+            if (NB == 2) {   // the two nodes' pairs share one reciprocal
+                tanh4_prescaled(ffma2(pk(x[0], x[0]), wx, yz[j]), ffma2(pk(x[NB - 1], x[NB - 1]), wx, yz[j]), a[0][j], a[NB - 1][j]);
+            } else {
 #pragma unroll
-            for (int n = 0; n < NB; ++n) a[n][j] = tanh2_prescaled(ffma2(pk(x[n], x[n]), wx, yz[j]));
+                for (int n = 0; n < NB; ++n) a[n][j] = tanh2_prescaled(ffma2(pk(x[n], x[n]), wx, yz[j]));
+            }
         }
 #pragma unroll
         for (int l = 1; l < L; ++l) {
@@ -317,10 +343,15 @@ struct MlpP {
                     }
                 }
             }
+            if (NB == 2) {
 #pragma unroll
-            for (int n = 0; n < NB; ++n)
+                for (int j = 0; j < HP; ++j) tanh4_prescaled(b[0][j], b[NB - 1][j], a[0][j], a[NB - 1][j]);
+            } else {
 #pragma unroll
-                for (int j = 0; j < HP; ++j) a[n][j] = tanh2_prescaled(b[n][j]);
+                for (int n = 0; n < NB; ++n)
+#pragma unroll
+                    for (int j = 0; j < HP; ++j) a[n][j] = tanh2_prescaled(b[n][j]);
+            }
         }
         const int oo = OFF + 4 * H + (L - 1) * (H * H + H);
 #pragma unroll
