@@ -3008,15 +3008,19 @@ __global__ void __launch_bounds__(kCubeFwdThreads) cube_fwd_kernel(PointsArgs a)
                         z = s.c_pos[3 * c + 2] + (float)(jz - 1) * s.dz;
             const float xs[3] = {px + -1.0f * s.dx, px + 0.0f * s.dx, px + 1.0f * s.dx};
             const unsigned side3 = (s.c_cube_side[c] >> (3 * j)) & 7u;
+            // branch-free over the sides: a warp at the interface holds plus AND minus vertices, so every item takes the
+            // paired plus-head evaluation of its three vertices (wasted on minus vertices, but one pass instead of the two
+            // or three a divergent warp would run) and the tiny minus head where a vertex needs it
             float u[3];
-            if (side3 == 7u) {
-                u64 yz[HP2];
-                NET::first_layer_yz(y, z, yz);
-                NET::P::template forward_many<0, 3>(xs, yz, u);
-            } else {
+            u64 yz[HP2];
+            NET::first_layer_yz(y, z, yz);
+            NET::P::template forward_many<0, 3>(xs, yz, u);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) u[i] = NET::eval((side3 >> i) & 1u, xs[i], y, z);
-            }
+            for (int i = 0; i < 3; ++i)
+                if (!((side3 >> i) & 1u)) {
+                    float am[NET::LMD][NET::HMW];
+                    u[i] = NET::M::template forward<NET::P::NP>(xs[i], y, z, am);
+                }
             const float* B = s.B + c * 28 + 3 * j;
             v = fmaf(B[2], u[2], fmaf(B[1], u[1], B[0] * u[0]));
         }
