@@ -36,10 +36,10 @@ F_GRAD = 0.93e3       # FLOP per lattice node for the dominant kernel (forward r
 B_STEP_FACES = 52.0
 B_STEP_ROWS = 76.0
 B_STEP_TMA = 36.0        # fused residual + adjoint: U, 3 face coefficients, 1/diag, rhs read once; R and G written
-# DRAM bytes (read + write) of one node_grad launch at 256^3, `ncu --set full` (profiles/r2s_ncu_summary.md)
-NODE_GRAD_TRAFFIC_256 = 160883968
+# DRAM bytes (read + write) of one node_grad launch at 256^3, `ncu --set full` (profiles/r2f_ncu_summary.md)
+NODE_GRAD_TRAFFIC_256 = 160720384
 NODE_GRAD_TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum of one node_grad launch at sphere 256^3, "
-                            "`ncu --set full` capture profiles/r2s_ncu_full_raw.csv (not re-measured in this run)")
+                            "`ncu --set full` capture profiles/r2f_ncu_full_raw.csv (not re-measured in this run)")
 FP32_NOMINAL = 74.5                  # TFLOP/s: 148 SM x 128 lanes x 2 x 1.965 GHz
 
 
