@@ -537,15 +537,19 @@ def main():
     per_rank = None
     if world > 1:
         # per-rank device time of one step's kernels without the exchange (load balance), gathered to rank 0
-        tt = 0.0
         nplan.upload_params(net, params)
-        for _ in range(5):
+        for _ in range(2):
+            pl.loss_grad_launch()
+        torch.cuda.synchronize()
+        samples = []
+        for _ in range(7):
             h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             h0.record()
             pl.loss_grad_launch()
             h1.record()
             torch.cuda.synchronize()
-            tt += h0.elapsed_time(h1) / 5
+            samples.append(h0.elapsed_time(h1))
+        tt = sorted(samples)[len(samples) // 2]     # median: eager launches, one slow sample must not read as imbalance
         allt = [torch.zeros(3, device=dev) for _ in range(world)]
         dist.all_gather(allt, torch.tensor([tt, float(pl.sites.n), float(pl.n_irr)], device=dev))
         per_rank = [{"rank": r, "ms_eager_no_exchange": float(a[0]), "crossed_sites": int(a[1]), "irregular_rows": int(a[2]),
