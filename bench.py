@@ -80,6 +80,14 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------
+def workload_string(args, world):
+    """config.workload: the same string in both arms (ours and --impl reference) for the same flags"""
+    nx = args.grid * world if args.scaling == "weak" else args.grid
+    return (f"{args.workload}: train grid {nx}x{args.grid}x{args.grid} ({nx * args.grid * args.grid} points, x-slabs over "
+            f"{world} GPU(s), {args.scaling} scaling), level set on {args.lvl}^3 lvl grid ({args.interp}), "
+            "MLP p 3-10-10-1 | m 3-1-1 tanh, optimizer custom(adam), one batch per GPU")
+
+
 def make_problem(name):
     from jax_dips_b200 import problems
     return problems.PROBLEMS[name]()
@@ -185,14 +193,15 @@ def run_reference(args):
     if rank != 0:
         return
     problem = make_problem(args.workload)
-    n_step = 2048
+    n_step = args.cpu_sample      # the same bounded sample as the cpu_baseline leg of our own arm
     res = cpu_baseline(problem, args, n_step, steps=args.steps, warmup=min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds"] * 1e3,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload} {args.grid}^3 train / {args.lvl}^3 lvl (bounded sample)",
-                       "sample_points_per_step": n_step},
+            "config": {"workload": workload_string(args, int(os.environ.get("WORLD_SIZE", "1"))),
+                       "sample": f"bounded sample of the workload: {n_step} of its training points per step (every k-th), "
+                                 "on the host cores", "sample_points_per_step": n_step},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -630,11 +639,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{args.workload}: train grid {Nx}x{Ny}x{Nz} ({n_points_total} points, "
-                                       f"x-slabs of {per} planes per GPU" +
-                                       (f", cost-balanced to {[b - a for a, b in slabs]}" if slabs else "") + "), level set on {args.lvl}^3 lvl grid "
-                                       f"({args.interp}), MLP p 3-10-10-1 | m 3-1-1 tanh, optimizer custom(adam), "
-                                       "one batch per GPU",
+                "config": {"workload": workload_string(args, world),
+                           "slabs": ([b - a for a, b in slabs] if slabs else f"{per} x-planes per GPU (equal blocks)"),
                            "l2": (f"row tables + work arrays ({table_mb:.0f} MB per GPU) exceed the 126 MB L2; no flush needed"
                                   if flush_buf is None else
                                   f"row tables + work arrays are {table_mb:.0f} MB per GPU (fit in the 126 MB L2): L2 flushed "
