@@ -311,6 +311,10 @@ typedef struct {
      * and its two events are library-owned (one set per device); the fork/join is CUDA-graph capturable, and all
      * work is ordered after what `stream` held on entry and before what is enqueued on `stream` afterwards. */
     float* G2; float* Rq;
+    /* Optional transposed copies of the list tables for the chain kernels (thread per site / per row: with [slot][item]
+     * a warp reads 32 consecutive floats per slot instead of 32 lines): B_soa [28][n_crossed], irr_c_soa / irr_wE_soa /
+     * irr_wU_soa [7][n_irr].  NULL = the item-major tables above. */
+    const float* B_soa; const int32_t* irr_c_soa; const float* irr_wE_soa; const float* irr_wU_soa;
 } nbm_shared_step_t;
 
 /* number of preconditioner parameters for hidden widths (d1, d2) */

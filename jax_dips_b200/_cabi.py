@@ -74,7 +74,8 @@ class SharedStep(C.Structure):
                 ("pc_d", c_f * 3),
                 ("ge_ptr", c_fp), ("ge_ent", c_fp), ("list_nodes", c_fp), ("n_list", C.c_int64), ("g_ptr", c_fp),
                 ("g_ent", c_fp),
-                ("stencil_tma", C.c_int), ("Hst", c_fp), ("G2", c_fp), ("Rq", c_fp)]
+                ("stencil_tma", C.c_int), ("Hst", c_fp), ("G2", c_fp), ("Rq", c_fp),
+                ("B_soa", c_fp), ("irr_c_soa", c_fp), ("irr_wE_soa", c_fp), ("irr_wU_soa", c_fp)]
 
 
 class PointsStep(C.Structure):

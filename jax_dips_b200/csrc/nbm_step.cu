@@ -795,13 +795,15 @@ __global__ void extrap_kernel(nbm_shared_step_t s) {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= s.n_crossed) return;
     int64_t e = s.c_node[c];
-    const float* B = s.B + c * 28;
+    // weights item-major [c][28] or, transposed for this access pattern, slot-major [28][n_crossed]
+    const float* B = s.B_soa ? s.B_soa + c : s.B + c * 28;
+    const int64_t bq = s.B_soa ? s.n_crossed : 1;
     int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
-    float acc = B[27];
+    float acc = B[27 * bq];
 #pragma unroll
     for (int q = 0; q < 27; ++q) {
         int a = q % 3 - 1, b = (q / 3) % 3 - 1, cc = q / 9 - 1;
-        acc = fmaf(B[q], s.U[e + a * sx + b * sy + cc], acc);
+        acc = fmaf(B[q * bq], s.U[e + a * sx + b * sy + cc], acc);
     }
     s.E[c] = acc;
     s.gE[c] = 0.0f;
@@ -1222,7 +1224,7 @@ __global__ void extrap_bwd_kernel(nbm_shared_step_t s, float* __restrict__ Gt) {
     if (g == 0.0f) return;
     int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
     int a = q % 3 - 1, b = (q / 3) % 3 - 1, cc = q / 9 - 1;
-    atomicAdd(Gt + s.c_node[c] + a * sx + b * sy + cc, s.B[c * 28 + q] * g);
+    atomicAdd(Gt + s.c_node[c] + a * sx + b * sy + cc, s.B[c * 28 + q] * g);   // (27 consecutive threads: item-major is coalesced)
 }
 
 // ---- the list chain beside the dense stencil (nbm_shared_step_t.G2 / Rq; faces table) -----------------------------
@@ -1240,9 +1242,15 @@ __global__ void irregular_fb_kernel(nbm_shared_step_t s) {
     float wE[7], wU[7], u[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
-        c[k] = s.irr_c[q * 7 + k];
-        wE[k] = s.irr_wE[q * 7 + k];
-        wU[k] = s.irr_wU[q * 7 + k];
+        if (s.irr_c_soa) {     // slot-major copies: consecutive rows of a warp read consecutive words
+            c[k] = s.irr_c_soa[k * s.n_irr + q];
+            wE[k] = s.irr_wE_soa[k * s.n_irr + q];
+            wU[k] = s.irr_wU_soa[k * s.n_irr + q];
+        } else {
+            c[k] = s.irr_c[q * 7 + k];
+            wE[k] = s.irr_wE[q * 7 + k];
+            wU[k] = s.irr_wU[q * 7 + k];
+        }
         u[k] = s.U[e + off[k]];
     }
     // same operation order as irregular_fwd_kernel
@@ -3305,6 +3313,7 @@ int nbm_loss_grad_shared_f32(const nbm_shared_step_t* s, nbm_stream_t stream) {
         NBM_REQUIRE(s->n_crossed == 0 || (s->ge_ptr && s->ge_ent), "null crossed-site incidence");
         NBM_REQUIRE(!s->S, "the gathered list adjoint and the fused adjoint (S) are alternatives");
     }
+    NBM_REQUIRE(!s->irr_c_soa == !s->irr_wE_soa && !s->irr_c_soa == !s->irr_wU_soa, "transposed irregular-row tables come as a set");
     if (s->G2 || s->Rq) {
         NBM_REQUIRE(s->G2 && s->Rq && s->list_nodes && s->n_list >= 0 && !s->g_ptr,
                     "the list chain beside the stencil needs G2, Rq and list_nodes (and no gathered adjoint)");

@@ -640,6 +640,17 @@ class SharedPlan:
                 self.Rq = torch.zeros(max(n_irr, 1), dtype=torch.float32, device=dev)
                 s.list_nodes, s.n_list = cabi.ptr(self.list_nodes), self.n_list
                 s.G2, s.Rq = cabi.ptr(self.G2), cabi.ptr(self.Rq)
+                # slot-major copies of the list tables for the chain kernels (thread per site / per row)
+                self.B_soa = self.irr_c_soa = self.irr_wE_soa = self.irr_wU_soa = None
+                if os.environ.get("NBM_LIST_SOA", "1") != "0":
+                    if cs.n > 0:
+                        self.B_soa = cs.B.view(-1, 28)[:cs.n].t().contiguous()
+                        s.B_soa = cabi.ptr(self.B_soa)
+                    if n_irr > 0:
+                        tr7 = lambda t: t[:n_irr * 7].view(n_irr, 7).t().contiguous()
+                        self.irr_c_soa, self.irr_wE_soa, self.irr_wU_soa = tr7(self.irr_c), tr7(self.irr_wE), tr7(self.irr_wU)
+                        s.irr_c_soa, s.irr_wE_soa, s.irr_wU_soa = (cabi.ptr(t) for t in (self.irr_c_soa, self.irr_wE_soa,
+                                                                                         self.irr_wU_soa))
             if precond is not None:
                 s.coef26 = cabi.ptr(self.coef26)
                 s.pc_d1, s.pc_d2, s.pc_scale = precond.widths[0], precond.widths[1], precond.scale
