@@ -3067,28 +3067,25 @@ __global__ void __launch_bounds__(kGradThreads, 1) cube_grad_kernel(PointsArgs a
     const int64_t lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
     for (int64_t base = lo; base < hi; base += kGradThreads) {
         const int64_t it = base + threadIdx.x;
-        bool live = it < hi;
-        int64_t c = 0;
-        int j = 0;
-        float ge = 0.0f;
-        if (live) {
-            c = it / 9;
-            j = (int)(it - c * 9);
-            const int64_t p = s.c_site[c] % a.n_points;
-            live = p >= s.p0 && p < s.p1;
-            if (live) ge = s.gE[c];
-            live = live && ge != 0.0f;
-        }
         float y = 0.0f, z = 0.0f, px = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
         unsigned side3 = 0u;
-        if (live) {
-            const int jy = j % 3, jz = j / 3;
-            px = s.c_pos[3 * c];
-            y = s.c_pos[3 * c + 1] + (float)(jy - 1) * s.dy;
-            z = s.c_pos[3 * c + 2] + (float)(jz - 1) * s.dz;
-            side3 = (s.c_cube_side[c] >> (3 * j)) & 7u;
+        if (it < hi) {
+            // every load of the item is issued before any of them is used: one memory round trip per round, not four
+            const int64_t c = it / 9;
+            const int j = (int)(it - c * 9), jy = j % 3, jz = j / 3;
+            const int64_t site = s.c_site[c];
+            const float ge0 = s.gE[c];
+            const float cx = s.c_pos[3 * c], cy = s.c_pos[3 * c + 1], cz = s.c_pos[3 * c + 2];
+            const unsigned cs = s.c_cube_side[c];
             const float* B = s.B + c * 28 + 3 * j;
-            g0 = B[0] * ge; g1 = B[1] * ge; g2 = B[2] * ge;
+            const float b0 = B[0], b1 = B[1], b2 = B[2];
+            const int64_t p = site % a.n_points;
+            const float ge = (p >= s.p0 && p < s.p1) ? ge0 : 0.0f;    // sites of other batches contribute nothing
+            px = cx;
+            y = cy + (float)(jy - 1) * s.dy;
+            z = cz + (float)(jz - 1) * s.dz;
+            side3 = (cs >> (3 * j)) & 7u;
+            g0 = b0 * ge; g1 = b1 * ge; g2 = b2 * ge;
         }
         u64 yz[HP2];
         P::template first_layer_yz<0>(y, z, yz);
