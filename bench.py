@@ -656,9 +656,10 @@ def main():
                                          else ("nccl" if world > 1 else "none")),
                            "crossed_sites": int(pl.sites.n), "irregular_rows": int(pl.n_irr),
                            "setup_seconds": t_setup, "loss": loss_now,
-                           "tolerances": "CUDA vs oracle: flags exact, fractions 1e-5 of the cell measure (5e-5 vs the "
-                                         "reference-generated goldens: the reference's own f32/x64 spread is 3e-5), rows "
-                                         "1e-5, loss and gradient 1e-4 (tests/, normwise)"},
+                           "tolerances": "CUDA vs oracle: flags exact, fractions 1e-5 of the cell measure (1e-4 vs the "
+                                         "reference-generated goldens: the reference's own f32/x64 spread is 3e-5 on the "
+                                         "12-23-cell sets and 6.2e-5 on the 220-cell sets), rows 1e-5, loss and gradient 1e-4 "
+                                         "(tests/, normwise)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "roofline": roof, "cpu_baseline": cpu}
         if parity is not None:
