@@ -355,14 +355,8 @@ def main():
                     torch.cuda.synchronize()
 
         def _capture(self, staged):
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream())
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.stream(side):
-                with torch.cuda.graph(graph, stream=side):
-                    self._step(staged)
-            torch.cuda.current_stream().wait_stream(side)
-            return graph
+            from jax_dips_b200.trainer import capture_graph      # the trainer's own capture (bare capture_begin / _end)
+            return capture_graph(lambda: self._step(staged), dev)
 
         def _step(self, staged):
             if staged:
