@@ -381,6 +381,10 @@ typedef struct {
      * carries x - dx, y - dy, z - dz in its own direction, its last entry the + side of the last point), side4 / U4 / G4
      * [4][(nx+1)(ny+1)(nz+1)].  NULL = the 7-lattice path.  Needs p0, p1 multiples of ny*nz. */
     const float* xs4; const float* ys4; const float* zs4; const uint8_t* side4; float* U4; float* G4;
+    /* Optional: the crossed sites that belong to this batch (indices into the level's crossed-site list, ascending).  The
+     * cube kernels then walk these n_live sites instead of scanning all n_crossed and filtering (a 131072-point batch of a
+     * 128^3 grid owns 1/16 of them).  NULL = scan. */
+    const int32_t* c_live; int64_t n_live;
 } nbm_points_step_t;
 
 /* General path (any cell size, any contiguous batch): 7 network evaluations per point (the reference

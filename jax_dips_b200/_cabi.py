@@ -94,7 +94,8 @@ class PointsStep(C.Structure):
                 ("xs7", c_fp), ("ys7", c_fp), ("zs7", c_fp), ("U7", c_fp), ("G7", c_fp),
                 ("coef26", c_fp), ("pc_params", c_fp), ("Pc", c_fp), ("pc_d1", C.c_int), ("pc_d2", C.c_int),
                 ("pc_scale", c_f), ("n_pc_rows", C.c_int),
-                ("xs4", c_fp), ("ys4", c_fp), ("zs4", c_fp), ("side4", c_fp), ("U4", c_fp), ("G4", c_fp)]
+                ("xs4", c_fp), ("ys4", c_fp), ("zs4", c_fp), ("side4", c_fp), ("U4", c_fp), ("G4", c_fp),
+                ("c_live", c_fp), ("n_live", C.c_int64)]
 
 
 class Optimizer(C.Structure):

@@ -3001,12 +3001,14 @@ __global__ void __launch_bounds__(kCubeFwdThreads) cube_fwd_kernel(PointsArgs a)
     const nbm_points_step_t& s = a.s;
     __shared__ float part[kCubeFwdThreads];
     constexpr int HP2 = NET::HPW / 2;
-    for (int64_t c0 = (int64_t)blockIdx.x * 32; c0 < s.n_crossed; c0 += (int64_t)gridDim.x * 32) {
+    const int64_t n_sites = s.c_live ? s.n_live : s.n_crossed;     // the batch's own sites, or all of them (filtered)
+    for (int64_t c0 = (int64_t)blockIdx.x * 32; c0 < n_sites; c0 += (int64_t)gridDim.x * 32) {
         const int sl = threadIdx.x / 9, j = threadIdx.x - sl * 9;
-        const int64_t c = c0 + sl;
+        int64_t c = c0 + sl;
         float v = 0.0f;
-        bool live = c < s.n_crossed;
+        bool live = c < n_sites;
         if (live) {
+            if (s.c_live) c = s.c_live[c];
             const int64_t p = s.c_site[c] % a.n_points;
             live = p >= s.p0 && p < s.p1;
         }
@@ -3063,7 +3065,7 @@ __global__ void __launch_bounds__(kGradThreads, 1) cube_grad_kernel(PointsArgs a
     for (int i = 0; i < M::NP; ++i) accm[i] = 0.0f;
     const bool par = (threadIdx.x & 1) != 0;
     // equal contiguous ranges of the (site, j) items per CTA; every thread of the CTA runs the same number of rounds
-    const int64_t total = s.n_crossed * 9;
+    const int64_t total = (s.c_live ? s.n_live : s.n_crossed) * 9;
     const int64_t lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
     for (int64_t base = lo; base < hi; base += kGradThreads) {
         const int64_t it = base + threadIdx.x;
@@ -3071,8 +3073,9 @@ __global__ void __launch_bounds__(kGradThreads, 1) cube_grad_kernel(PointsArgs a
         unsigned side3 = 0u;
         if (it < hi) {
             // every load of the item is issued before any of them is used: one memory round trip per round, not four
-            const int64_t c = it / 9;
-            const int j = (int)(it - c * 9), jy = j % 3, jz = j / 3;
+            const int64_t ci = it / 9;
+            const int j = (int)(it - ci * 9), jy = j % 3, jz = j / 3;
+            const int64_t c = s.c_live ? (int64_t)s.c_live[ci] : ci;
             const int64_t site = s.c_site[c];
             const float ge0 = s.gE[c];
             const float cx = s.c_pos[3 * c], cy = s.c_pos[3 * c + 1], cz = s.c_pos[3 * c + 2];
@@ -3184,7 +3187,8 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     static const int rows_per_sm = getenv("NBM_ROWS_CTAS") ? atoi(getenv("NBM_ROWS_CTAS")) : 6;
     const int gridR = (int)min((int64_t)sms * rows_per_sm, (nb + kThreads - 1) / kThreads);
     int gridE = 0;
-    if (s.n_crossed > 0) gridE = (int)min((int64_t)sms, (s.n_crossed * 32 + kThreads - 1) / kThreads);
+    const int64_t n_sites = s.c_live ? s.n_live : s.n_crossed;      // crossed sites the cube kernels walk
+    if (n_sites > 0) gridE = (int)min((int64_t)sms, (n_sites * 32 + kThreads - 1) / kThreads);
     const bool pc = s.coef26 != nullptr;
     const int n_pc = pc ? PrecondNet<8, 4>::NP : 0;
     const int stride = NET::NP + n_pc + 1;
@@ -3198,9 +3202,9 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     // preconditioner rows every kernel writes only its own columns, so start from zero
     if (pc) cudaMemsetAsync(s.partials, 0, sizeof(float) * (size_t)rows_needed * stride, st);
     static const bool cube_kernels = !(getenv("NBM_CUBE_KERNELS") && getenv("NBM_CUBE_KERNELS")[0] == '0');
-    if (s.n_crossed > 0 && cube_kernels)
-        cube_fwd_kernel<NET><<<(unsigned)min((int64_t)sms * 8, (s.n_crossed + 31) / 32), kCubeFwdThreads, 0, st>>>(a);
-    else if (s.n_crossed > 0)
+    if (n_sites > 0 && cube_kernels)
+        cube_fwd_kernel<NET><<<(unsigned)min((int64_t)sms * 8, (n_sites + 31) / 32), kCubeFwdThreads, 0, st>>>(a);
+    else if (s.n_crossed > 0 && !cube_kernels)
         points_extrap_kernel<NET><<<(unsigned)min((int64_t)sms * 4, (s.n_crossed * 32 + kThreads - 1) / kThreads),
                                     kThreads, 0, st>>>(a);
     fwd_nodes_kernel<NET, true><<<gridF, kThreads, 0, st>>>(v, T);

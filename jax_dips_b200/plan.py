@@ -15,6 +15,7 @@ import ctypes as C
 import os
 from typing import Callable, Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import _cabi as cabi
@@ -940,6 +941,15 @@ class PointsPlan:
         if self.shared4:
             s.xs4, s.ys4, s.zs4 = cabi.ptr(level.xs4), cabi.ptr(level.ys4), cabi.ptr(level.zs4)
             s.side4, s.U4, s.G4 = cabi.ptr(level.side4), cabi.ptr(level.U4), cabi.ptr(level.G4)
+        # the crossed sites of THIS batch (the cube kernels walk them instead of scanning the level's whole list)
+        self.c_live = None
+        if cs.n > 0 and (self.p0 > 0 or self.p1 < level.n_points):
+            if getattr(level, "_site_point_host", None) is None:       # one device read per level, shared by its batches
+                level._site_point_host = (cs.idx[:cs.n] % level.n_points).cpu().numpy()
+            pts = level._site_point_host
+            live = np.nonzero((pts >= self.p0) & (pts < self.p1))[0].astype(np.int32)
+            self.c_live = torch.from_numpy(live).to(level.device)
+            s.c_live, s.n_live = cabi.ptr(self.c_live), int(live.size)
         if level.precond is not None:
             s.coef26, s.Pc = cabi.ptr(level.coef26), cabi.ptr(level.Pc)
             s.pc_d1, s.pc_d2, s.pc_scale = level.precond.widths[0], level.precond.widths[1], level.precond.scale
