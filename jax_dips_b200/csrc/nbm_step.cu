@@ -2258,12 +2258,17 @@ __global__ void __launch_bounds__(kThreads) precond_fwd_kernel(const float* __re
 
 // K4a: deterministic sum of the per-CTA partial rows: one warp per column, lane l adds rows l, l + 32, ... in order,
 // then a fixed shuffle tree (the row count and therefore the summation order depend only on the launch geometry)
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int rows, int np1, float* __restrict__ out) {
+// (`extra`: n_extra more addends of the LAST column - the per-CTA loss sums of the general path's rows kernel, kept as one
+// compact strip instead of one mostly-zero partial row each)
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int rows, int np1, float* __restrict__ out,
+                                       const float* __restrict__ extra = nullptr, int n_extra = 0) {
     const int lane = threadIdx.x & 31;
     const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (i >= np1) return;
     float v = 0.0f;
     for (int r = lane; r < rows; r += 32) v += partials[(size_t)r * np1 + i];
+    if (i == np1 - 1)
+        for (int r = lane; r < n_extra; r += 32) v += extra[r];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) out[i] = v;
@@ -2862,7 +2867,8 @@ __global__ void __launch_bounds__(kThreads) points_extrap_kernel(PointsArgs a) {
 // kernel cleared it; two addends: the order cannot change the sum)
 template <bool S4>
 __global__ void __launch_bounds__(kThreads) points_rows_kernel(PointsArgs a, const float* __restrict__ U7,
-                                                               float* __restrict__ G7, int row0, int np1) {
+                                                               float* __restrict__ G7, int row0, int np1,
+                                                               float* __restrict__ loss_strip) {
     const nbm_points_step_t& s = a.s;
     const int64_t N = a.n_points;
     const int64_t sy4 = s.nz + 1, sx4 = (int64_t)(s.ny + 1) * sy4, ne4 = (int64_t)(s.nx + 1) * sx4;
@@ -2954,6 +2960,14 @@ __global__ void __launch_bounds__(kThreads) points_rows_kernel(PointsArgs a, con
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
+    if (loss_strip) {   // one float per CTA; the reduction kernel adds the strip to the loss column
+        if (threadIdx.x == 0) {
+            float t = 0.0f;
+            for (int wv = 0; wv < kThreads / 32; ++wv) t += red[wv];
+            loss_strip[blockIdx.x] = t;
+        }
+        return;
+    }
     float* row = s.partials + (size_t)(row0 + blockIdx.x) * np1;
     for (int i = threadIdx.x; i < np1 - 1; i += kThreads) row[i] = 0.0f;
     if (threadIdx.x == 0) {
@@ -3193,7 +3207,13 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     const int n_pc = pc ? PrecondNet<8, 4>::NP : 0;
     const int stride = NET::NP + n_pc + 1;
     const int gridP = pc ? min(s.n_pc_rows, 3 * sms) : 0;
-    const int rows_needed = gridG + gridR + gridE + gridP;
+    // partial rows: [gridG gradient rows][gridR loss rows][gridE cube rows][gridP preconditioner rows]; without a
+    // preconditioner the rows kernel's per-CTA loss sums are ONE compact strip of gridR floats behind the cube rows
+    // instead of gridR mostly-zero rows (the reduction then reads 296 rows instead of up to 1184)
+    const bool strip = !pc;
+    const int rowsR = strip ? 0 : gridR, strip_rows = strip ? (gridR + stride - 1) / stride : 0;
+    const int rows_needed = gridG + rowsR + gridE + gridP + strip_rows;
+    float* loss_strip = strip ? s.partials + (size_t)(gridG + gridE) * stride : nullptr;
     if (rows_needed > s.n_partial_rows) {
         set_error("partials buffer has %d rows, %d needed", s.n_partial_rows, rows_needed);
         return NBM_ERR_WORKSPACE;
@@ -3211,12 +3231,12 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
     if (pc)
         precond_fwd_kernel<8, 4><<<(unsigned)min((int64_t)sms * 8, (nb + kThreads - 1) / kThreads), kThreads, 0, st>>>(
             s.coef26 + s.p0, a.n_points, nb, s.pc_params, s.pc_scale, s.Pc + s.p0);
-    if (s4) points_rows_kernel<true><<<gridR, kThreads, 0, st>>>(a, s.U4, s.G4, gridG, stride);
-    else points_rows_kernel<false><<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, gridG, stride);
+    if (s4) points_rows_kernel<true><<<gridR, kThreads, 0, st>>>(a, s.U4, s.G4, gridG, stride, loss_strip);
+    else points_rows_kernel<false><<<gridR, kThreads, 0, st>>>(a, s.U7, s.G7, gridG, stride, loss_strip);
     if (pc)   // loss + d loss/d theta_P from the raw residuals kept in `rows`
         precond_kernel<8, 4><<<gridP, kThreads, 0, st>>>(s.coef26 + s.p0, a.n_points, s.rows + s.p0, nullptr, nb, s.pc_params,
                                                          s.pc_scale, s.inv_n_points,
-                                                         s.partials + (size_t)(gridG + gridR + gridE) * stride, stride,
+                                                         s.partials + (size_t)(gridG + rowsR + gridE) * stride, stride,
                                                          NET::NP, NET::NP + n_pc);
     v.row0 = 0; v.row_stride = pc ? stride : 0; v.loss_col = NET::NP + n_pc;
     {
@@ -3233,11 +3253,12 @@ static int launch_points(const nbm_points_step_t& s, cudaStream_t st) {
             if (e != cudaSuccess) return cuda_check(e, "cube_grad attribute");
             configured |= 1ull << (dev & 63);
         }
-        cube_grad_kernel<NET><<<gridE, kGradThreads, bytes, st>>>(a, gridG + gridR, stride);
+        cube_grad_kernel<NET><<<gridE, kGradThreads, bytes, st>>>(a, gridG + rowsR, stride);
     } else if (gridE > 0) {
-        points_extrap_bwd_kernel<NET><<<gridE, kThreads, 0, st>>>(a, gridG + gridR, stride);
+        points_extrap_bwd_kernel<NET><<<gridE, kThreads, 0, st>>>(a, gridG + rowsR, stride);
     }
-    reduce_partials_kernel<<<(stride * 32 + 127) / 128, 128, 0, st>>>(s.partials, rows_needed, stride, s.loss_grad);
+    reduce_partials_kernel<<<(stride * 32 + 127) / 128, 128, 0, st>>>(s.partials, gridG + rowsR + gridE + gridP, stride, s.loss_grad,
+                                                                      loss_strip, strip ? gridR : 0);
     return cuda_check(cudaGetLastError(), "points step launch");
 }
 
