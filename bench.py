@@ -643,7 +643,7 @@ def main():
                            "adjoint": ("fused into the gradient kernel (TMA ring)" if pl.fused else
                                        ("residual rows + adjoint stencil in one kernel fed by 3-D TMA boxes (T never leaves the SM)"
                                         if pl.stencil_tma_active else "separate stencil pass")),
-                           "lists": ("side stream beside the TMA stencil, merged into G by one kernel" if pl.overlap_lists
+                           "lists": ("side stream beside the dense stencil kernel(s), merged into G by one kernel" if pl.overlap_lists
                                      else "in line after the dense stencil"),
                            "cuda_graph": used_graph,
                            "allreduce": ("peer-memory kernel fused with the partial reduction" if comm is not None
