@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(kThreads, 3) fwd_nodes_kernel(NodeView v, Task
 
 // A2: E[c] = sum_q B[c][q] U[node_c + off_q] + B[c][27]   (discretization.py:464-513); clears gE
 // (thread per crossed site; a warp-per-site variant with a shuffle reduction measured 14.9 us against 8.4 us)
-__global__ void extrap_kernel(nbm_shared_step_t s) {
+__global__ void __launch_bounds__(128) extrap_kernel(nbm_shared_step_t s) {
     pdl_trigger();
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= s.n_crossed) return;
@@ -799,12 +799,19 @@ __global__ void extrap_kernel(nbm_shared_step_t s) {
     const float* B = s.B_soa ? s.B_soa + c : s.B + c * 28;
     const int64_t bq = s.B_soa ? s.n_crossed : 1;
     int64_t sx = (int64_t)s.ey * s.ez, sy = s.ez;
-    float acc = B[27 * bq];
+    // all 55 loads are issued before the first use (register arrays): the kernel sits on the step's critical path on small
+    // lattices, where its cost is memory round trips, not throughput
+    float w[28], u[27];
+#pragma unroll
+    for (int q = 0; q < 28; ++q) w[q] = B[q * bq];
 #pragma unroll
     for (int q = 0; q < 27; ++q) {
         int a = q % 3 - 1, b = (q / 3) % 3 - 1, cc = q / 9 - 1;
-        acc = fmaf(B[q * bq], s.U[e + a * sx + b * sy + cc], acc);
+        u[q] = s.U[e + a * sx + b * sy + cc];
     }
+    float acc = w[27];
+#pragma unroll
+    for (int q = 0; q < 27; ++q) acc = fmaf(w[q], u[q], acc);
     s.E[c] = acc;
     s.gE[c] = 0.0f;
 }
