@@ -1260,15 +1260,19 @@ __global__ void irregular_fb_kernel(nbm_shared_step_t s) {
         }
         u[k] = s.U[e + off[k]];
     }
+    float Ek[7];          // (the far-side values are fetched together, before the accumulation chain needs the first)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) Ek[k] = c[k] >= 0 ? s.E[c[k]] : 0.0f;
+    const float rhs_q = s.irr_rhs[q];
     // same operation order as irregular_fwd_kernel
     float r = 0.0f;
 #pragma unroll
     for (int k = 0; k < 7; ++k)
-        if (c[k] >= 0) r = fmaf(wE[k], s.E[c[k]], r);
+        if (c[k] >= 0) r = fmaf(wE[k], Ek[k], r);
     const uint8_t nlr = s.irr_nl[q];
     float Ec = 0.0f, nlw = 0.0f;
     if (nlr) {
-        Ec = s.E[c[0]];
+        Ec = Ek[0];
         nlw = s.irr_nlw[q];
         r = fmaf(nlw, nlr == 1 ? nl_apply(s.nonlinear_m, s.nl_coef_m, Ec) : nl_apply(s.nonlinear_p, s.nl_coef_p, Ec), r);
     }
@@ -1282,7 +1286,7 @@ __global__ void irregular_fb_kernel(nbm_shared_step_t s) {
         r = fmaf(nla, nl_apply(s.nonlinear_m, s.nl_coef_m, u[0]), r);
         r = fmaf(nlb, nl_apply(s.nonlinear_p, s.nl_coef_p, u[0]), r);
     }
-    r -= s.irr_rhs[q];
+    r -= rhs_q;
     s.Rq[q] = r;
     // adjoint (irregular_bwd_kernel with nl_center = true)
     if (s.nl)
